@@ -1,0 +1,207 @@
+/*
+ * qmlb200.h - C ABI of the B200 (sm_100a) backend for the qml-essentials
+ * circuit-execution hot path.
+ *
+ * The reference (cirKITers/qml-essentials, pure Python on JAX) has no FFI; its
+ * de-facto backend seam is `Script.execute` (qml_essentials/script.py:137-147),
+ * which traces the circuit under `jax.vmap` (script.py:302-329) and runs the
+ * einsum kernels of qml_essentials/simulation.py.  This library replaces what
+ * sits below that seam:
+ *
+ *   qmlb_program_create   <- script.py:272-329 `_build_plan` (trace + vmap + jit):
+ *                            the host compiler hands over a flat program instead
+ *   qmlb_run              <- script.py:358-397 `_dispatch` -> compiled(*args), i.e.
+ *                            simulation.py:131-201 `simulate_and_measure`:
+ *                            simulate_pure (:65-104), simulate_mixed (:107-128,
+ *                            operations.py:485-512,1551-1578), measure_state
+ *                            (:204-271), measure_density (:274-317)
+ *   qmlb_sample           <- simulation.py:320-377 `sample_shots` (the integer
+ *                            bookkeeping; the uniform stream is an input)
+ *   qmlb_workspace_bytes  <- memory.py:54-139 `estimate_peak_bytes`
+ *   qmlb_purity / qmlb_overlap_fidelity
+ *                         <- entanglement.py:86-103 (Meyer-Wallach purities) and
+ *                            expressibility.py:48-66 (pair fidelities), reduced on
+ *                            device so only O(B) numbers leave the GPU
+ *
+ * Conventions.  One state index has `n_bits` bits.  Statevector programs:
+ * n_bits = n_qubits, wire q is bit n_qubits-1-q (wire 0 = MSB, simulation.py:100).
+ * Density programs: n_bits = 2*n_qubits, rho[i][j] lives at index i*2^n + j, so
+ * ket wire q is bit 2n-1-q and bra wire q is bit n-1-q (operations.py:505-510).
+ * The state starts as |0..0> (index 0 = 1).  A k-bit operation lists its bits
+ * most-significant first: local value v = sum_j bit(bits[j]) << (k-1-j), and a
+ * matrix M acts as new[v] = sum_u M[v][u] old[u] (operations.py:38-50).
+ *
+ * Ownership.  The caller owns every device buffer (arguments, output,
+ * workspace); the library keeps no pointer past a call.  `qmlb_program` is an
+ * opaque handle with explicit create/destroy.  All functions return QMLB_OK or
+ * a negative code; `qmlb_last_error()` is a thread-local message.  Nothing
+ * aborts.  All launches go to the given stream; no function synchronises
+ * except qmlb_program_create/destroy and qmlb_fma_peak.
+ */
+#ifndef QMLB200_H
+#define QMLB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define QMLB_VERSION 100
+
+#define QMLB_OK 0
+#define QMLB_ERR_INVALID (-1)     /* malformed program / arguments            */
+#define QMLB_ERR_UNSUPPORTED (-2) /* valid but not implemented by the kernels */
+#define QMLB_ERR_CUDA (-3)        /* CUDA runtime error (message has details) */
+#define QMLB_ERR_WORKSPACE (-4)   /* workspace too small                      */
+
+/* precision of the evolved state */
+#define QMLB_C64 0
+#define QMLB_C128 1
+
+/* operation kinds */
+#define QMLB_OP_MAT 0   /* dense 2^k x 2^k matrix from `src`                       */
+#define QMLB_OP_CTRL1 1 /* bits = {control, target}: 2x2 `src` on target if control */
+#define QMLB_OP_PERM 2  /* new[v] = old[perm[v]], perm = consts[aux .. aux+2^k)      */
+#define QMLB_OP_DIAG 3  /* new[v] = d[v] * old[v], d from `src` (2^k entries)        */
+
+/* matrix sources */
+#define QMLB_SRC_CONST 0  /* consts[a0]: 4^k complex (flags&2: 2^k complex diagonal)  */
+#define QMLB_SRC_TRIG 1   /* C0 + cos(kappa*t) A + sin(kappa*t) B; a0,a1,a2; angle    */
+#define QMLB_SRC_CHAIN 2  /* 2x2 product of sources items[a0 .. a0+a1), first acts 1st */
+#define QMLB_SRC_DIAGPH 3 /* d[v] = exp(-i * marks[v] * t), marks = consts[a0] (real) */
+#define QMLB_SRC_TABLE 4  /* per-element matrix: argument a0, complex offset a1,
+                             flags&1 = conjugate                                      */
+#define QMLB_SRC_SUPER 5  /* 4x4 superoperator on (ket bit, bra bit): product over
+                             items[a0 .. a0+a1) of either a 2x2 source U (-> U (x)
+                             conj U) or a constant 4x4 (k = 2)                        */
+
+/* result types (script.py:151-159) */
+#define QMLB_OUT_STATE 0   /* (B, 2^n) complex                       */
+#define QMLB_OUT_PROBS 1   /* (B, 2^n) real                          */
+#define QMLB_OUT_EXPVAL 2  /* (B, n_obs) real                        */
+#define QMLB_OUT_DENSITY 3 /* (B, 2^n, 2^n) complex                  */
+
+/* observables */
+#define QMLB_OBS_ZSTRING 0 /* product of Z on the bits of zmask (n-bit index) */
+#define QMLB_OBS_DIAG 1    /* diagonal: obs_consts[a0] holds 2^k complex      */
+#define QMLB_OBS_DENSE 2   /* dense:    obs_consts[a0] holds 4^k complex      */
+
+#define QMLB_MAX_OP_BITS 8
+#define QMLB_MAX_ARGS 8
+
+typedef struct {
+  int32_t kind, k, src, aux;
+  int32_t bits[QMLB_MAX_OP_BITS];
+} qmlb_op;
+
+typedef struct {
+  int32_t kind, k, a0, a1, a2, angle, flags, pad;
+  double kappa;
+} qmlb_source;
+
+/* angle = c0 + sum over terms[first .. first+n) of coeff * arg[arg][row][offset] */
+typedef struct {
+  int32_t first, n;
+  double c0;
+} qmlb_angle;
+
+typedef struct {
+  int32_t arg, offset;
+  double coeff;
+} qmlb_term;
+
+typedef struct {
+  int32_t kind, k, a0, pad;
+  int64_t zmask;
+  int32_t bits[QMLB_MAX_OP_BITS]; /* positions in the n-qubit index, MSB first */
+} qmlb_obs;
+
+/* Batched argument: float64 device matrix; element b (global batch index) reads
+ * row ((b / div) % mod).  ptr may be NULL for unused slots. */
+typedef struct {
+  const double* ptr;
+  int64_t stride; /* doubles per row */
+  int64_t div, mod;
+} qmlb_arg;
+
+/* Host-side description of a program; everything is copied by create. */
+typedef struct {
+  int32_t n_qubits, n_bits, density, dtype, out_type, reserved;
+  const qmlb_op* ops;
+  int32_t n_ops;
+  const qmlb_source* sources;
+  int32_t n_sources;
+  const int32_t* items;
+  int32_t n_items;
+  const qmlb_angle* angles;
+  int32_t n_angles;
+  const qmlb_term* terms;
+  int32_t n_terms;
+  const double* consts; /* complex entries interleaved (re, im) */
+  int64_t n_consts;
+  const qmlb_obs* obs;
+  int32_t n_obs;
+  const double* obs_consts;
+  int64_t n_obs_consts;
+} qmlb_program_desc;
+
+typedef struct qmlb_program qmlb_program;
+
+int qmlb_version(void);
+/* Number of CUDA kernels this library has launched in this process so far. */
+unsigned long long qmlb_launch_count(void);
+const char* qmlb_last_error(void);
+
+/* Validates, schedules and uploads a program to the current CUDA device. */
+int qmlb_program_create(const qmlb_program_desc* desc, qmlb_program** out);
+int qmlb_program_destroy(qmlb_program* prog);
+
+/* strategy: 0 = register-resident (one thread per circuit), 1 = shared-memory
+ * resident (one warp / CTA per circuit), 2 = streamed tile passes over HBM.
+ * n_passes: state passes per run (strategy 2), n_device_ops: ops after fusion. */
+int qmlb_program_info(const qmlb_program* prog, int32_t* strategy, int32_t* n_passes,
+                      int32_t* n_device_ops);
+
+/* Bytes of scratch `qmlb_run` needs for `batch` elements (may be 0). */
+size_t qmlb_workspace_bytes(const qmlb_program* prog, int64_t batch);
+
+/* Evolves `batch` elements with global indices batch_offset .. batch_offset+batch-1
+ * (the offset only enters the argument row computation, so a chunk or a rank's
+ * shard can run against the full, unsliced arguments) and writes the result of
+ * the program's out_type to `out` (row-major (batch, ...), real or complex of the
+ * program precision).  `stream` is a cudaStream_t. */
+int qmlb_run(const qmlb_program* prog, const qmlb_arg* args, int32_t n_args, int64_t batch,
+             int64_t batch_offset, void* out, void* workspace, size_t workspace_bytes,
+             void* stream);
+
+/* Shot bookkeeping of simulation.py:352-357 for `batch` probability vectors of
+ * length 2^n_qubits (float64 when dtype == QMLB_C128, else float32):
+ *   p_cuml = cumsum(p) (sequential order);  r = p_cuml[last] * (1 - u);
+ *   index  = number of entries of p_cuml strictly below r, clamped to 2^n - 1;
+ *   counts[b][index] += 1          (int32, zeroed by the call)
+ * uniforms: (batch, shots) float64 in [0, 1). */
+int qmlb_sample(const void* probs, int dtype, const double* uniforms, int64_t batch,
+                int32_t n_qubits, int64_t shots, int32_t* counts, void* stream);
+
+/* Per-qubit purities Tr(rho_q^2) of the single-qubit reduced states of `batch`
+ * pure states (is_density = 0, (batch, 2^n)) or density matrices (is_density = 1):
+ * out[b][q], real of the given precision (entanglement.py:86-103). */
+int qmlb_purity(const void* states, int dtype, int is_density, int64_t batch,
+                int32_t n_qubits, void* out, void* stream);
+
+/* |<psi_b | psi_{b+half}>|^2 for b < half over (2*half, 2^n) pure states - the pair
+ * fidelity of expressibility.py:48-66 for pure states.  out: (half,) real. */
+int qmlb_overlap_fidelity(const void* states, int dtype, int64_t half, int32_t n_qubits,
+                          void* out, void* stream);
+
+/* Measurement aid: sustained FMA throughput of this GPU in the given real
+ * precision (TFLOP/s), used as the roofline denominator of the register-resident
+ * regime.  Blocks until done. */
+int qmlb_fma_peak(int dtype, double* tflops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QMLB200_H */

@@ -1,0 +1,665 @@
+// C ABI of the B200 backend: program validation / scheduling / upload and the
+// launch sequences.  See include/qmlb200.h.
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <type_traits>
+#include <vector>
+
+#include "qmlb_internal.h"
+#include "qmlb_measure.cuh"
+#include "qmlb_reg.cuh"
+
+using namespace qmlb;
+
+namespace qmlb {
+std::atomic<unsigned long long> g_launches{0};
+}
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+
+#define CUDA_TRY(expr)                                                              \
+  do {                                                                              \
+    cudaError_t e__ = (expr);                                                       \
+    if (e__ != cudaSuccess)                                                         \
+      return fail(QMLB_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e__)); \
+  } while (0)
+
+constexpr int THREADS = qmlb::TILE_THREADS;
+constexpr int SM_COUNT_FALLBACK = 148;
+
+int env_int(const char* name, int dflt) {
+  const char* v = std::getenv(name);
+  return v ? std::atoi(v) : dflt;
+}
+
+}  // namespace
+
+namespace {
+
+size_t cs_of(int dtype) { return dtype == QMLB_C128 ? 16 : 8; }
+size_t rs_of(int dtype) { return dtype == QMLB_C128 ? 8 : 4; }
+
+int validate(const qmlb_program_desc* d, qmlb_program* p) {
+  if (d->n_qubits < 1 || d->n_bits != (d->density ? 2 * d->n_qubits : d->n_qubits))
+    return fail(QMLB_ERR_INVALID, "n_bits does not match n_qubits/density");
+  if (d->n_bits > 40) return fail(QMLB_ERR_UNSUPPORTED, "more than 40 state bits");
+  if (d->dtype != QMLB_C64 && d->dtype != QMLB_C128)
+    return fail(QMLB_ERR_INVALID, "dtype must be QMLB_C64 or QMLB_C128");
+  if (d->out_type < 0 || d->out_type > 3) return fail(QMLB_ERR_INVALID, "bad out_type");
+  if (d->out_type == QMLB_OUT_STATE && d->density)
+    return fail(QMLB_ERR_INVALID,
+                "Measurement type 'state' is not defined for mixed (noisy) circuits");
+  for (int i = 0; i < d->n_sources; ++i) {
+    const qmlb_source& s = d->sources[i];
+    if (s.kind < 0 || s.kind > QMLB_SRC_SUPER || s.k < 1 || s.k > QMLB_MAX_OP_BITS)
+      return fail(QMLB_ERR_INVALID, "bad source record");
+    if ((s.kind == QMLB_SRC_TRIG || s.kind == QMLB_SRC_DIAGPH) &&
+        (s.angle < 0 || s.angle >= d->n_angles))
+      return fail(QMLB_ERR_INVALID, "source references a missing angle");
+    if (s.kind == QMLB_SRC_CHAIN || s.kind == QMLB_SRC_SUPER) {
+      if (s.a0 < 0 || s.a1 < 1 || s.a0 + s.a1 > d->n_items)
+        return fail(QMLB_ERR_INVALID, "chain items out of range");
+      for (int t = 0; t < s.a1; ++t) {
+        int id = d->items[s.a0 + t];
+        if (id < 0 || id >= d->n_sources) return fail(QMLB_ERR_INVALID, "bad chain item");
+        const qmlb_source& it = d->sources[id];
+        bool elem1 = it.k == 1 && (it.kind == QMLB_SRC_CONST || it.kind == QMLB_SRC_TRIG ||
+                                   it.kind == QMLB_SRC_TABLE);
+        if (s.kind == QMLB_SRC_CHAIN && !elem1)
+          return fail(QMLB_ERR_INVALID, "chain item must be an elementary 2x2 source");
+        if (s.kind == QMLB_SRC_SUPER && !elem1 &&
+            !(it.k == 1 && it.kind == QMLB_SRC_CHAIN) &&
+            !(it.k == 2 && it.kind == QMLB_SRC_CONST))
+          return fail(QMLB_ERR_INVALID, "superchain item must be a 2x2 source or const 4x4");
+      }
+    }
+    if (s.kind == QMLB_SRC_TABLE) {
+      if (s.a0 < 0 || s.a0 >= QMLB_MAX_ARGS) return fail(QMLB_ERR_INVALID, "bad table arg");
+      p->max_arg = std::max(p->max_arg, s.a0);
+    }
+  }
+  for (int i = 0; i < d->n_terms; ++i) {
+    if (d->terms[i].arg < 0 || d->terms[i].arg >= QMLB_MAX_ARGS)
+      return fail(QMLB_ERR_INVALID, "term references argument slot outside 0..7");
+    p->max_arg = std::max(p->max_arg, d->terms[i].arg);
+  }
+  for (int i = 0; i < d->n_angles; ++i)
+    if (d->angles[i].first < 0 || d->angles[i].first + d->angles[i].n > d->n_terms)
+      return fail(QMLB_ERR_INVALID, "angle terms out of range");
+  for (int i = 0; i < d->n_ops; ++i) {
+    const qmlb_op& o = d->ops[i];
+    if (o.kind < 0 || o.kind > QMLB_OP_DIAG || o.k < 1 || o.k > QMLB_MAX_OP_BITS)
+      return fail(QMLB_ERR_INVALID, "bad op record");
+    uint64_t seen = 0;
+    for (int j = 0; j < o.k; ++j) {
+      if (o.bits[j] < 0 || o.bits[j] >= d->n_bits)
+        return fail(QMLB_ERR_INVALID, "op bit outside the state");
+      if (seen >> o.bits[j] & 1) return fail(QMLB_ERR_INVALID, "op repeats a bit");
+      seen |= 1ull << o.bits[j];
+    }
+    if (o.kind != QMLB_OP_PERM && (o.src < 0 || o.src >= d->n_sources))
+      return fail(QMLB_ERR_INVALID, "op references a missing source");
+    if (o.kind == QMLB_OP_PERM && (o.aux < 0 || o.aux + (1 << o.k) > d->n_consts))
+      return fail(QMLB_ERR_INVALID, "permutation table out of range");
+    if ((o.kind == QMLB_OP_MAT || o.kind == QMLB_OP_PERM) && o.k > 4)
+      return fail(QMLB_ERR_UNSUPPORTED, "dense / permutation ops on more than 4 bits");
+    if (o.kind == QMLB_OP_CTRL1 && o.k != 2) return fail(QMLB_ERR_INVALID, "CTRL1 needs 2 bits");
+  }
+  for (int i = 0; i < d->n_obs; ++i) {
+    const qmlb_obs& o = d->obs[i];
+    if (o.kind < 0 || o.kind > QMLB_OBS_DENSE || o.k < 1 || o.k > QMLB_MAX_OP_BITS)
+      return fail(QMLB_ERR_INVALID, "bad observable record");
+    if (o.kind == QMLB_OBS_DENSE && o.k > 4)
+      return fail(QMLB_ERR_UNSUPPORTED, "dense observables on more than 4 qubits");
+    for (int j = 0; j < o.k; ++j)
+      if (o.bits[j] < 0 || o.bits[j] >= d->n_qubits)
+        return fail(QMLB_ERR_INVALID, "observable bit outside the register");
+  }
+  if (d->out_type == QMLB_OUT_EXPVAL && d->n_obs < 1)
+    return fail(QMLB_ERR_INVALID, "expval needs at least one observable");
+  return QMLB_OK;
+}
+
+int op_entries(const qmlb_program* p, const qmlb_op& o) {
+  if (o.kind == QMLB_OP_PERM) return 0;
+  const qmlb_source& s = p->sources[o.src];
+  return source_entries(s.kind, s.k, s.flags);
+}
+
+// split a pass' ops into windows whose matrices fit `matw` entries
+void make_windows(const qmlb_program* p, QmlbPassHost& ps, int matw) {
+  ps.matoff.assign(ps.ops.size(), 0);
+  ps.windows.clear();
+  int first = 0, used = 0;
+  for (size_t i = 0; i < ps.ops.size(); ++i) {
+    int e = op_entries(p, ps.ops[i]);
+    if (used + e > matw && (int)i > first) {
+      ps.windows.push_back(make_int2(first, (int)i - first));
+      first = (int)i;
+      used = 0;
+    }
+    ps.matoff[i] = used;
+    used += e;
+  }
+  if ((int)ps.ops.size() > first || ps.ops.empty())
+    ps.windows.push_back(make_int2(first, (int)ps.ops.size() - first));
+  ps.matw = matw;
+}
+
+// Greedy pass construction for streamed execution: every pass owns the `m_low`
+// least-significant bits (contiguous -> coalesced) plus up to kt - m_low others.
+void schedule_passes(qmlb_program* p, int kt, int m_low) {
+  const int N = p->n_bits;
+  std::vector<char> done(p->ops.size(), 0);
+  size_t remaining = p->ops.size();
+  bool first_pass = true;
+  while (remaining > 0 || first_pass) {
+    uint64_t S = (m_low >= 64) ? ~0ull : ((1ull << m_low) - 1);
+    uint64_t blocked = 0;
+    QmlbPassHost ps;
+    std::vector<size_t> picked;
+    for (size_t i = 0; i < p->ops.size(); ++i) {
+      if (done[i]) continue;
+      const qmlb_op& o = p->ops[i];
+      uint64_t bits = 0;
+      for (int j = 0; j < o.k; ++j) bits |= 1ull << o.bits[j];
+      if (bits & blocked) {
+        blocked |= bits;
+        continue;
+      }
+      if (o.kind == QMLB_OP_DIAG) {  // applied on global indices: needs no tile bits
+        picked.push_back(i);
+        continue;
+      }
+      uint64_t U = S | bits;
+      if (__builtin_popcountll(U) <= kt) {
+        S = U;
+        picked.push_back(i);
+      } else {
+        blocked |= bits;
+      }
+    }
+    // pad the tile to kt bits with the lowest unused bits (keeps tiles large)
+    for (int g = 0; g < N && __builtin_popcountll(S) < std::min(kt, N); ++g) S |= 1ull << g;
+    for (int g = 0; g < N; ++g)
+      if (S >> g & 1) ps.tile_bits.push_back(g);
+    std::vector<int> local(N, -1);
+    for (size_t j = 0; j < ps.tile_bits.size(); ++j) local[ps.tile_bits[j]] = (int)j;
+    for (size_t i : picked) {
+      qmlb_op o = p->ops[i];
+      if (o.kind != QMLB_OP_DIAG)
+        for (int j = 0; j < o.k; ++j) o.bits[j] = local[o.bits[j]];
+      ps.ops.push_back(o);
+      done[i] = 1;
+    }
+    remaining -= picked.size();
+    ps.flags = QMLB_PASS_STORE | (first_pass ? QMLB_PASS_INIT : 0);
+    p->passes.push_back(std::move(ps));
+    first_pass = false;
+    if (picked.empty() && remaining > 0) break;  // cannot happen (k <= 4 <= kt)
+  }
+}
+
+template <typename V>
+size_t place(size_t& off, const std::vector<V>& v) {
+  off = (off + 15) & ~size_t(15);
+  size_t at = off;
+  off += v.size() * sizeof(V);
+  return at;
+}
+
+int upload(qmlb_program* p) {
+  size_t off = 0;
+  size_t o_ops = place(off, p->ops), o_src = place(off, p->sources),
+         o_items = place(off, p->items), o_ang = place(off, p->angles),
+         o_terms = place(off, p->terms), o_consts = place(off, p->consts),
+         o_obs = place(off, p->obs), o_oc = place(off, p->obs_consts);
+  struct PO {
+    size_t ops, matoff, win;
+  };
+  std::vector<PO> po(p->passes.size());
+  for (size_t i = 0; i < p->passes.size(); ++i) {
+    po[i].ops = place(off, p->passes[i].ops);
+    po[i].matoff = place(off, p->passes[i].matoff);
+    po[i].win = place(off, p->passes[i].windows);
+  }
+  off = (off + 15) & ~size_t(15);
+  std::vector<unsigned char> host(off + 16, 0);
+  auto put = [&](size_t at, const void* src, size_t n) {
+    if (n) std::memcpy(host.data() + at, src, n);
+  };
+  put(o_ops, p->ops.data(), p->ops.size() * sizeof(qmlb_op));
+  put(o_src, p->sources.data(), p->sources.size() * sizeof(qmlb_source));
+  put(o_items, p->items.data(), p->items.size() * sizeof(int32_t));
+  put(o_ang, p->angles.data(), p->angles.size() * sizeof(qmlb_angle));
+  put(o_terms, p->terms.data(), p->terms.size() * sizeof(qmlb_term));
+  put(o_consts, p->consts.data(), p->consts.size() * sizeof(double));
+  put(o_obs, p->obs.data(), p->obs.size() * sizeof(qmlb_obs));
+  put(o_oc, p->obs_consts.data(), p->obs_consts.size() * sizeof(double));
+  for (size_t i = 0; i < p->passes.size(); ++i) {
+    put(po[i].ops, p->passes[i].ops.data(), p->passes[i].ops.size() * sizeof(qmlb_op));
+    put(po[i].matoff, p->passes[i].matoff.data(), p->passes[i].matoff.size() * 4);
+    put(po[i].win, p->passes[i].windows.data(), p->passes[i].windows.size() * sizeof(int2));
+  }
+  CUDA_TRY(cudaMalloc(&p->blob, host.size()));
+  CUDA_TRY(cudaMemcpy(p->blob, host.data(), host.size(), cudaMemcpyHostToDevice));
+  unsigned char* base = static_cast<unsigned char*>(p->blob);
+  DevProg& d = p->dev;
+  d.ops = reinterpret_cast<const qmlb_op*>(base + o_ops);
+  d.src = reinterpret_cast<const qmlb_source*>(base + o_src);
+  d.items = reinterpret_cast<const int32_t*>(base + o_items);
+  d.ang = reinterpret_cast<const qmlb_angle*>(base + o_ang);
+  d.terms = reinterpret_cast<const qmlb_term*>(base + o_terms);
+  d.consts = reinterpret_cast<const double*>(base + o_consts);
+  d.obs = reinterpret_cast<const qmlb_obs*>(base + o_obs);
+  d.obs_consts = reinterpret_cast<const double*>(base + o_oc);
+  d.n_ops = (int)p->ops.size();
+  d.n_obs = (int)p->obs.size();
+  d.n_bits = p->n_bits;
+  d.n_qubits = p->n_qubits;
+  d.density = p->density;
+  d.out_type = p->out_type;
+  for (size_t i = 0; i < p->passes.size(); ++i) {
+    QmlbPassHost& ps = p->passes[i];
+    PassDev& pd = ps.dev;
+    pd.ops = reinterpret_cast<const qmlb_op*>(base + po[i].ops);
+    pd.matoff = reinterpret_cast<const int32_t*>(base + po[i].matoff);
+    pd.windows = reinterpret_cast<const int2*>(base + po[i].win);
+    pd.n_windows = (int)ps.windows.size();
+    pd.k_tile = (int)ps.tile_bits.size();
+    pd.n_bits = p->n_bits;
+    pd.flags = ps.flags;
+    pd.matw = ps.matw;
+    pd.identity_map = 1;
+    for (size_t j = 0; j < ps.tile_bits.size(); ++j) {
+      pd.tile_bits[j] = ps.tile_bits[j];
+      if (ps.tile_bits[j] != (int)j) pd.identity_map = 0;
+    }
+  }
+  return QMLB_OK;
+}
+
+bool all_zstring(const qmlb_program* p) {
+  for (const auto& o : p->obs)
+    if (o.kind != QMLB_OBS_ZSTRING) return false;
+  return true;
+}
+
+int plan(qmlb_program* p) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) == cudaSuccess) {
+    int sms = 0;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess &&
+        sms > 0)
+      p->sm_count = sms;
+  }
+  const size_t cs = cs_of(p->dtype);
+  const int N = p->n_bits;
+  const int force = env_int("QMLB_FORCE_STRATEGY", -1);
+
+  // ---- strategy 0: registers --------------------------------------------------
+  bool reg_ok = !p->density && N <= REG_MAX_BITS;
+  for (const auto& o : p->ops) reg_ok = reg_ok && reg_supports(o, p->consts.data(), N);
+  if ((reg_ok && force < 0) || (reg_ok && force == 0)) {
+    p->strategy = 0;
+    if (p->out_type == QMLB_OUT_STATE) {
+      p->direct_out = true;
+      p->reg_mode = 0;
+    } else if (p->out_type == QMLB_OUT_PROBS) {
+      p->direct_out = true;
+      p->reg_mode = 1;
+    } else if (p->out_type == QMLB_OUT_EXPVAL && all_zstring(p)) {
+      p->direct_out = true;
+      p->reg_mode = 2;
+    } else {
+      p->direct_out = false;
+      p->reg_mode = 0;
+    }
+    return QMLB_OK;
+  }
+
+  // ---- strategy 1: whole state in shared memory ---------------------------------
+  const int init_max = env_int("QMLB_SMEM_STATE_BITS", p->dtype == QMLB_C128 ? 13 : 14);
+  p->direct_out = (p->out_type == QMLB_OUT_STATE) ||
+                  (p->out_type == QMLB_OUT_DENSITY && p->density);
+  if ((N <= init_max && force != 2) || force == 1) {
+    if (N > QMLB_MAX_TILE_BITS) return fail(QMLB_ERR_UNSUPPORTED, "state too large for smem");
+    p->strategy = 1;
+    QmlbPassHost ps;
+    for (int g = 0; g < N; ++g) ps.tile_bits.push_back(g);
+    ps.ops = p->ops;
+    ps.flags = QMLB_PASS_INIT | QMLB_PASS_STORE;
+    p->warp_team = N <= 7;
+    p->teams = p->warp_team ? THREADS / 32 : 1;
+    const size_t tile_bytes = (size_t(1) << N) * cs;
+    // matrix buffer: whole circuit if it fits next to the state in <= 96 KB per CTA
+    int need = 0, biggest = 1;
+    for (const auto& o : ps.ops) {
+      need += op_entries(p, o);
+      biggest = std::max(biggest, op_entries(p, o));
+    }
+    size_t budget = 96 * 1024;
+    size_t per_team = budget / p->teams;
+    int cap = per_team > tile_bytes ? (int)((per_team - tile_bytes) / cs) : 0;
+    cap = std::max(cap, std::max(biggest, 256));
+    int matw = std::max(1, std::min(need, cap));
+    make_windows(p, ps, matw);
+    p->smem = p->teams * (tile_bytes + (size_t)matw * cs);
+    p->passes.push_back(std::move(ps));
+    return QMLB_OK;
+  }
+
+  // ---- strategy 2: streamed tile passes -------------------------------------------
+  p->strategy = 2;
+  int kt = env_int("QMLB_TILE_BITS", p->dtype == QMLB_C128 ? 12 : 13);
+  kt = std::min(kt, std::min(N, QMLB_MAX_TILE_BITS));
+  int m_low = std::min(env_int("QMLB_TILE_LOW_BITS", 5), kt);
+  schedule_passes(p, kt, m_low);
+  p->warp_team = false;
+  p->teams = 1;
+  const int matw_cap = env_int("QMLB_TILE_MATW", 1024);
+  size_t smem = 0;
+  for (auto& ps : p->passes) {
+    int need = 0, biggest = 1;
+    for (const auto& o : ps.ops) {
+      need += op_entries(p, o);
+      biggest = std::max(biggest, op_entries(p, o));
+    }
+    int matw = std::max(1, std::min(need, std::max(matw_cap, biggest)));
+    make_windows(p, ps, matw);
+    smem = std::max(smem, (size_t(1) << ps.tile_bits.size()) * cs + (size_t)matw * cs);
+  }
+  p->smem = smem;
+  return QMLB_OK;
+}
+
+int expval_chunks(const qmlb_program* p, int64_t batch) {
+  const int64_t dim = int64_t(1) << p->n_qubits;
+  if (p->out_type != QMLB_OUT_EXPVAL) return 1;
+  if (batch < (int64_t)p->sm_count * 4 && dim > 4096) {
+    int chunks = (int)std::min<int64_t>(dim / 4096,
+                                        ((int64_t)p->sm_count * 4 + batch - 1) / batch);
+    return std::max(chunks, 1);
+  }
+  return 1;
+}
+
+template <typename T>
+int launch_measure(const qmlb_program* p, const cx<T>* state, int64_t batch, void* out,
+                   unsigned char* scratch, cudaStream_t st) {
+  const int64_t dim = int64_t(1) << p->n_qubits;
+  if (p->out_type == QMLB_OUT_PROBS) {
+    int64_t total = batch * dim;
+    int grid = (int)std::min<int64_t>((total + 255) / 256, (int64_t)p->sm_count * 16);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    k_probs<T><<<std::max(grid, 1), 256, 0, st>>>(state, static_cast<T*>(out), batch,
+                                                 p->n_qubits, p->density);
+  } else if (p->out_type == QMLB_OUT_DENSITY) {
+    int64_t total = batch * dim * dim;
+    int grid = (int)std::min<int64_t>((total + 255) / 256, (int64_t)p->sm_count * 16);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    k_outer<T><<<std::max(grid, 1), 256, 0, st>>>(state, static_cast<cx<T>*>(out), batch,
+                                                 p->n_qubits);
+  } else if (p->out_type == QMLB_OUT_EXPVAL) {
+    const int chunks = expval_chunks(p, batch);
+    const int n_obs = (int)p->obs.size();
+    if (chunks == 1) {
+      g_launches.fetch_add(1, std::memory_order_relaxed);
+    k_expval<T><<<(unsigned)batch, 256, 0, st>>>(p->dev, state, static_cast<T*>(out),
+                                                  batch, 1);
+    } else {
+      T* partial = reinterpret_cast<T*>(scratch);
+      g_launches.fetch_add(1, std::memory_order_relaxed);
+    k_expval<T><<<(unsigned)(batch * chunks), 256, 0, st>>>(p->dev, state, partial, batch,
+                                                             chunks);
+      int64_t n = batch * n_obs;
+      g_launches.fetch_add(1, std::memory_order_relaxed);
+    k_sum_chunks<T><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(
+          partial, static_cast<T*>(out), n, chunks);
+    }
+  }
+  CUDA_TRY(cudaGetLastError());
+  return QMLB_OK;
+}
+
+template <typename T>
+int run_typed(const qmlb_program* p, const RunArgs& R, void* out, void* workspace,
+              size_t ws_bytes, cudaStream_t st) {
+  const size_t cs = cs_of(p->dtype);
+  const size_t state_bytes = p->direct_out ? 0 : (size_t)R.batch * (size_t(1) << p->n_bits) * cs;
+  size_t need = state_bytes;
+  const int chunks = expval_chunks(p, R.batch);
+  size_t part_off = (need + 255) & ~size_t(255);
+  if (!p->direct_out && chunks > 1)
+    need = part_off + (size_t)R.batch * p->obs.size() * chunks * rs_of(p->dtype);
+  if (need > ws_bytes) return fail(QMLB_ERR_WORKSPACE, "workspace too small");
+  cx<T>* state = p->direct_out ? static_cast<cx<T>*>(out) : static_cast<cx<T>*>(workspace);
+
+  if (p->strategy == 0) {
+    void* dst = p->direct_out ? out : workspace;
+    CUDA_TRY((std::is_same<T, double>::value ? launch_reg_f64 : launch_reg_f32)(p, R, dst, st));
+  } else {
+    for (const QmlbPassHost& ps : p->passes) {
+      const int kt = (int)ps.tile_bits.size();
+      const int64_t tiles = R.batch << (p->n_bits - kt);
+      const int64_t blocks_needed = (tiles + p->teams - 1) / p->teams;
+      const unsigned grid = (unsigned)std::max<int64_t>(
+          1, std::min<int64_t>(blocks_needed, (int64_t)p->sm_count * 8));
+      CUDA_TRY((std::is_same<T, double>::value ? launch_tile_f64 : launch_tile_f32)(
+          p, R, ps.dev, grid, state, st));
+    }
+  }
+  if (!p->direct_out)
+    return launch_measure<T>(p, state, R.batch, out,
+                             static_cast<unsigned char*>(workspace) + part_off, st);
+  return QMLB_OK;
+}
+
+int set_smem_attr(const qmlb_program* p) {
+  if (p->strategy == 0 || p->smem <= 48 * 1024) return QMLB_OK;
+  CUDA_TRY(p->dtype == QMLB_C128 ? tile_set_smem_f64(p->smem) : tile_set_smem_f32(p->smem));
+  return QMLB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int qmlb_version(void) { return QMLB_VERSION; }
+
+unsigned long long qmlb_launch_count(void) { return g_launches.load(); }
+
+const char* qmlb_last_error(void) { return g_err.c_str(); }
+
+int qmlb_program_create(const qmlb_program_desc* d, qmlb_program** out) {
+  if (!d || !out) return fail(QMLB_ERR_INVALID, "null argument");
+  *out = nullptr;
+  qmlb_program* p = new qmlb_program();
+  int rc = validate(d, p);
+  if (rc != QMLB_OK) {
+    delete p;
+    return rc;
+  }
+  p->n_qubits = d->n_qubits;
+  p->n_bits = d->n_bits;
+  p->density = d->density;
+  p->dtype = d->dtype;
+  p->out_type = d->out_type;
+  p->ops.assign(d->ops, d->ops + d->n_ops);
+  p->sources.assign(d->sources, d->sources + d->n_sources);
+  p->items.assign(d->items, d->items + d->n_items);
+  p->angles.assign(d->angles, d->angles + d->n_angles);
+  p->terms.assign(d->terms, d->terms + d->n_terms);
+  p->consts.assign(d->consts, d->consts + d->n_consts);
+  p->obs.assign(d->obs, d->obs + d->n_obs);
+  p->obs_consts.assign(d->obs_consts, d->obs_consts + d->n_obs_consts);
+  rc = plan(p);
+  if (rc == QMLB_OK) rc = upload(p);
+  if (rc == QMLB_OK) rc = set_smem_attr(p);
+  if (rc != QMLB_OK) {
+    if (p->blob) cudaFree(p->blob);
+    delete p;
+    return rc;
+  }
+  *out = p;
+  return QMLB_OK;
+}
+
+int qmlb_program_destroy(qmlb_program* p) {
+  if (!p) return QMLB_OK;
+  if (p->blob) cudaFree(p->blob);
+  delete p;
+  return QMLB_OK;
+}
+
+int qmlb_program_info(const qmlb_program* p, int32_t* strategy, int32_t* n_passes,
+                      int32_t* n_device_ops) {
+  if (!p) return fail(QMLB_ERR_INVALID, "null program");
+  if (strategy) *strategy = p->strategy;
+  if (n_passes) *n_passes = p->strategy == 0 ? 1 : (int32_t)p->passes.size();
+  if (n_device_ops) *n_device_ops = (int32_t)p->ops.size();
+  return QMLB_OK;
+}
+
+size_t qmlb_workspace_bytes(const qmlb_program* p, int64_t batch) {
+  if (!p || batch <= 0) return 0;
+  if (p->direct_out) return 0;
+  size_t need = (size_t)batch * (size_t(1) << p->n_bits) * cs_of(p->dtype);
+  const int chunks = expval_chunks(p, batch);
+  if (chunks > 1) {
+    need = (need + 255) & ~size_t(255);
+    need += (size_t)batch * p->obs.size() * chunks * rs_of(p->dtype);
+  }
+  return need;
+}
+
+int qmlb_run(const qmlb_program* p, const qmlb_arg* args, int32_t n_args, int64_t batch,
+             int64_t batch_offset, void* out, void* workspace, size_t workspace_bytes,
+             void* stream) {
+  if (!p || !out) return fail(QMLB_ERR_INVALID, "null program or output");
+  if (batch <= 0) return QMLB_OK;
+  if (n_args < 0 || n_args > QMLB_MAX_ARGS) return fail(QMLB_ERR_INVALID, "bad n_args");
+  if (p->max_arg >= n_args) return fail(QMLB_ERR_INVALID, "program needs more arguments");
+  RunArgs R;
+  std::memset(&R, 0, sizeof(R));
+  for (int i = 0; i < QMLB_MAX_ARGS; ++i) {
+    R.a[i].div = 1;
+    R.a[i].mod = 1;
+  }
+  for (int i = 0; i < n_args; ++i) {
+    R.a[i] = args[i];
+    if (R.a[i].div < 1 || R.a[i].mod < 1) return fail(QMLB_ERR_INVALID, "arg div/mod < 1");
+  }
+  for (const auto& t : p->terms)
+    if (!R.a[t.arg].ptr) return fail(QMLB_ERR_INVALID, "program reads a NULL argument");
+  R.batch = batch;
+  R.batch_offset = batch_offset;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (p->dtype == QMLB_C128) return run_typed<double>(p, R, out, workspace, workspace_bytes, st);
+  return run_typed<float>(p, R, out, workspace, workspace_bytes, st);
+}
+
+int qmlb_sample(const void* probs, int dtype, const double* uniforms, int64_t batch,
+                int32_t n_qubits, int64_t shots, int32_t* counts, void* stream) {
+  if (!probs || !uniforms || !counts) return fail(QMLB_ERR_INVALID, "null argument");
+  if (n_qubits < 1 || n_qubits > 14) return fail(QMLB_ERR_UNSUPPORTED, "shots need n <= 14");
+  if (batch <= 0) return QMLB_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const size_t dim = size_t(1) << n_qubits;
+  CUDA_TRY(cudaMemsetAsync(counts, 0, (size_t)batch * dim * sizeof(int32_t), st));
+  if (dtype == QMLB_C128) {
+    size_t smem = dim * sizeof(double);
+    if (smem > 48 * 1024)
+      CUDA_TRY(cudaFuncSetAttribute(k_sample<double>,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    k_sample<double><<<(unsigned)batch, 256, smem, st>>>(
+        static_cast<const double*>(probs), uniforms, n_qubits, shots, counts);
+  } else {
+    size_t smem = dim * sizeof(float);
+    if (smem > 48 * 1024)
+      CUDA_TRY(cudaFuncSetAttribute(k_sample<float>,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    k_sample<float><<<(unsigned)batch, 256, smem, st>>>(static_cast<const float*>(probs),
+                                                        uniforms, n_qubits, shots, counts);
+  }
+  CUDA_TRY(cudaGetLastError());
+  return QMLB_OK;
+}
+
+int qmlb_purity(const void* states, int dtype, int is_density, int64_t batch,
+                int32_t n_qubits, void* out, void* stream) {
+  if (!states || !out) return fail(QMLB_ERR_INVALID, "null argument");
+  if (batch <= 0) return QMLB_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  if (dtype == QMLB_C128)
+    k_purity<double><<<(unsigned)batch, 256, 0, st>>>(
+        static_cast<const cx<double>*>(states), is_density, n_qubits, static_cast<double*>(out));
+  else
+    k_purity<float><<<(unsigned)batch, 256, 0, st>>>(
+        static_cast<const cx<float>*>(states), is_density, n_qubits, static_cast<float*>(out));
+  CUDA_TRY(cudaGetLastError());
+  return QMLB_OK;
+}
+
+int qmlb_overlap_fidelity(const void* states, int dtype, int64_t half, int32_t n_qubits,
+                          void* out, void* stream) {
+  if (!states || !out) return fail(QMLB_ERR_INVALID, "null argument");
+  if (half <= 0) return QMLB_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  if (dtype == QMLB_C128)
+    k_overlap<double><<<(unsigned)half, 256, 0, st>>>(
+        static_cast<const cx<double>*>(states), half, n_qubits, static_cast<double*>(out));
+  else
+    k_overlap<float><<<(unsigned)half, 256, 0, st>>>(
+        static_cast<const cx<float>*>(states), half, n_qubits, static_cast<float*>(out));
+  CUDA_TRY(cudaGetLastError());
+  return QMLB_OK;
+}
+
+int qmlb_fma_peak(int dtype, double* tflops) {
+  if (!tflops) return fail(QMLB_ERR_INVALID, "null argument");
+  int dev = 0, sms = SM_COUNT_FALLBACK;
+  CUDA_TRY(cudaGetDevice(&dev));
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int grid = sms * 8, threads = 256, iters = 1 << 15;
+  void* buf = nullptr;
+  CUDA_TRY(cudaMalloc(&buf, (size_t)grid * threads * sizeof(double)));
+  cudaEvent_t e0, e1;
+  CUDA_TRY(cudaEventCreate(&e0));
+  CUDA_TRY(cudaEventCreate(&e1));
+  float best = 1e30f;
+  for (int rep = 0; rep < 4; ++rep) {
+    CUDA_TRY(cudaEventRecord(e0));
+    if (dtype == QMLB_C128)
+      k_fma_peak<double><<<grid, threads>>>(static_cast<double*>(buf), iters);
+    else
+      k_fma_peak<float><<<grid, threads>>>(static_cast<float*>(buf), iters);
+    CUDA_TRY(cudaEventRecord(e1));
+    CUDA_TRY(cudaEventSynchronize(e1));
+    float ms = 0;
+    CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+    if (rep > 0) best = std::min(best, ms);
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(buf);
+  const double flops = (double)grid * threads * (double)iters * 8.0 * 2.0;
+  *tflops = flops / (best * 1e-3) / 1e12;
+  return QMLB_OK;
+}
+
+}  // extern "C"

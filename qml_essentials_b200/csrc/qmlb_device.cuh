@@ -1,0 +1,254 @@
+// Device-side program view and matrix-source evaluation shared by all kernels.
+// sm_100a only.  See include/qmlb200.h for the program semantics.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/qmlb200.h"
+
+namespace qmlb {
+
+template <typename T>
+struct cx {
+  T x, y;
+};
+
+template <typename T>
+__host__ __device__ __forceinline__ cx<T> mk(T x, T y) {
+  cx<T> r;
+  r.x = x;
+  r.y = y;
+  return r;
+}
+template <typename T>
+__device__ __forceinline__ cx<T> cmul(cx<T> a, cx<T> b) {
+  return mk<T>(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+// acc += a * b
+template <typename T>
+__device__ __forceinline__ void cfma(cx<T>& acc, cx<T> a, cx<T> b) {
+  acc.x = fma(a.x, b.x, acc.x);
+  acc.x = fma(-a.y, b.y, acc.x);
+  acc.y = fma(a.x, b.y, acc.y);
+  acc.y = fma(a.y, b.x, acc.y);
+}
+template <typename T>
+__device__ __forceinline__ cx<T> cconj(cx<T> a) {
+  return mk<T>(a.x, -a.y);
+}
+template <typename T>
+__device__ __forceinline__ cx<T> cadd(cx<T> a, cx<T> b) {
+  return mk<T>(a.x + b.x, a.y + b.y);
+}
+
+__device__ __forceinline__ void sincos_t(double a, double* s, double* c) { sincos(a, s, c); }
+__device__ __forceinline__ void sincos_t(float a, float* s, float* c) { sincosf(a, s, c); }
+
+// Device copy of a program (all pointers are device pointers into one blob).
+struct DevProg {
+  const qmlb_op* ops;
+  const qmlb_source* src;
+  const int32_t* items;
+  const qmlb_angle* ang;
+  const qmlb_term* terms;
+  const double* consts;
+  const qmlb_obs* obs;
+  const double* obs_consts;
+  int32_t n_ops, n_obs, n_bits, n_qubits, density, out_type;
+};
+
+struct RunArgs {
+  qmlb_arg a[QMLB_MAX_ARGS];
+  int64_t batch;         // elements in this launch
+  int64_t batch_offset;  // global index of element 0
+};
+
+__device__ __forceinline__ const double* arg_row(const RunArgs& R, int arg, int64_t b) {
+  const qmlb_arg& a = R.a[arg];
+  int64_t row = (b / a.div) % a.mod;
+  return a.ptr + row * a.stride;
+}
+
+__device__ __forceinline__ double eval_angle(const DevProg& P, const RunArgs& R, int aid,
+                                             int64_t b) {
+  qmlb_angle a = P.ang[aid];
+  double th = a.c0;
+  for (int t = 0; t < a.n; ++t) {
+    qmlb_term tm = P.terms[a.first + t];
+    th = fma(tm.coeff, arg_row(R, tm.arg, b)[tm.offset], th);
+  }
+  return th;
+}
+
+template <typename T>
+__device__ __forceinline__ cx<T> ld_const(const double* consts, int off) {
+  const double2 v = reinterpret_cast<const double2*>(consts)[off];
+  return mk<T>((T)v.x, (T)v.y);
+}
+
+// 2x2 "elementary" source (CONST / TRIG / TABLE with k = 1) into registers.
+template <typename T>
+__device__ __forceinline__ void eval_elem2(const DevProg& P, const RunArgs& R,
+                                           const qmlb_source& s, int64_t b, cx<T> m[4]) {
+  if (s.kind == QMLB_SRC_CONST) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) m[i] = ld_const<T>(P.consts, s.a0 + i);
+  } else if (s.kind == QMLB_SRC_TRIG) {
+    T sn, cs;
+    sincos_t((T)(eval_angle(P, R, s.angle, b) * s.kappa), &sn, &cs);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      cx<T> c0 = ld_const<T>(P.consts, s.a0 + i);
+      cx<T> a = ld_const<T>(P.consts, s.a1 + i);
+      cx<T> bb = ld_const<T>(P.consts, s.a2 + i);
+      m[i] = mk<T>(c0.x + cs * a.x + sn * bb.x, c0.y + cs * a.y + sn * bb.y);
+    }
+  } else {  // QMLB_SRC_TABLE
+    const double2* row = reinterpret_cast<const double2*>(arg_row(R, s.a0, b)) + s.a1;
+    T sg = (s.flags & 1) ? (T)-1 : (T)1;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) m[i] = mk<T>((T)row[i].x, sg * (T)row[i].y);
+  }
+}
+
+// m = f * m for 2x2 (row-major)
+template <typename T>
+__device__ __forceinline__ void mul2_left(const cx<T> f[4], cx<T> m[4]) {
+  cx<T> r[4];
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      cx<T> acc = cmul(f[i * 2 + 0], m[0 * 2 + j]);
+      cfma(acc, f[i * 2 + 1], m[1 * 2 + j]);
+      r[i * 2 + j] = acc;
+    }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) m[i] = r[i];
+}
+
+// Any k = 1 source (elementary or CHAIN) into registers.
+template <typename T>
+__device__ __forceinline__ void eval_2x2(const DevProg& P, const RunArgs& R, int sid,
+                                         int64_t b, cx<T> m[4]) {
+  qmlb_source s = P.src[sid];
+  if (s.kind != QMLB_SRC_CHAIN) {
+    eval_elem2<T>(P, R, s, b, m);
+    return;
+  }
+  eval_elem2<T>(P, R, P.src[P.items[s.a0]], b, m);
+  for (int i = 1; i < s.a1; ++i) {
+    cx<T> f[4];
+    eval_elem2<T>(P, R, P.src[P.items[s.a0 + i]], b, f);
+    mul2_left<T>(f, m);
+  }
+}
+
+// Generic source into memory `out` (4^k entries row-major, or 2^k for diagonal
+// sources).  Executed by ONE thread per source; `out` may be shared or local.
+template <typename T>
+__device__ void eval_source_mem(const DevProg& P, const RunArgs& R, int sid, int64_t b,
+                                cx<T>* out) {
+  qmlb_source s = P.src[sid];
+  const int d = 1 << s.k;
+  switch (s.kind) {
+    case QMLB_SRC_CONST: {
+      int n = (s.flags & 2) ? d : d * d;
+      for (int i = 0; i < n; ++i) out[i] = ld_const<T>(P.consts, s.a0 + i);
+      break;
+    }
+    case QMLB_SRC_TRIG: {
+      T sn, cs;
+      sincos_t((T)(eval_angle(P, R, s.angle, b) * s.kappa), &sn, &cs);
+      for (int i = 0; i < d * d; ++i) {
+        cx<T> c0 = ld_const<T>(P.consts, s.a0 + i);
+        cx<T> a = ld_const<T>(P.consts, s.a1 + i);
+        cx<T> bb = ld_const<T>(P.consts, s.a2 + i);
+        out[i] = mk<T>(c0.x + cs * a.x + sn * bb.x, c0.y + cs * a.y + sn * bb.y);
+      }
+      break;
+    }
+    case QMLB_SRC_CHAIN: {
+      cx<T> m[4];
+      eval_2x2<T>(P, R, sid, b, m);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) out[i] = m[i];
+      break;
+    }
+    case QMLB_SRC_DIAGPH: {
+      double th = eval_angle(P, R, s.angle, b);
+      for (int i = 0; i < d; ++i) {
+        T sn, cs;
+        sincos_t((T)(-P.consts[s.a0 + i] * th), &sn, &cs);
+        out[i] = mk<T>(cs, sn);
+      }
+      break;
+    }
+    case QMLB_SRC_TABLE: {
+      const double2* row = reinterpret_cast<const double2*>(arg_row(R, s.a0, b)) + s.a1;
+      T sg = (s.flags & 1) ? (T)-1 : (T)1;
+      for (int i = 0; i < d * d; ++i) out[i] = mk<T>((T)row[i].x, sg * (T)row[i].y);
+      break;
+    }
+    case QMLB_SRC_SUPER: {
+      // S = prod_i item_i, item = U (x) conj(U) for a 2x2 source, or a constant 4x4
+      cx<T> S[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) S[i] = mk<T>((i % 5 == 0) ? (T)1 : (T)0, (T)0);
+      for (int it = 0; it < s.a1; ++it) {
+        int id = P.items[s.a0 + it];
+        cx<T> F[16];
+        if (P.src[id].k == 2) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) F[i] = ld_const<T>(P.consts, P.src[id].a0 + i);
+        } else {
+          cx<T> u[4];
+          eval_2x2<T>(P, R, id, b, u);
+          // (U (x) conj U)[(a,b),(c,d)] = U[a][c] * conj(U[b][d])
+#pragma unroll
+          for (int a = 0; a < 2; ++a)
+#pragma unroll
+            for (int bb = 0; bb < 2; ++bb)
+#pragma unroll
+              for (int c = 0; c < 2; ++c)
+#pragma unroll
+                for (int dd = 0; dd < 2; ++dd)
+                  F[(a * 2 + bb) * 4 + (c * 2 + dd)] =
+                      cmul(u[a * 2 + c], cconj(u[bb * 2 + dd]));
+        }
+        cx<T> N[16];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            cx<T> acc = mk<T>((T)0, (T)0);
+#pragma unroll
+            for (int l = 0; l < 4; ++l) cfma(acc, F[i * 4 + l], S[l * 4 + j]);
+            N[i * 4 + j] = acc;
+          }
+#pragma unroll
+        for (int i = 0; i < 16; ++i) S[i] = N[i];
+      }
+#pragma unroll
+      for (int i = 0; i < 16; ++i) out[i] = S[i];
+      break;
+    }
+  }
+}
+
+// number of complex entries a source writes
+__host__ __device__ __forceinline__ int source_entries(int kind, int k, int flags) {
+  int d = 1 << k;
+  if (kind == QMLB_SRC_DIAGPH) return d;
+  if (kind == QMLB_SRC_CONST && (flags & 2)) return d;
+  return d * d;
+}
+
+// insert a zero bit at position `bit` of g
+__device__ __forceinline__ uint32_t insert0(uint32_t g, int bit) {
+  uint32_t low = g & ((1u << bit) - 1u);
+  return ((g >> bit) << (bit + 1)) | low;
+}
+
+}  // namespace qmlb

@@ -1,0 +1,65 @@
+// Internal declarations shared by the translation units of libqmlb200.
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <string>
+#include <vector>
+
+#include "qmlb_device.cuh"
+#include "qmlb_tile_types.h"
+
+struct QmlbPassHost {
+  std::vector<qmlb_op> ops;      // tile-local bits (DIAG keeps global bits)
+  std::vector<int32_t> matoff;
+  std::vector<int2> windows;
+  std::vector<int> tile_bits;    // ascending global bits
+  int flags = 0;
+  int matw = 0;
+  qmlb::PassDev dev{};           // device view (pointers into the program blob)
+};
+
+struct qmlb_program {
+  int n_qubits = 0, n_bits = 0, density = 0, dtype = 0, out_type = 0;
+  std::vector<qmlb_op> ops;
+  std::vector<qmlb_source> sources;
+  std::vector<int32_t> items;
+  std::vector<qmlb_angle> angles;
+  std::vector<qmlb_term> terms;
+  std::vector<double> consts;
+  std::vector<qmlb_obs> obs;
+  std::vector<double> obs_consts;
+  int max_arg = -1;
+
+  int strategy = 0;
+  bool direct_out = false;   // evolution kernel writes the final result itself
+  int reg_mode = 0;
+  bool warp_team = false;
+  int teams = 1;
+  size_t smem = 0;
+  std::vector<QmlbPassHost> passes;
+  int sm_count = 148;
+
+  void* blob = nullptr;
+  qmlb::DevProg dev{};
+};
+
+namespace qmlb {
+
+extern std::atomic<unsigned long long> g_launches;  // kernels launched by this library
+
+constexpr int REG_MAX_BITS = 5;
+constexpr int TILE_THREADS = 256;
+
+// launchers (one translation unit per precision so the build parallelises)
+cudaError_t launch_reg_f32(const qmlb_program* p, const RunArgs& R, void* dst, cudaStream_t st);
+cudaError_t launch_reg_f64(const qmlb_program* p, const RunArgs& R, void* dst, cudaStream_t st);
+cudaError_t launch_tile_f32(const qmlb_program* p, const RunArgs& R, const PassDev& pass,
+                            unsigned grid, void* state, cudaStream_t st);
+cudaError_t launch_tile_f64(const qmlb_program* p, const RunArgs& R, const PassDev& pass,
+                            unsigned grid, void* state, cudaStream_t st);
+cudaError_t tile_set_smem_f32(size_t bytes);
+cudaError_t tile_set_smem_f64(size_t bytes);
+
+}  // namespace qmlb

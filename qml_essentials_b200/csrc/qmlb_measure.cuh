@@ -1,0 +1,302 @@
+// Measurement kernels over states resident in global memory
+// (simulation.py:204-317 measure_state / measure_density, jaqsi-level purities and
+// pair fidelities).  Reductions use a fixed order (warp shuffle tree, then warps in
+// index order, then chunk partials in index order) so results are bitwise
+// reproducible and independent of how a batch is sharded across GPUs.
+#pragma once
+
+#include "qmlb_device.cuh"
+
+namespace qmlb {
+
+template <typename T>
+__device__ __forceinline__ T warp_sum(T v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// sum over the CTA; result valid in thread 0.  `red` holds >= 32 T.
+template <typename T>
+__device__ __forceinline__ T block_sum(T v, T* red) {
+  v = warp_sum(v);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  __syncthreads();
+  if (l == 0) red[w] = v;
+  __syncthreads();
+  T r = (T)0;
+  if (threadIdx.x == 0) {
+    const int nw = (blockDim.x + 31) >> 5;
+    for (int i = 0; i < nw; ++i) r += red[i];
+  }
+  return r;
+}
+
+// probabilities: |psi_i|^2 or Re rho_ii
+template <typename T>
+__global__ void k_probs(const cx<T>* __restrict__ st, T* __restrict__ out, int64_t batch,
+                        int n_qubits, int density) {
+  const int64_t dim = (int64_t)1 << n_qubits;
+  const int64_t total = batch * dim;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    if (density) {
+      const int64_t b = i / dim, j = i % dim;
+      out[i] = st[b * dim * dim + j * (dim + 1)].x;
+    } else {
+      const cx<T> a = st[i];
+      out[i] = a.x * a.x + a.y * a.y;
+    }
+  }
+}
+
+// rho = |psi><psi| for noise-free circuits asked for "density" (simulation.py:188-189)
+template <typename T>
+__global__ void k_outer(const cx<T>* __restrict__ st, cx<T>* __restrict__ out,
+                        int64_t batch, int n_qubits) {
+  const int64_t dim = (int64_t)1 << n_qubits;
+  const int64_t total = batch * dim * dim;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t b = i / (dim * dim), r = (i / dim) % dim, c = i % dim;
+    const cx<T> x = st[b * dim + r], y = st[b * dim + c];
+    out[i] = mk<T>(x.x * y.x + x.y * y.y, x.y * y.x - x.x * y.y);
+  }
+}
+
+#define QMLB_OBS_GROUP 8
+
+// Expectation values.  Grid: batch * chunks CTAs; CTA (bl, c) reduces chunk c of
+// element bl for every observable and writes partial[(bl * n_obs + j) * chunks + c]
+// (directly the result when chunks == 1).
+template <typename T>
+__global__ void __launch_bounds__(256) k_expval(DevProg P, const cx<T>* __restrict__ st,
+                                                T* __restrict__ partial, int64_t batch,
+                                                int chunks) {
+  __shared__ T red[32];
+  const int n = P.n_qubits;
+  const int64_t dim = (int64_t)1 << n;
+  const int64_t bl = blockIdx.x / chunks;
+  const int c = blockIdx.x % chunks;
+  const cx<T>* s = st + (size_t)bl * (P.density ? dim * dim : dim);
+
+  auto prob = [&](int64_t i) -> T {
+    if (P.density) return s[i * (dim + 1)].x;
+    const cx<T> a = s[i];
+    return a.x * a.x + a.y * a.y;
+  };
+
+  int j = 0;
+  while (j < P.n_obs) {
+    if (P.obs[j].kind != QMLB_OBS_DENSE) {
+      // group of up to 8 consecutive diagonal-type observables: one sweep
+      int cnt = 0;
+      while (j + cnt < P.n_obs && cnt < QMLB_OBS_GROUP &&
+             P.obs[j + cnt].kind != QMLB_OBS_DENSE)
+        ++cnt;
+      T acc[QMLB_OBS_GROUP];
+#pragma unroll
+      for (int o = 0; o < QMLB_OBS_GROUP; ++o) acc[o] = (T)0;
+      const int64_t per = (dim + chunks - 1) / chunks;
+      const int64_t lo = c * per, hi = (lo + per < dim) ? lo + per : dim;
+      for (int64_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+        const T p = prob(i);
+#pragma unroll
+        for (int o = 0; o < QMLB_OBS_GROUP; ++o) {
+          if (o < cnt) {
+            const qmlb_obs& ob = P.obs[j + o];
+            T d;
+            if (ob.kind == QMLB_OBS_ZSTRING) {
+              d = (__popcll((unsigned long long)(i & ob.zmask)) & 1) ? (T)-1 : (T)1;
+            } else {
+              int v = 0;
+              for (int t = 0; t < ob.k; ++t) v |= (int)((i >> ob.bits[t]) & 1) << (ob.k - 1 - t);
+              d = (T)P.obs_consts[2 * (ob.a0 + v)];
+            }
+            acc[o] = fma(p, d, acc[o]);
+          }
+        }
+      }
+#pragma unroll
+      for (int o = 0; o < QMLB_OBS_GROUP; ++o) {
+        if (o < cnt) {
+          const T r = block_sum<T>(acc[o], red);
+          if (threadIdx.x == 0) partial[((size_t)bl * P.n_obs + j + o) * chunks + c] = r;
+        }
+      }
+      j += cnt;
+    } else {
+      // dense k-qubit observable: sum over the n-k untouched bits of
+      //   pure : sum_{r,c} conj(psi[r]) O[r][c] psi[c]
+      //   mixed: sum_{a,b} O[a][b] rho[idx(b)][idx(a)]          (Tr(O rho))
+      const qmlb_obs& ob = P.obs[j];
+      const int k = ob.k, d = 1 << k;
+      int sorted[QMLB_MAX_OP_BITS];
+      for (int t = 0; t < k; ++t) sorted[t] = ob.bits[t];
+      for (int a = 0; a < k; ++a)
+        for (int t = 0; t + 1 < k - a; ++t)
+          if (sorted[t] > sorted[t + 1]) {
+            int x = sorted[t];
+            sorted[t] = sorted[t + 1];
+            sorted[t + 1] = x;
+          }
+      const int64_t groups = dim >> k;
+      const int64_t per = (groups + chunks - 1) / chunks;
+      const int64_t lo = c * per, hi = (lo + per < groups) ? lo + per : groups;
+      T acc = (T)0;
+      for (int64_t g = lo + threadIdx.x; g < hi; g += blockDim.x) {
+        int64_t base = g;
+        for (int t = 0; t < k; ++t) {
+          const int64_t low = base & (((int64_t)1 << sorted[t]) - 1);
+          base = ((base >> sorted[t]) << (sorted[t] + 1)) | low;
+        }
+        for (int r = 0; r < d; ++r) {
+          int64_t ir = base;
+          for (int t = 0; t < k; ++t) ir |= (int64_t)((r >> (k - 1 - t)) & 1) << ob.bits[t];
+          for (int cc = 0; cc < d; ++cc) {
+            int64_t ic = base;
+            for (int t = 0; t < k; ++t)
+              ic |= (int64_t)((cc >> (k - 1 - t)) & 1) << ob.bits[t];
+            const T oR = (T)P.obs_consts[2 * (ob.a0 + r * d + cc)];
+            const T oI = (T)P.obs_consts[2 * (ob.a0 + r * d + cc) + 1];
+            if (oR == (T)0 && oI == (T)0) continue;
+            if (P.density) {
+              const cx<T> x = s[ic * dim + ir];  // rho[c][r]
+              acc += oR * x.x - oI * x.y;
+            } else {
+              const cx<T> x = s[ir], y = s[ic];
+              // Re( conj(x) * O * y )
+              const T tr = oR * y.x - oI * y.y, ti = oR * y.y + oI * y.x;
+              acc += x.x * tr + x.y * ti;
+            }
+          }
+        }
+      }
+      const T r = block_sum<T>(acc, red);
+      if (threadIdx.x == 0) partial[((size_t)bl * P.n_obs + j) * chunks + c] = r;
+      ++j;
+    }
+  }
+}
+
+// out[i] = sum_c partial[i * chunks + c] in index order
+template <typename T>
+__global__ void k_sum_chunks(const T* __restrict__ partial, T* __restrict__ out,
+                             int64_t n, int chunks) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  T r = (T)0;
+  for (int c = 0; c < chunks; ++c) r += partial[i * chunks + c];
+  out[i] = r;
+}
+
+// Shot bookkeeping (simulation.py:352-357): one CTA per element.
+template <typename T>
+__global__ void __launch_bounds__(256) k_sample(const T* __restrict__ probs,
+                                                const double* __restrict__ uniforms,
+                                                int n_qubits, int64_t shots,
+                                                int32_t* __restrict__ counts) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  T* cum = reinterpret_cast<T*>(smem_raw);
+  const int dim = 1 << n_qubits;
+  const int64_t b = blockIdx.x;
+  const T* p = probs + b * dim;
+  if (threadIdx.x == 0) {  // sequential order: matches the oracle's cumsum bit for bit
+    T run = (T)0;
+    for (int i = 0; i < dim; ++i) {
+      run += p[i];
+      cum[i] = run;
+    }
+  }
+  __syncthreads();
+  const T total = cum[dim - 1];
+  int32_t* cnt = counts + b * dim;
+  const double* u = uniforms + b * shots;
+  for (int64_t sidx = threadIdx.x; sidx < shots; sidx += blockDim.x) {
+    const T r = total * ((T)1 - (T)u[sidx]);
+    int lo = 0, hi = dim;  // first index with cum[idx] >= r  (searchsorted, side=left)
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if (cum[mid] < r)
+        lo = mid + 1;
+      else
+        hi = mid;
+    }
+    if (lo > dim - 1) lo = dim - 1;
+    atomicAdd(&cnt[lo], 1);
+  }
+}
+
+// Single-qubit reduced purities Tr(rho_q^2) (entanglement.py:86-103).
+// One CTA per element; out[b][q].
+template <typename T>
+__global__ void __launch_bounds__(256) k_purity(const cx<T>* __restrict__ st, int density,
+                                                int n_qubits, T* __restrict__ out) {
+  __shared__ T red[32];
+  const int64_t dim = (int64_t)1 << n_qubits;
+  const int64_t b = blockIdx.x;
+  const cx<T>* s = st + (size_t)b * (density ? dim * dim : dim);
+  for (int q = 0; q < n_qubits; ++q) {
+    const int bit = n_qubits - 1 - q;
+    // reduced 2x2: r00, r11 real, r01 complex
+    T r00 = 0, r11 = 0, xr = 0, xi = 0;
+    for (int64_t g = threadIdx.x; g < dim / 2; g += blockDim.x) {
+      const int64_t low = g & (((int64_t)1 << bit) - 1);
+      const int64_t i0 = ((g >> bit) << (bit + 1)) | low, i1 = i0 | ((int64_t)1 << bit);
+      if (density) {
+        r00 += s[i0 * dim + i0].x;
+        r11 += s[i1 * dim + i1].x;
+        const cx<T> c = s[i0 * dim + i1];
+        xr += c.x;
+        xi += c.y;
+      } else {
+        const cx<T> a = s[i0], c = s[i1];
+        r00 += a.x * a.x + a.y * a.y;
+        r11 += c.x * c.x + c.y * c.y;
+        xr += a.x * c.x + a.y * c.y;  // a * conj(c)
+        xi += a.y * c.x - a.x * c.y;
+      }
+    }
+    r00 = block_sum<T>(r00, red);
+    r11 = block_sum<T>(r11, red);
+    xr = block_sum<T>(xr, red);
+    xi = block_sum<T>(xi, red);
+    if (threadIdx.x == 0)
+      out[b * n_qubits + q] = r00 * r00 + r11 * r11 + (T)2 * (xr * xr + xi * xi);
+  }
+}
+
+// |<psi_b|psi_{b+half}>|^2 ; one CTA per pair.
+template <typename T>
+__global__ void __launch_bounds__(256) k_overlap(const cx<T>* __restrict__ st, int64_t half,
+                                                 int n_qubits, T* __restrict__ out) {
+  __shared__ T red[32];
+  const int64_t dim = (int64_t)1 << n_qubits;
+  const int64_t b = blockIdx.x;
+  const cx<T>* x = st + (size_t)b * dim;
+  const cx<T>* y = st + (size_t)(b + half) * dim;
+  T re = 0, im = 0;
+  for (int64_t i = threadIdx.x; i < dim; i += blockDim.x) {
+    const cx<T> a = x[i], c = y[i];
+    re += a.x * c.x + a.y * c.y;
+    im += a.x * c.y - a.y * c.x;
+  }
+  re = block_sum<T>(re, red);
+  im = block_sum<T>(im, red);
+  if (threadIdx.x == 0) out[b] = re * re + im * im;
+}
+
+// FMA-throughput probe (roofline denominator of the register regime)
+template <typename T>
+__global__ void __launch_bounds__(256) k_fma_peak(T* out, int iters) {
+  T a0 = (T)threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5,
+    a6 = a0 + 6, a7 = a0 + 7;
+  const T m = (T)0.999999, c = (T)1e-7;
+  for (int i = 0; i < iters; ++i) {
+    a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+    a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+  }
+  out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+
+}  // namespace qmlb

@@ -1,0 +1,28 @@
+// Instantiates the register kernel for one precision (QMLB_T / QMLB_SUFFIX).
+#include "qmlb_internal.h"
+#include "qmlb_reg.cuh"
+
+namespace qmlb {
+
+template <int N>
+static void launch_n(const qmlb_program* p, const RunArgs& R, void* dst, cudaStream_t st) {
+  const int threads = 128;
+  const unsigned grid = (unsigned)((R.batch + threads - 1) / threads);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  k_reg<QMLB_T, N><<<grid, threads, 0, st>>>(p->dev, R, p->reg_mode, dst);
+}
+
+cudaError_t QMLB_LAUNCH_REG(const qmlb_program* p, const RunArgs& R, void* dst,
+                            cudaStream_t st) {
+  switch (p->n_bits) {
+    case 1: launch_n<1>(p, R, dst, st); break;
+    case 2: launch_n<2>(p, R, dst, st); break;
+    case 3: launch_n<3>(p, R, dst, st); break;
+    case 4: launch_n<4>(p, R, dst, st); break;
+    case 5: launch_n<5>(p, R, dst, st); break;
+    default: return cudaErrorInvalidValue;
+  }
+  return cudaGetLastError();
+}
+
+}  // namespace qmlb
