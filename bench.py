@@ -1,0 +1,315 @@
+"""Benchmark of the circuit-execution hot path on B200 (BASELINE.json metric:
+circuit evals/sec, batched).
+
+Workload (BASELINE.json configs[1], SURVEY.md section 8(d) cfg 2, grid B "dense"):
+``Model(n_qubits=4, n_layers=4, "Hardware_Efficient")``, expval on all 4 qubits,
+1024 parameter samples (NumPy default_rng(1000), uniform[0, 2pi)) x a 264-point
+input grid (``Coefficients._fourier_transform`` with mfs=8) = 270 336 circuit
+evaluations per step, complex128.
+
+One JSON line on stdout (rank 0):
+  value     evals/s with params/inputs resident in HBM (kernel launches only, CUDA events)
+  e2e       evals/s through Model.__call__ with host NumPy arrays: H2D of params+inputs
+            and D2H of the (264, 1024, 4) float64 result inside the timed region
+  roofline  dominant kernel (k_reg<double,4>) against the FP64 FMA peak measured on the
+            same GPU by qmlb_fma_peak (MEASURED_PEAKS.json has no FMA figure)
+  cpu_baseline  the reference-faithful CPU restatement (oracle, one batched einsum per
+            tape op, torch-CPU complex128, all host threads) on a bounded sample
+``--impl reference`` times only that CPU restatement (the reference itself needs JAX,
+which this image does not have - DESIGN.md).
+
+Multi-GPU (torchrun): weak scaling - every rank evaluates its own 1024 parameter
+samples (independent circuits, no data-path collective), then one small NCCL
+all-reduce of the per-frequency coefficient statistics (sum and sum of squares of
+the 264-point mean-expval signal), which is what FCC averages need.
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_QUBITS, N_LAYERS, ANSATZ = 4, 4, "Hardware_Efficient"
+N_PARAM_SAMPLES, MFS = 1024, 8
+ALGO_FLOP_PER_EVAL = 26624  # 76 one-qubit + 20 CX dense gates, n = 4
+L2_FLUSH_BYTES = 512 * 1024 * 1024
+
+
+def workload(seed: int = 1000):
+    from qml_essentials_b200.model import Model
+
+    model = Model(n_qubits=N_QUBITS, n_layers=N_LAYERS, circuit_type=ANSATZ)
+    rng = np.random.default_rng(seed)
+    params = rng.uniform(0.0, 2 * np.pi, (N_PARAM_SAMPLES, *model._params_shape))
+    n_freqs = MFS * model.degree[0]
+    inputs = np.arange(0.0, 2 * np.pi, 2 * np.pi / n_freqs).reshape(-1, 1)
+    return model, params, inputs
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks + throttle reasons during the timed region."""
+
+    def __init__(self, gpu_index: int):
+        super().__init__(daemon=True)
+        self.gpu, self.rows, self._stop = gpu_index, [], threading.Event()
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(
+                    ["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits",
+                     "-i", str(self.gpu)], capture_output=True, text=True, timeout=5).stdout
+                self.rows.append([x.strip() for x in out.strip().split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def stop(self):
+        self._stop.set()
+        self.join(timeout=3)
+        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 6
+                          for i in range(4) if r[2 + i].lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None,
+                "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(self.rows)}
+
+
+def oracle_cpu_evals_per_s(params, inputs, n_param_sample, threads, repeats=2):
+    """Reference-faithful CPU restatement on a bounded sample: all grid points x
+    `n_param_sample` parameter sets, one batched einsum per tape op (torch-CPU)."""
+    from oracle import circuits as oc
+    from oracle import sim as osim
+
+    B_I, B_P = inputs.shape[0], n_param_sample
+    ii, pp, _ = oc.assimilate_index(B_I, B_P)
+    p_b = np.moveaxis(params[:B_P][pp], 0, -1)  # (L', P, B)
+    x_b = [inputs[ii, 0]]
+    tape = oc.variational_tape(N_QUBITS, N_LAYERS, ANSATZ, p_b, x_b)
+    B = B_I * B_P
+    best = None
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        st = osim.simulate_batched(tape, N_QUBITS, B, backend="torch", threads=threads)
+        probs = np.abs(st) ** 2
+        pt = probs.reshape((B,) + (2,) * N_QUBITS)
+        ev = np.stack([pt.sum(axis=tuple(a + 1 for a in range(N_QUBITS) if a != q))
+                       @ np.array([1.0, -1.0]) for q in range(N_QUBITS)], axis=1)
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    return B / best, ev.reshape(B_I, B_P, N_QUBITS), f"{B_I} grid points x {B_P} param sets"
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    model, params, inputs = workload()
+    n_sample = 256
+    times = []
+    for i in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        v, _, sample = oracle_cpu_evals_per_s(params, inputs, n_sample, cores, repeats=1)
+        if i >= args.warmup:
+            times.append(time.perf_counter() - t0)
+    B = inputs.shape[0] * n_sample
+    value = B * len(times) / sum(times)
+    line = {
+        "impl": "reference", "metric": "circuit evals/sec (batched)", "value": value,
+        "unit": "evals/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * sum(times) / len(times), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "complex128 (f64)",
+        "data": "synthetic",
+        "config": {"workload": "cfg2: Model(4,4,Hardware_Efficient) expval, 264-point grid",
+                   "evals_per_step": B, "note": "reference-faithful CPU restatement (no "
+                   "XLA): the reference needs JAX, absent from this image"},
+        "cpu_baseline": {"value": value, "unit": "evals/s", "cores": cores, "kind": "port",
+                         "sample": sample},
+        "e2e": {"value": value, "unit": "evals/s", "h2d_bytes_per_step": 0,
+                "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--precision", default="complex128", choices=["complex128", "complex64"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    from qml_essentials_b200 import config, script
+    from qml_essentials_b200.backend import QMLB_C128
+
+    config.set_precision(args.precision)
+    ex = script.get_executor()
+    model, params, inputs = workload(seed=1000 + rank)  # every rank: its own samples
+    B_I, B_P = inputs.shape[0], params.shape[0]
+    B = B_I * B_P
+    n_freq = B_I
+
+    # ---- plan + stage (device-resident arguments) --------------------------------
+    model(params=params, inputs=inputs)  # records + compiles the plan, creates the program
+    plan = next(p for p in model.script._jit_cache.values()
+                if hasattr(p, "program") and p.device)
+    # rebuild the device call exactly as Script does, but keep it resident
+    obs = model._build_obs()[1]
+    ax_p, ax_i, ax_r = model._batch_axes(B)
+    in_axes = (ax_p, ax_i, ax_r, script.BatchAxis(0, 1, B, B), None)
+    host_args = model.script._device_args(
+        plan, (params, inputs, model.pulse_params, script.LazyKeys(model.random_key, B),
+               model.enc_params), in_axes, B)
+    call = ex.stage(plan, host_args, B)
+    stats = torch.zeros(2 * n_freq, dtype=torch.float64, device=dev)
+    flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=dev)
+
+    def step_device():
+        out = call.launch()  # (B, 4) expvals, flat order b = i * B_P + p
+        if world > 1:
+            sig = out.view(B_I, B_P, N_QUBITS).mean(dim=2)  # mean expval per (x, sample)
+            stats[:n_freq] = sig.sum(dim=1)
+            stats[n_freq:] = (sig * sig).sum(dim=1)
+            dist.all_reduce(stats)
+        return out
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step_device()
+    barrier()
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = ex.launch_count()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+          for _ in range(args.steps)]
+    for s, e in ev:
+        flush.fill_(1)  # L2 flush between timed iterations (untimed)
+        s.record()
+        out = step_device()
+        e.record()
+    barrier()
+    dev_ms = sum(s.elapsed_time(e) for s, e in ev)
+    launches = ex.launch_count() - launches0
+
+    # kernel-only duration of the dominant kernel (one launch per step)
+    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+           for _ in range(args.steps)]
+    for s, e in kev:
+        flush.fill_(1)
+        s.record()
+        call.launch()
+        e.record()
+    torch.cuda.synchronize()
+    kern_ms = sum(s.elapsed_time(e) for s, e in kev) / args.steps
+
+    # ---- end to end through Model.__call__ (host arrays in, host array out) --------
+    for _ in range(args.warmup):
+        res = model(params=params, inputs=inputs)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        res = model(params=params, inputs=inputs)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    clocks = sampler.stop() if rank == 0 else None
+
+    t = torch.tensor([dev_ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms, e2e_ms = float(t[0]), float(t[1])
+
+    if rank == 0:
+        total_evals = B * world * args.steps
+        value = total_evals / (dev_ms * 1e-3)
+        e2e_value = total_evals / (e2e_ms * 1e-3)
+        prec64 = args.precision == "complex128"
+        peak_tf = ex.fma_peak_tflops(args.precision)
+        achieved_tf = ALGO_FLOP_PER_EVAL * B / (kern_ms * 1e-3) / 1e12
+        line = {
+            "metric": "circuit evals/sec (batched)", "value": value, "unit": "evals/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "complex128 (f64)" if prec64 else "complex64 (f32)",
+            "data": "synthetic",
+            "config": {
+                "workload": "BASELINE configs[1] / SURVEY 8(d) cfg2 grid B: Model(4,4,"
+                            "'Hardware_Efficient') expval on 4 qubits, 1024 param samples "
+                            "(default_rng(1000+rank)) x 264-point input grid per GPU",
+                "evals_per_step_per_gpu": B, "cache": "L2 flushed (512 MiB write) between "
+                "timed iterations", "parallelism": f"batch-sharded x{world}",
+            },
+            "e2e": {"value": e2e_value, "unit": "evals/s",
+                    "h2d_bytes_per_step": int(params.nbytes + inputs.nbytes),
+                    "d2h_bytes_per_step": int(res.nbytes),
+                    "ms_per_step": e2e_ms / args.steps,
+                    "api": "Model.__call__(params, inputs) with NumPy arrays"},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": {
+                "bound": "fp64_fma" if prec64 else "fp32_fma",
+                "kernel": f"k_reg<{'double' if prec64 else 'float'},4>",
+                "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
+                "frac": achieved_tf / peak_tf, "traffic": None,
+                "kernel_ms": kern_ms,
+                "note": "achieved = algorithmic (unfused, dense) 26624 flop/eval x 270336 "
+                        "evals / CUDA-event launch time; peak = qmlb_fma_peak measured on "
+                        "this GPU (no FMA figure in MEASURED_PEAKS.json)",
+            },
+        }
+        if not args.no_cpu_baseline and world == 1:
+            cores = os.cpu_count() or 1
+            cpu_v, cpu_ev, sample = oracle_cpu_evals_per_s(params, inputs, 256, cores)
+            err = float(np.abs(res[:, :256, :] - cpu_ev).max())
+            line["cpu_baseline"] = {"value": cpu_v, "unit": "evals/s", "cores": cores,
+                                    "kind": "port", "sample": sample,
+                                    "max_abs_err_vs_gpu": err}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -441,7 +441,7 @@ class _Lowerer:
         factors = spec.factors if isinstance(spec, ProductMat) else [spec]
         ket = [self.ket_bit(w) for w in wires]
         for f in factors:
-            if self.density and isinstance(f, ConstMat):
+            if self.density and isinstance(f, ConstMat) and 2 * len(wires) <= 4:
                 perm = _permutation_of(f.matrix)
                 if perm is not None and not _is_identity(f.matrix):
                     # U (x) conj(U) of a permutation is one permutation of 2k bits

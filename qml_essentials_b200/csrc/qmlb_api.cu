@@ -158,7 +158,7 @@ void make_windows(const qmlb_program* p, QmlbPassHost& ps, int matw) {
 
 // Greedy pass construction for streamed execution: every pass owns the `m_low`
 // least-significant bits (contiguous -> coalesced) plus up to kt - m_low others.
-void schedule_passes(qmlb_program* p, int kt, int m_low) {
+int schedule_passes(qmlb_program* p, int kt, int m_low) {
   const int N = p->n_bits;
   std::vector<char> done(p->ops.size(), 0);
   size_t remaining = p->ops.size();
@@ -206,8 +206,11 @@ void schedule_passes(qmlb_program* p, int kt, int m_low) {
     ps.flags = QMLB_PASS_STORE | (first_pass ? QMLB_PASS_INIT : 0);
     p->passes.push_back(std::move(ps));
     first_pass = false;
-    if (picked.empty() && remaining > 0) break;  // cannot happen (k <= 4 <= kt)
+    if (picked.empty() && remaining > 0)
+      return fail(QMLB_ERR_UNSUPPORTED,
+                  "an operation does not fit a tile (QMLB_TILE_BITS too small)");
   }
+  return QMLB_OK;
 }
 
 template <typename V>
@@ -364,7 +367,11 @@ int plan(qmlb_program* p) {
   int kt = env_int("QMLB_TILE_BITS", p->dtype == QMLB_C128 ? 12 : 13);
   kt = std::min(kt, std::min(N, QMLB_MAX_TILE_BITS));
   int m_low = std::min(env_int("QMLB_TILE_LOW_BITS", 5), kt);
-  schedule_passes(p, kt, m_low);
+  if (kt < m_low + 4) m_low = std::max(0, kt - 4);  // every op (<= 4 bits) must fit a tile
+  {
+    int rc = schedule_passes(p, kt, m_low);
+    if (rc != QMLB_OK) return rc;
+  }
   p->warp_team = false;
   p->teams = 1;
   const int matw_cap = env_int("QMLB_TILE_MATW", 1024);

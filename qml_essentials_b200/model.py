@@ -695,6 +695,12 @@ class Model:
         self.random_key, sub_key = safe_random_split(self.random_key)
         meas_type, obs = self._build_obs()
         exec_kwargs = dict(noise_params=self.noise_params, gate_mode=self.gate_mode)
+        # everything _variational reads from `self` (not from its arguments) must
+        # take part in the plan cache key
+        self.script.cache_salt = (
+            bool(self.remove_zero_encoding and self._zero_inputs and self.batch_shape[0] == 1),
+            self._data_reupload.tobytes(), self.n_layers, self.has_dru,
+        )
 
         shot_key = None
         if self.shots is not None:

@@ -156,6 +156,9 @@ class Script:
         self.f = f
         self._n_qubits = n_qubits
         self.precision = precision
+        # hashable extra cache-key component for state the circuit function reads
+        # besides its arguments (Model: zero-input shortcut, re-upload mask, ...)
+        self.cache_salt = None
         self._jit_cache: dict = {}
 
     # -- recording ------------------------------------------------------------
@@ -225,7 +228,9 @@ class Script:
     def _signature(self, type, obs, args, kwargs, in_axes, shots, baked):
         sig = []
         for i, (a, ax) in enumerate(zip(args, in_axes)):
-            axk = ax._key() if isinstance(ax, BatchAxis) else ax
+            # the program does not depend on batch sizes or factors, only on the axis
+            axk = ("B", ax.axis) if isinstance(ax, BatchAxis) else (
+                None if ax is None else ("B", ax))
             if _is_float_array(a):
                 if i in baked:
                     sig.append((axk, _make_hashable(a)))
@@ -250,6 +255,7 @@ class Script:
             self._precision(),
             obs_sig,
             ("shots", shots) if shots is not None else None,
+            self.cache_salt,
         )
 
     # -- planning ---------------------------------------------------------------
@@ -413,8 +419,8 @@ class Script:
         for_shots = shots is not None and type in ("probs", "expval")
         # the set of baked (value-keyed) arguments is discovered on the first build
         probe_key = ("_baked", type, tuple(
-            (ax._key() if isinstance(ax, BatchAxis) else ax) for ax in in_axes),
-            _make_hashable({k: v for k, v in kwargs.items()}), len(args))
+            (("B", ax.axis) if isinstance(ax, BatchAxis) else ax) for ax in in_axes),
+            _make_hashable({k: v for k, v in kwargs.items()}), len(args), self.cache_salt)
         baked = self._jit_cache.get(probe_key, ())
         cache_key = self._signature(type, obs, args, kwargs, in_axes,
                                     shots if for_shots else None, baked)

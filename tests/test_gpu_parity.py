@@ -1,0 +1,188 @@
+"""Parity through the C ABI on a B200: the CUDA kernels against the oracle on the
+same seeded inputs (1e-10 complex128, 1e-5 complex64), the reference's KATs, the
+three execution strategies against each other, bit-exact shot bookkeeping, and
+size-independent invariants at BASELINE sizes."""
+
+import os
+import subprocess
+import sys
+import warnings
+
+import numpy as np
+import pytest
+
+import kat_cases
+import parity_cases as pc
+from qml_essentials_b200 import operations as op
+from qml_essentials_b200.model import Model
+from qml_essentials_b200.script import Script, get_executor
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _worst(d):
+    return max(v for v in d.values() if isinstance(v, (int, float)))
+
+
+def test_native_library_is_the_executor():
+    ex = get_executor()
+    assert ex.name == "cuda-sm100a"
+    n0 = ex.launch_count()
+    Script(kat_cases.bell, 2).execute("probs")
+    assert ex.launch_count() > n0
+
+
+def test_reference_kats_on_gpu():
+    kat_cases.run_all(lambda c, n, t, o, args=(): Script(c, n_qubits=n).execute(
+        t, obs=o, args=args))
+    kat_cases.run_all(lambda c, n, t, o, args=(): Script(
+        c, n_qubits=n, precision="complex64").execute(t, obs=o, args=args), atol=1e-5)
+
+
+@pytest.mark.parametrize("precision", ["complex128", "complex64"])
+def test_every_gate_and_channel(precision):
+    tol = pc.TOL[precision]
+    assert _worst(pc.case_every_gate(precision)) < tol
+    assert _worst(pc.case_every_channel(precision)) < tol
+
+
+@pytest.mark.parametrize("precision", ["complex128", "complex64"])
+def test_baseline_configs_reduced(precision):
+    for name, err in pc.case_baseline_configs(precision).items():
+        assert err < pc.TOL[precision], name
+
+
+@pytest.mark.parametrize("precision", ["complex128", "complex64"])
+def test_all_ansaetze_and_noise_keys(precision):
+    for name, err in {**pc.case_all_ansaetze(precision), **pc.case_noise_keys(precision)}.items():
+        assert err < pc.TOL[precision], name
+
+
+@pytest.mark.parametrize("precision", ["complex128", "complex64"])
+def test_shots_counts_bit_exact(precision):
+    r = pc.case_shots(precision)
+    assert r["count_mismatch"] == 0
+    assert r["expval_err"] < 1e-12 and r["sums"] < 1e-12
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 5, 6, 7, 9, 10, 12])
+def test_statevector_sizes_across_kernel_regimes(n):
+    """n <= 5 register kernel, 6..7 warp teams, 8..13 CTA teams (complex128)."""
+    L = 1 if n > 8 else 2
+    assert pc.case_model(n, L, "Circuit_19" if n > 1 else "No_Entangling", 3, 2, "probs") < 1e-10
+    if n >= 2:
+        assert pc.case_model(n, L, "Hardware_Efficient", 2, 2, "expval") < 1e-10
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 4, 5])
+def test_noisy_density_sizes(n):
+    noise = {"Depolarizing": 0.01, "AmplitudeDamping": 0.02, "PhaseFlip": 0.005}
+    assert pc.case_model(n, 2, "Strongly_Entangling" if n > 1 else "No_Entangling", 2, 2,
+                         "density", noise=noise) < 1e-10
+
+
+def test_streamed_strategy_matches_resident_strategy():
+    """Force the HBM-streamed tile passes on small states (separate processes: the
+    strategy is an environment switch read at program creation)."""
+    code = ("import sys; sys.path.insert(0, 'tests'); import parity_cases as pc; "
+            "e = max(pc.case_model(7, 2, 'Hardware_Efficient', 2, 3, 'state'),"
+            " pc.case_model(8, 1, 'Circuit_19', 2, 2, 'expval'),"
+            " pc.case_model(3, 2, 'Strongly_Entangling', 2, 2, 'density',"
+            " noise={'Depolarizing': 0.01, 'AmplitudeDamping': 0.02}),"
+            " pc.case_model(4, 1, 'Circuit_6', 1, 2, 'probs', noise={'BitFlip': 0.1,"
+            " 'MultiQubitDepolarizing': 0.05})); print('ERR', e); assert e < 1e-10")
+    for kt, low in (("6", "2"), ("5", "1"), ("7", "5")):
+        env = dict(os.environ, QMLB_FORCE_STRATEGY="2", QMLB_TILE_BITS=kt,
+                   QMLB_TILE_LOW_BITS=low, QMLB_TILE_MATW="40")
+        r = subprocess.run([sys.executable, "-c", code], cwd=ROOT, env=env,
+                           capture_output=True, text=True)
+        assert r.returncode == 0, r.stdout + r.stderr
+
+
+def test_chunked_equals_full_on_device(monkeypatch):
+    from qml_essentials_b200 import memory
+
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        m = Model(4, 2, "Circuit_19")
+        x = np.linspace(-1, 1, 37)
+        full = m(inputs=x, execution_type="density")
+        m2 = Model(4, 2, "Circuit_19")
+        monkeypatch.setattr(memory, "compute_chunk_size", lambda *a, **k: 10)
+        assert np.array_equal(full, m2(inputs=x, execution_type="density"))
+
+
+def test_full_size_cfg2_invariants_and_sample_parity():
+    """BASELINE config 2 at full size (270 336 evals): |<Z>| <= 1, batch-order
+    consistency against single-parameter calls, and oracle parity on a sample."""
+    import bench
+
+    model, params, inputs = bench.workload()
+    res = model(params=params, inputs=inputs)
+    assert res.shape == (264, 1024, 4) and np.all(np.abs(res) <= 1 + 1e-12)
+    one = model(params=params[17], inputs=inputs)
+    assert np.allclose(res[:, 17], one, atol=1e-12)
+    _, cpu_ev, _ = bench.oracle_cpu_evals_per_s(params, inputs, 4, os.cpu_count(), repeats=1)
+    assert np.abs(res[:, :4] - cpu_ev).max() < 1e-10
+    m32 = bench.workload()[0]
+    m32.script.precision = "complex64"
+    assert np.abs(m32(params=params[:64], inputs=inputs) - res[:, :64]).max() < 1e-5
+
+
+def test_full_size_cfg3_density_invariants():
+    """Config 3 circuit (n=6, Circuit_15): trace 1, Hermitian, idempotent (pure)."""
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        m = Model(6, 3, "Circuit_15")
+        p = np.random.default_rng(1000).uniform(0, 2 * np.pi, (2000, *m._params_shape))
+        rho = m(params=p, execution_type="density")
+    assert rho.shape == (2000, 64, 64)
+    assert np.allclose(np.trace(rho, axis1=1, axis2=2), 1, atol=1e-10)
+    assert np.allclose(rho, np.conj(np.swapaxes(rho, 1, 2)), atol=1e-12)
+    assert np.allclose(rho[:50] @ rho[:50], rho[:50], atol=1e-10)
+
+
+def test_noisy_density_n7_streamed_invariants():
+    """Noisy density beyond shared memory (n = 7: 4^7 x 16 B = 256 KiB per state)
+    runs as streamed tile passes: valid state + agreement with probs output."""
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        m = Model(7, 2, "Strongly_Entangling")
+        x = np.linspace(-1, 1, 6)
+        noise = {"Depolarizing": 0.01, "AmplitudeDamping": 0.02}
+        rho = m(inputs=x, execution_type="density", noise_params=dict(noise))
+        pr = m(inputs=x, execution_type="probs", noise_params=dict(noise))
+        ev = m(inputs=x, execution_type="expval", noise_params=dict(noise))
+    assert np.allclose(np.trace(rho, axis1=1, axis2=2), 1, atol=1e-10)
+    assert np.allclose(rho, np.conj(np.swapaxes(rho, 1, 2)), atol=1e-12)
+    pur = np.real(np.einsum("bij,bji->b", rho, rho))
+    assert np.all(pur < 1 - 1e-3) and np.all(pur > 1 / 128)
+    assert np.allclose(np.real(np.einsum("bii->bi", rho)), pr.reshape(6, -1), atol=1e-12)
+    z0 = np.array([1 - 2 * ((i >> 6) & 1) for i in range(128)])
+    assert np.allclose(ev[:, 0], pr.reshape(6, -1) @ z0, atol=1e-12)
+    assert pc.case_model(7, 1, "Strongly_Entangling", 1, 1, "density", noise=noise) < 1e-10
+
+
+def test_device_side_purity_and_overlap_reductions():
+    import torch
+
+    from oracle import sim as osim
+
+    ex = get_executor()
+    rng = np.random.default_rng(3)
+    B, n = 10, 5
+    st = rng.normal(size=(B, 2**n)) + 1j * rng.normal(size=(B, 2**n))
+    st /= np.linalg.norm(st, axis=1, keepdims=True)
+    t = torch.from_numpy(st).to(ex.device)
+    pur = ex.purities(t, n, False).cpu().numpy()
+    fid = ex.overlap_fidelities(t, n).cpu().numpy()
+    for b in range(B):
+        rho = np.outer(st[b], st[b].conj())
+        for q in range(n):
+            r = osim.partial_trace(rho, n, [q])
+            assert abs(pur[b, q] - np.real(np.trace(r @ r))) < 1e-12
+    assert np.allclose(fid, np.abs(np.einsum("bi,bi->b", st[:5].conj(), st[5:])) ** 2,
+                       atol=1e-12)
+    rho_b = torch.from_numpy(np.einsum("bi,bj->bij", st, st.conj())).to(ex.device)
+    assert np.allclose(ex.purities(rho_b, n, True).cpu().numpy(), pur, atol=1e-12)

@@ -10,7 +10,7 @@ sys.path.insert(0, os.path.join(os.path.dirname(__file__), ".."))
 if len(sys.argv) > 1:
     os.environ["QMLB_FORCE_STRATEGY"] = sys.argv[1]
     if sys.argv[1] == "2":
-        os.environ.setdefault("QMLB_TILE_BITS", "4")
+        os.environ.setdefault("QMLB_TILE_BITS", "6")
         os.environ.setdefault("QMLB_TILE_LOW_BITS", "2")
 import parity_cases as pc  # noqa: E402
 
