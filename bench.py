@@ -61,13 +61,13 @@ class ClockSampler(threading.Thread):
 
     def __init__(self, gpu_index: int):
         super().__init__(daemon=True)
-        self.gpu, self.rows, self._stop = gpu_index, [], threading.Event()
+        self.gpu, self.rows, self._halt = gpu_index, [], threading.Event()
 
     def run(self):
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
              "clocks_event_reasons.sw_power_cap")
-        while not self._stop.is_set():
+        while not self._halt.is_set():
             try:
                 out = subprocess.run(
                     ["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits",
@@ -75,10 +75,10 @@ class ClockSampler(threading.Thread):
                 self.rows.append([x.strip() for x in out.strip().split(",")])
             except Exception:
                 pass
-            self._stop.wait(0.2)
+            self._halt.wait(0.2)
 
     def stop(self):
-        self._stop.set()
+        self._halt.set()
         self.join(timeout=3)
         sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
         mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]

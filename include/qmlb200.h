@@ -88,6 +88,17 @@ extern "C" {
 #define QMLB_OBS_DIAG 1    /* diagonal: obs_consts[a0] holds 2^k complex      */
 #define QMLB_OBS_DENSE 2   /* dense:    obs_consts[a0] holds 4^k complex      */
 
+#define QMLB_SRC_PRE 6    /* hoisted 2x2 factor pre[a2]: depends on argument slot a1 only;
+                             a0 = its index among the pre entries of that slot.  Read
+                             from a per-row table filled by the precompute kernel when
+                             the slot has fewer distinct rows than the batch, else
+                             evaluated inline                                         */
+
+/* source flags */
+#define QMLB_FLAG_CONJ 1     /* TABLE: conjugate                                      */
+#define QMLB_FLAG_DIAGVEC 2  /* CONST: 2^k diagonal entries instead of a matrix       */
+#define QMLB_FLAG_ROT_SHIFT 2 /* TRIG, k = 1: bits 2-3 = 1/2/3 -> exactly RX/RY/RZ    */
+
 #define QMLB_MAX_OP_BITS 8
 #define QMLB_MAX_ARGS 8
 
@@ -111,6 +122,12 @@ typedef struct {
   int32_t arg, offset;
   double coeff;
 } qmlb_term;
+
+/* hoisted factor: 2x2 source `src` (elementary or chain of elementary sources)
+ * that depends only on argument slot `arg`; `local` = index within that slot */
+typedef struct {
+  int32_t src, arg, local, pad;
+} qmlb_pre;
 
 typedef struct {
   int32_t kind, k, a0, pad;
@@ -145,6 +162,8 @@ typedef struct {
   int32_t n_obs;
   const double* obs_consts;
   int64_t n_obs_consts;
+  const qmlb_pre* pre;
+  int32_t n_pre;
 } qmlb_program_desc;
 
 typedef struct qmlb_program qmlb_program;
@@ -164,8 +183,10 @@ int qmlb_program_destroy(qmlb_program* prog);
 int qmlb_program_info(const qmlb_program* prog, int32_t* strategy, int32_t* n_passes,
                       int32_t* n_device_ops);
 
-/* Bytes of scratch `qmlb_run` needs for `batch` elements (may be 0). */
-size_t qmlb_workspace_bytes(const qmlb_program* prog, int64_t batch);
+/* Bytes of scratch `qmlb_run` needs for `batch` elements with these arguments
+ * (hoisted-factor tables + state + reduction partials; may be 0). */
+size_t qmlb_workspace_bytes(const qmlb_program* prog, const qmlb_arg* args, int32_t n_args,
+                            int64_t batch);
 
 /* Evolves `batch` elements with global indices batch_offset .. batch_offset+batch-1
  * (the offset only enters the argument row computation, so a chunk or a rank's

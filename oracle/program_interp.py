@@ -11,7 +11,7 @@ product: ``Script.execute`` only ever calls the CUDA library.
 import numpy as np
 
 OP_MAT, OP_CTRL1, OP_PERM, OP_DIAG = 0, 1, 2, 3
-SRC_CONST, SRC_TRIG, SRC_CHAIN, SRC_DIAGPH, SRC_TABLE, SRC_SUPER = 0, 1, 2, 3, 4, 5
+SRC_CONST, SRC_TRIG, SRC_CHAIN, SRC_DIAGPH, SRC_TABLE, SRC_SUPER, SRC_PRE = 0, 1, 2, 3, 4, 5, 6
 OBS_ZSTRING, OBS_DIAG, OBS_DENSE = 0, 1, 2
 
 
@@ -68,6 +68,12 @@ class Interp:
             m = rows[:, 2 * s["a1"] : 2 * s["a1"] + 2 * d * d].copy().view(np.complex128)
             m = m.reshape(self.B, d, d)
             return m.conj() if s["flags"] & 1 else m
+        if kind == SRC_PRE:
+            # hoisted factor: same value as the source it was hoisted from, evaluated for
+            # the row of argument a1 this element reads (table lookup on the device)
+            pre = self.p.pre[s["a2"]]
+            assert pre["arg"] == s["a1"] and pre["local"] == s["a0"]
+            return self.source(pre["src"])
         if kind == SRC_SUPER:
             ids = self.p.items[s["a0"] : s["a0"] + s["a1"]]
             S = np.eye(4, dtype=np.complex128)[None]

@@ -59,6 +59,7 @@ class _Desc(C.Structure):
         ("consts", C.c_void_p), ("n_consts", C.c_int64),
         ("obs", C.c_void_p), ("n_obs", C.c_int32),
         ("obs_consts", C.c_void_p), ("n_obs_consts", C.c_int64),
+        ("pre", C.c_void_p), ("n_pre", C.c_int32),
     ]
 
 
@@ -78,7 +79,7 @@ def load_library(path: str = LIB_PATH) -> C.CDLL:
     lib.qmlb_program_destroy.argtypes = [C.c_void_p]
     lib.qmlb_program_info.argtypes = [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32),
                                       C.POINTER(C.c_int32)]
-    lib.qmlb_workspace_bytes.argtypes = [C.c_void_p, C.c_int64]
+    lib.qmlb_workspace_bytes.argtypes = [C.c_void_p, C.POINTER(_Arg), C.c_int32, C.c_int64]
     lib.qmlb_workspace_bytes.restype = C.c_size_t
     lib.qmlb_run.argtypes = [C.c_void_p, C.POINTER(_Arg), C.c_int32, C.c_int64, C.c_int64,
                              C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
@@ -105,7 +106,8 @@ class ProgramHandle:
         dt = QMLB_C128 if precision == "complex128" else QMLB_C64
         keep = [np.ascontiguousarray(x) for x in (
             prog.ops, prog.sources, prog.items, prog.angles, prog.terms, prog.consts,
-            obs_recs, obs_pool)]
+            obs_recs, obs_pool,
+            prog.pre if prog.pre is not None else np.zeros(0, dtype=compiler.PRE_DTYPE))]
         d = _Desc(
             n_qubits=prog.n_qubits, n_bits=prog.n_bits, density=int(prog.density), dtype=dt,
             out_type=int(out_type), reserved=0,
@@ -117,6 +119,7 @@ class ProgramHandle:
             consts=_np_ptr(keep[5]), n_consts=len(keep[5]),
             obs=_np_ptr(keep[6]), n_obs=len(keep[6]),
             obs_consts=_np_ptr(keep[7]), n_obs_consts=len(keep[7]),
+            pre=_np_ptr(keep[8]), n_pre=len(keep[8]),
         )
         rc = lib.qmlb_program_create(C.byref(d), C.byref(self.ptr))
         if rc != 0:
@@ -160,16 +163,16 @@ class DeviceCall:
             compiler.OUT_DENSITY: ((batch, dim, dim), cplx),
         }[handle.out_type]
         self.out = torch.empty(shape, dtype=dt, device=ex.device)
-        ws = ex.lib.qmlb_workspace_bytes(handle.ptr, self.batch)
-        self.ws_bytes = int(ws)
-        self.ws = torch.empty(max(self.ws_bytes, 1), dtype=torch.uint8, device=ex.device)
-        self.c_args = (_Arg * len(dev_args))()
+        self.c_args = (_Arg * max(len(dev_args), 1))()
         for i, a in enumerate(dev_args):
             if a is None:
                 self.c_args[i] = _Arg(None, 0, 1, 1)
             else:
                 t, div, mod = a
                 self.c_args[i] = _Arg(t.data_ptr(), t.shape[1], int(div), int(mod))
+        ws = ex.lib.qmlb_workspace_bytes(handle.ptr, self.c_args, len(dev_args), self.batch)
+        self.ws_bytes = int(ws)
+        self.ws = torch.empty(max(self.ws_bytes, 1), dtype=torch.uint8, device=ex.device)
 
     def launch(self):
         import torch

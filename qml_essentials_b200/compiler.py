@@ -48,7 +48,8 @@ from .symbolic import Sym, is_symbolic
 
 # ---- enums shared with csrc/qmlb_program.h ---------------------------------
 OP_MAT, OP_CTRL1, OP_PERM, OP_DIAG = 0, 1, 2, 3
-SRC_CONST, SRC_TRIG, SRC_CHAIN, SRC_DIAGPH, SRC_TABLE, SRC_SUPER = 0, 1, 2, 3, 4, 5
+SRC_CONST, SRC_TRIG, SRC_CHAIN, SRC_DIAGPH, SRC_TABLE, SRC_SUPER, SRC_PRE = 0, 1, 2, 3, 4, 5, 6
+FLAG_CONJ, FLAG_DIAGVEC, FLAG_ROT_SHIFT = 1, 2, 2  # flags bits 2-3: 1=RX 2=RY 3=RZ
 OUT_STATE, OUT_PROBS, OUT_EXPVAL, OUT_DENSITY = 0, 1, 2, 3
 OBS_ZSTRING, OBS_DIAG, OBS_DENSE = 0, 1, 2
 MAX_OP_BITS = 8
@@ -63,6 +64,7 @@ SRC_DTYPE = np.dtype(
 )
 ANGLE_DTYPE = np.dtype([("first", "<i4"), ("n", "<i4"), ("c0", "<f8")])
 TERM_DTYPE = np.dtype([("arg", "<i4"), ("offset", "<i4"), ("coeff", "<f8")])
+PRE_DTYPE = np.dtype([("src", "<i4"), ("arg", "<i4"), ("local", "<i4"), ("pad", "<i4")])
 OBS_DTYPE = np.dtype(
     [("kind", "<i4"), ("k", "<i4"), ("a0", "<i4"), ("pad", "<i4"), ("zmask", "<i8"),
      ("bits", "<i4", (MAX_OP_BITS,))]
@@ -89,6 +91,7 @@ class Program:
     terms: np.ndarray
     consts: np.ndarray  # float64 pool (complex entries interleaved re, im)
     n_args: int  # number of batched argument slots referenced by terms / tables
+    pre: np.ndarray = None  # hoisted batch-invariant 2x2 factors (see _Builder.hoist)
     n_tape_ops: int = 0
     meta: dict = field(default_factory=dict)
 
@@ -171,7 +174,7 @@ class _Builder:
             return self.add_source(
                 SRC_TRIG, k, a0=self.add_complex(spec.C0), a1=self.add_complex(spec.A),
                 a2=self.add_complex(spec.B), angle=self.add_angle(spec.theta),
-                kappa=spec.kappa,
+                kappa=spec.kappa, flags=_rotation_axis(spec) << FLAG_ROT_SHIFT,
             )
         if isinstance(spec, _TableMat):
             self.max_arg = max(self.max_arg, spec.arg)
@@ -202,6 +205,120 @@ class _Builder:
         first = len(self.items)
         self.items.extend(ids)
         return self.add_source(SRC_SUPER, 2, a0=first, a1=len(ids))
+
+
+def _hoist(b: "_Builder"):
+    """Hoist batch-invariant factors out of the per-element work.
+
+    Every 2x2 factor of a fused chain depends (through its angle) on the rows of
+    some argument slots.  A maximal run of factors that depends on exactly ONE
+    slot (constants ride along) is the same for every batch element that reads
+    the same row of that slot - e.g. in BASELINE config 2 the RY.RZ.RY product of
+    a layer depends only on the parameter sample (1024 distinct values) and the
+    encoding RX only on the grid point (264 values), while the batch has 270 336
+    elements.  Such runs become `pre` entries: a precompute kernel evaluates them
+    once per distinct row into a table and the main program reads them through
+    SRC_PRE sources (or evaluates them inline when the slot is per-element).
+    """
+    src, items = b.sources, b.items
+
+    def angle_slots(aid):
+        first, n, _ = b.angles[aid]
+        return frozenset(a for (a, _o, _c) in b.terms[first:first + n])
+
+    def elem_slots(sid):
+        kind = src[sid][0]
+        if kind == SRC_CONST:
+            return frozenset()
+        if kind == SRC_TRIG:
+            return angle_slots(src[sid][5])
+        return None  # TABLE etc.: never hoisted
+
+    pre = []
+    counts = {}
+
+    def make_pre(seg_src, slot):
+        local = counts.get(slot, 0)
+        counts[slot] = local + 1
+        pre.append((seg_src, slot, local, 0))
+        return (SRC_PRE, 1, local, slot, len(pre) - 1, -1, 0, 0, 0.0)
+
+    chain_items = set()
+    n_src0 = len(src)
+    for sid in range(n_src0):
+        if src[sid][0] != SRC_CHAIN:
+            continue
+        ids = items[src[sid][2]: src[sid][2] + src[sid][3]]
+        chain_items.update(ids)
+        parts, cur, cur_slot, pend = [], [], None, []
+        for i in ids:
+            d = elem_slots(i)
+            if d is not None and len(d) == 0:
+                (cur if cur else pend).append(i)
+                continue
+            if d is None or len(d) > 1:
+                if cur:
+                    parts.append(("seg", cur_slot, cur))
+                for c in pend:
+                    parts.append(("inline", None, [c]))
+                parts.append(("inline", None, [i]))
+                cur, cur_slot, pend = [], None, []
+                continue
+            (slot,) = d
+            if cur and slot == cur_slot:
+                cur.append(i)
+            else:
+                if cur:
+                    parts.append(("seg", cur_slot, cur))
+                cur, cur_slot, pend = pend + [i], slot, []
+        if cur:
+            parts.append(("seg", cur_slot, cur))
+        for c in pend:
+            parts.append(("inline", None, [c]))
+        if not any(p[0] == "seg" for p in parts):
+            continue
+        new_ids = []
+        for kind, slot, seg in parts:
+            if kind == "inline":
+                new_ids.extend(seg)
+                continue
+            if len(seg) == 1:
+                seg_src = seg[0]
+            else:
+                first = len(items)
+                items.extend(seg)
+                src.append((SRC_CHAIN, 1, first, len(seg), 0, -1, 0, 0, 0.0))
+                seg_src = len(src) - 1
+            src.append(make_pre(seg_src, slot))
+            new_ids.append(len(src) - 1)
+        if len(new_ids) == 1:
+            src[sid] = src[new_ids[0]]
+        else:
+            first = len(items)
+            items.extend(new_ids)
+            src[sid] = (SRC_CHAIN, 1, first, len(new_ids), 0, -1, 0, 0, 0.0)
+    # elementary 2x2 TRIG sources referenced directly (ops, CTRL1, superchain items)
+    for sid in range(n_src0):
+        rec = src[sid]
+        if rec[0] == SRC_TRIG and rec[1] == 1 and sid not in chain_items:
+            d = elem_slots(sid)
+            if d is not None and len(d) == 1:
+                src.append(rec)
+                src[sid] = make_pre(len(src) - 1, next(iter(d)))
+    return pre
+
+
+_PAULIS = (np.array([[0, 1], [1, 0]]), np.array([[0, -1j], [1j, 0]]), np.array([[1, 0], [0, -1]]))
+
+
+def _rotation_axis(spec) -> int:
+    """1/2/3 if spec is exactly cos(k t) I - i sin(k t) {X,Y,Z} (kernel fast path)."""
+    if spec.C0.shape != (2, 2) or np.any(spec.C0 != 0) or not np.array_equal(spec.A, np.eye(2)):
+        return 0
+    for axis, P in enumerate(_PAULIS):
+        if np.array_equal(spec.B, -1j * P):
+            return axis + 1
+    return 0
 
 
 class _TableMat:
@@ -484,6 +601,7 @@ class _Lowerer:
     def finish(self, n_tape_ops: int) -> Program:
         self.flush(sorted(self.pending))
         b = self.b
+        pre = _hoist(b)
         ops = np.zeros(len(b.ops), dtype=OP_DTYPE)
         for i, (kind, k, src, aux, bits) in enumerate(b.ops):
             ops[i] = (kind, k, src, aux, bits)
@@ -498,6 +616,7 @@ class _Lowerer:
             terms=np.array(b.terms, dtype=TERM_DTYPE),
             consts=np.array(b.consts, dtype=np.float64),
             n_args=b.max_arg + 1,
+            pre=np.array(pre, dtype=PRE_DTYPE),
             n_tape_ops=n_tape_ops,
         )
 

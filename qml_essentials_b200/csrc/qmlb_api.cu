@@ -61,7 +61,7 @@ int validate(const qmlb_program_desc* d, qmlb_program* p) {
                 "Measurement type 'state' is not defined for mixed (noisy) circuits");
   for (int i = 0; i < d->n_sources; ++i) {
     const qmlb_source& s = d->sources[i];
-    if (s.kind < 0 || s.kind > QMLB_SRC_SUPER || s.k < 1 || s.k > QMLB_MAX_OP_BITS)
+    if (s.kind < 0 || s.kind > QMLB_SRC_PRE || s.k < 1 || s.k > QMLB_MAX_OP_BITS)
       return fail(QMLB_ERR_INVALID, "bad source record");
     if ((s.kind == QMLB_SRC_TRIG || s.kind == QMLB_SRC_DIAGPH) &&
         (s.angle < 0 || s.angle >= d->n_angles))
@@ -74,7 +74,7 @@ int validate(const qmlb_program_desc* d, qmlb_program* p) {
         if (id < 0 || id >= d->n_sources) return fail(QMLB_ERR_INVALID, "bad chain item");
         const qmlb_source& it = d->sources[id];
         bool elem1 = it.k == 1 && (it.kind == QMLB_SRC_CONST || it.kind == QMLB_SRC_TRIG ||
-                                   it.kind == QMLB_SRC_TABLE);
+                                   it.kind == QMLB_SRC_TABLE || it.kind == QMLB_SRC_PRE);
         if (s.kind == QMLB_SRC_CHAIN && !elem1)
           return fail(QMLB_ERR_INVALID, "chain item must be an elementary 2x2 source");
         if (s.kind == QMLB_SRC_SUPER && !elem1 &&
@@ -86,6 +86,48 @@ int validate(const qmlb_program_desc* d, qmlb_program* p) {
     if (s.kind == QMLB_SRC_TABLE) {
       if (s.a0 < 0 || s.a0 >= QMLB_MAX_ARGS) return fail(QMLB_ERR_INVALID, "bad table arg");
       p->max_arg = std::max(p->max_arg, s.a0);
+    }
+    if (s.kind == QMLB_SRC_PRE) {
+      if (s.k != 1 || s.a2 < 0 || s.a2 >= d->n_pre || d->pre[s.a2].arg != s.a1 ||
+          d->pre[s.a2].local != s.a0)
+        return fail(QMLB_ERR_INVALID, "hoisted source does not match its pre entry");
+    }
+  }
+  {
+    int count[QMLB_MAX_ARGS] = {0};
+    for (int i = 0; i < d->n_pre; ++i) {
+      const qmlb_pre& e = d->pre[i];
+      if (e.arg < 0 || e.arg >= QMLB_MAX_ARGS || e.src < 0 || e.src >= d->n_sources)
+        return fail(QMLB_ERR_INVALID, "bad pre entry");
+      if (e.local != count[e.arg]++)
+        return fail(QMLB_ERR_INVALID, "pre entries of a slot must be numbered in order");
+      // the hoisted source: elementary 2x2 or a chain of elementary 2x2 (no nesting)
+      const qmlb_source& h = d->sources[e.src];
+      auto elem = [&](const qmlb_source& it) {
+        return it.k == 1 && (it.kind == QMLB_SRC_CONST || it.kind == QMLB_SRC_TRIG);
+      };
+      bool ok = elem(h);
+      if (h.kind == QMLB_SRC_CHAIN && h.k == 1) {
+        ok = h.a0 >= 0 && h.a1 >= 1 && h.a0 + h.a1 <= d->n_items;
+        for (int t = 0; ok && t < h.a1; ++t) {
+          int id = d->items[h.a0 + t];
+          ok = id >= 0 && id < d->n_sources && elem(d->sources[id]);
+        }
+      }
+      if (!ok) return fail(QMLB_ERR_INVALID, "pre entry must hoist elementary 2x2 sources");
+      // ... whose angles read slot `arg` only
+      auto slot_ok = [&](const qmlb_source& it) {
+        if (it.kind != QMLB_SRC_TRIG) return true;
+        if (it.angle < 0 || it.angle >= d->n_angles) return false;
+        const qmlb_angle& a = d->angles[it.angle];
+        for (int t = 0; t < a.n; ++t)
+          if (a.first + t >= d->n_terms || d->terms[a.first + t].arg != e.arg) return false;
+        return true;
+      };
+      ok = slot_ok(h);
+      if (h.kind == QMLB_SRC_CHAIN)
+        for (int t = 0; ok && t < h.a1; ++t) ok = slot_ok(d->sources[d->items[h.a0 + t]]);
+      if (!ok) return fail(QMLB_ERR_INVALID, "pre entry reads another argument slot");
     }
   }
   for (int i = 0; i < d->n_terms; ++i) {
@@ -226,7 +268,10 @@ int upload(qmlb_program* p) {
   size_t o_ops = place(off, p->ops), o_src = place(off, p->sources),
          o_items = place(off, p->items), o_ang = place(off, p->angles),
          o_terms = place(off, p->terms), o_consts = place(off, p->consts),
-         o_obs = place(off, p->obs), o_oc = place(off, p->obs_consts);
+         o_obs = place(off, p->obs), o_oc = place(off, p->obs_consts),
+         o_pre = place(off, p->pre);
+  size_t o_ids[QMLB_MAX_ARGS];
+  for (int a = 0; a < QMLB_MAX_ARGS; ++a) o_ids[a] = place(off, p->pre_ids[a]);
   struct PO {
     size_t ops, matoff, win;
   };
@@ -249,6 +294,9 @@ int upload(qmlb_program* p) {
   put(o_consts, p->consts.data(), p->consts.size() * sizeof(double));
   put(o_obs, p->obs.data(), p->obs.size() * sizeof(qmlb_obs));
   put(o_oc, p->obs_consts.data(), p->obs_consts.size() * sizeof(double));
+  put(o_pre, p->pre.data(), p->pre.size() * sizeof(qmlb_pre));
+  for (int a = 0; a < QMLB_MAX_ARGS; ++a)
+    put(o_ids[a], p->pre_ids[a].data(), p->pre_ids[a].size() * sizeof(int32_t));
   for (size_t i = 0; i < p->passes.size(); ++i) {
     put(po[i].ops, p->passes[i].ops.data(), p->passes[i].ops.size() * sizeof(qmlb_op));
     put(po[i].matoff, p->passes[i].matoff.data(), p->passes[i].matoff.size() * 4);
@@ -266,6 +314,10 @@ int upload(qmlb_program* p) {
   d.consts = reinterpret_cast<const double*>(base + o_consts);
   d.obs = reinterpret_cast<const qmlb_obs*>(base + o_obs);
   d.obs_consts = reinterpret_cast<const double*>(base + o_oc);
+  d.pre = reinterpret_cast<const qmlb_pre*>(base + o_pre);
+  d.n_pre = (int)p->pre.size();
+  for (int a = 0; a < QMLB_MAX_ARGS; ++a)
+    p->pre_ids_dev[a] = reinterpret_cast<const int32_t*>(base + o_ids[a]);
   d.n_ops = (int)p->ops.size();
   d.n_obs = (int)p->obs.size();
   d.n_bits = p->n_bits;
@@ -439,21 +491,58 @@ int launch_measure(const qmlb_program* p, const cx<T>* state, int64_t batch, voi
   return QMLB_OK;
 }
 
-template <typename T>
-int run_typed(const qmlb_program* p, const RunArgs& R, void* out, void* workspace,
-              size_t ws_bytes, cudaStream_t st) {
-  const size_t cs = cs_of(p->dtype);
-  const size_t state_bytes = p->direct_out ? 0 : (size_t)R.batch * (size_t(1) << p->n_bits) * cs;
-  size_t need = state_bytes;
-  const int chunks = expval_chunks(p, R.batch);
-  size_t part_off = (need + 255) & ~size_t(255);
+// Hoisted-factor tables: slot a gets one when it has fewer distinct rows than half the
+// batch (otherwise its factors are evaluated inline).  Returns the bytes used.
+size_t pre_layout(const qmlb_program* p, const qmlb_arg* a, int64_t batch, bool on[QMLB_MAX_ARGS],
+                  size_t off[QMLB_MAX_ARGS]) {
+  size_t total = 0;
+  for (int s = 0; s < QMLB_MAX_ARGS; ++s) {
+    on[s] = false;
+    off[s] = 0;
+    const size_t n = p->pre_ids[s].size();
+    if (n == 0 || a[s].mod * 2 > batch) continue;
+    on[s] = true;
+    off[s] = total;
+    total += (n * (size_t)a[s].mod * 4 * cs_of(p->dtype) + 255) & ~size_t(255);
+  }
+  return total;
+}
+
+size_t state_layout(const qmlb_program* p, int64_t batch, size_t* part_off) {
+  size_t need = p->direct_out ? 0 : (size_t)batch * (size_t(1) << p->n_bits) * cs_of(p->dtype);
+  *part_off = (need + 255) & ~size_t(255);
+  const int chunks = expval_chunks(p, batch);
   if (!p->direct_out && chunks > 1)
-    need = part_off + (size_t)R.batch * p->obs.size() * chunks * rs_of(p->dtype);
+    need = *part_off + (size_t)batch * p->obs.size() * chunks * rs_of(p->dtype);
+  return (need + 255) & ~size_t(255);
+}
+
+template <typename T>
+int run_typed(const qmlb_program* p, RunArgs& R, void* out, void* workspace, size_t ws_bytes,
+              cudaStream_t st) {
+  bool on[QMLB_MAX_ARGS];
+  size_t toff[QMLB_MAX_ARGS], part_off = 0;
+  const size_t tab_bytes = pre_layout(p, R.a, R.batch, on, toff);
+  const size_t need = tab_bytes + state_layout(p, R.batch, &part_off);
   if (need > ws_bytes) return fail(QMLB_ERR_WORKSPACE, "workspace too small");
-  cx<T>* state = p->direct_out ? static_cast<cx<T>*>(out) : static_cast<cx<T>*>(workspace);
+  unsigned char* wsb = static_cast<unsigned char*>(workspace);
+  for (int s = 0; s < QMLB_MAX_ARGS; ++s) {
+    R.pre_on[s] = on[s];
+    R.pre_tab[s] = on[s] ? wsb + toff[s] : nullptr;
+  }
+  for (int s = 0; s < QMLB_MAX_ARGS; ++s) {
+    if (!on[s]) continue;
+    const int n_ids = (int)p->pre_ids[s].size();
+    const int64_t total = (int64_t)n_ids * R.a[s].mod;
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    k_pre<T><<<(unsigned)((total + 127) / 128), 128, 0, st>>>(
+        p->dev, R, s, p->pre_ids_dev[s], n_ids, reinterpret_cast<cx<T>*>(wsb + toff[s]));
+  }
+  unsigned char* ws_state = wsb + tab_bytes;
+  cx<T>* state = p->direct_out ? static_cast<cx<T>*>(out) : reinterpret_cast<cx<T>*>(ws_state);
 
   if (p->strategy == 0) {
-    void* dst = p->direct_out ? out : workspace;
+    void* dst = p->direct_out ? out : static_cast<void*>(ws_state);
     CUDA_TRY((std::is_same<T, double>::value ? launch_reg_f64 : launch_reg_f32)(p, R, dst, st));
   } else {
     for (const QmlbPassHost& ps : p->passes) {
@@ -467,8 +556,7 @@ int run_typed(const qmlb_program* p, const RunArgs& R, void* out, void* workspac
     }
   }
   if (!p->direct_out)
-    return launch_measure<T>(p, state, R.batch, out,
-                             static_cast<unsigned char*>(workspace) + part_off, st);
+    return launch_measure<T>(p, state, R.batch, out, ws_state + part_off, st);
   return QMLB_OK;
 }
 
@@ -510,6 +598,8 @@ int qmlb_program_create(const qmlb_program_desc* d, qmlb_program** out) {
   p->consts.assign(d->consts, d->consts + d->n_consts);
   p->obs.assign(d->obs, d->obs + d->n_obs);
   p->obs_consts.assign(d->obs_consts, d->obs_consts + d->n_obs_consts);
+  if (d->n_pre > 0) p->pre.assign(d->pre, d->pre + d->n_pre);
+  for (int i = 0; i < (int)p->pre.size(); ++i) p->pre_ids[p->pre[i].arg].push_back(i);
   rc = plan(p);
   if (rc == QMLB_OK) rc = upload(p);
   if (rc == QMLB_OK) rc = set_smem_attr(p);
@@ -538,16 +628,19 @@ int qmlb_program_info(const qmlb_program* p, int32_t* strategy, int32_t* n_passe
   return QMLB_OK;
 }
 
-size_t qmlb_workspace_bytes(const qmlb_program* p, int64_t batch) {
+size_t qmlb_workspace_bytes(const qmlb_program* p, const qmlb_arg* args, int32_t n_args,
+                            int64_t batch) {
   if (!p || batch <= 0) return 0;
-  if (p->direct_out) return 0;
-  size_t need = (size_t)batch * (size_t(1) << p->n_bits) * cs_of(p->dtype);
-  const int chunks = expval_chunks(p, batch);
-  if (chunks > 1) {
-    need = (need + 255) & ~size_t(255);
-    need += (size_t)batch * p->obs.size() * chunks * rs_of(p->dtype);
+  qmlb_arg a[QMLB_MAX_ARGS];
+  for (int i = 0; i < QMLB_MAX_ARGS; ++i) {
+    a[i].ptr = nullptr;
+    a[i].stride = 0;
+    a[i].div = 1;
+    a[i].mod = (i < n_args && args && args[i].mod >= 1) ? args[i].mod : 1;
   }
-  return need;
+  bool on[QMLB_MAX_ARGS];
+  size_t toff[QMLB_MAX_ARGS], part_off = 0;
+  return pre_layout(p, a, batch, on, toff) + state_layout(p, batch, &part_off);
 }
 
 int qmlb_run(const qmlb_program* p, const qmlb_arg* args, int32_t n_args, int64_t batch,
@@ -566,6 +659,7 @@ int qmlb_run(const qmlb_program* p, const qmlb_arg* args, int32_t n_args, int64_
   for (int i = 0; i < n_args; ++i) {
     R.a[i] = args[i];
     if (R.a[i].div < 1 || R.a[i].mod < 1) return fail(QMLB_ERR_INVALID, "arg div/mod < 1");
+    if (R.a[i].mod > 0x7fffffffLL) return fail(QMLB_ERR_UNSUPPORTED, "argument with >= 2^31 rows");
   }
   for (const auto& t : p->terms)
     if (!R.a[t.arg].ptr) return fail(QMLB_ERR_INVALID, "program reads a NULL argument");

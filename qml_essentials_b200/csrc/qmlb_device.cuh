@@ -55,28 +55,41 @@ struct DevProg {
   const double* consts;
   const qmlb_obs* obs;
   const double* obs_consts;
-  int32_t n_ops, n_obs, n_bits, n_qubits, density, out_type;
+  const qmlb_pre* pre;
+  int32_t n_ops, n_obs, n_bits, n_qubits, density, out_type, n_pre, pad;
 };
 
 struct RunArgs {
   qmlb_arg a[QMLB_MAX_ARGS];
   int64_t batch;         // elements in this launch
   int64_t batch_offset;  // global index of element 0
+  const void* pre_tab[QMLB_MAX_ARGS];  // per slot: [n_pre_slot][mod][4] complex, or unused
+  int32_t pre_on[QMLB_MAX_ARGS];       // 1: read hoisted factors from pre_tab, 0: inline
 };
 
-__device__ __forceinline__ const double* arg_row(const RunArgs& R, int arg, int64_t b) {
-  const qmlb_arg& a = R.a[arg];
-  int64_t row = (b / a.div) % a.mod;
-  return a.ptr + row * a.stride;
+// Row of argument `a` that batch element b reads.  Kernels that evaluate many
+// angles per element cache these (the 64-bit div/mod is expensive).
+struct RowsDirect {
+  const RunArgs& R;
+  int64_t b;
+  __device__ __forceinline__ int64_t operator()(int a) const {
+    return (b / R.a[a].div) % R.a[a].mod;
+  }
+};
+
+template <typename Rows>
+__device__ __forceinline__ const double* arg_row(const RunArgs& R, const Rows& rows, int arg) {
+  return R.a[arg].ptr + rows(arg) * R.a[arg].stride;
 }
 
-__device__ __forceinline__ double eval_angle(const DevProg& P, const RunArgs& R, int aid,
-                                             int64_t b) {
+template <typename Rows>
+__device__ __forceinline__ double eval_angle(const DevProg& P, const RunArgs& R,
+                                             const Rows& rows, int aid) {
   qmlb_angle a = P.ang[aid];
   double th = a.c0;
   for (int t = 0; t < a.n; ++t) {
     qmlb_term tm = P.terms[a.first + t];
-    th = fma(tm.coeff, arg_row(R, tm.arg, b)[tm.offset], th);
+    th = fma(tm.coeff, arg_row(R, rows, tm.arg)[tm.offset], th);
   }
   return th;
 }
@@ -87,26 +100,36 @@ __device__ __forceinline__ cx<T> ld_const(const double* consts, int off) {
   return mk<T>((T)v.x, (T)v.y);
 }
 
-// 2x2 "elementary" source (CONST / TRIG / TABLE with k = 1) into registers.
-template <typename T>
+// 2x2 elementary source (CONST / TRIG / TABLE, k = 1) into registers.
+template <typename T, typename Rows>
 __device__ __forceinline__ void eval_elem2(const DevProg& P, const RunArgs& R,
-                                           const qmlb_source& s, int64_t b, cx<T> m[4]) {
-  if (s.kind == QMLB_SRC_CONST) {
+                                           const Rows& rows, const qmlb_source& s,
+                                           cx<T> m[4]) {
+  if (s.kind == QMLB_SRC_TRIG) {
+    T sn, cs;
+    sincos_t((T)(eval_angle(P, R, rows, s.angle) * s.kappa), &sn, &cs);
+    const int axis = (s.flags >> QMLB_FLAG_ROT_SHIFT) & 3;
+    if (axis == 1) {  // RX
+      m[0] = mk<T>(cs, 0); m[1] = mk<T>(0, -sn); m[2] = mk<T>(0, -sn); m[3] = mk<T>(cs, 0);
+    } else if (axis == 2) {  // RY
+      m[0] = mk<T>(cs, 0); m[1] = mk<T>(-sn, 0); m[2] = mk<T>(sn, 0); m[3] = mk<T>(cs, 0);
+    } else if (axis == 3) {  // RZ
+      m[0] = mk<T>(cs, -sn); m[1] = mk<T>(0, 0); m[2] = mk<T>(0, 0); m[3] = mk<T>(cs, sn);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        cx<T> c0 = ld_const<T>(P.consts, s.a0 + i);
+        cx<T> a = ld_const<T>(P.consts, s.a1 + i);
+        cx<T> bb = ld_const<T>(P.consts, s.a2 + i);
+        m[i] = mk<T>(c0.x + cs * a.x + sn * bb.x, c0.y + cs * a.y + sn * bb.y);
+      }
+    }
+  } else if (s.kind == QMLB_SRC_CONST) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) m[i] = ld_const<T>(P.consts, s.a0 + i);
-  } else if (s.kind == QMLB_SRC_TRIG) {
-    T sn, cs;
-    sincos_t((T)(eval_angle(P, R, s.angle, b) * s.kappa), &sn, &cs);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      cx<T> c0 = ld_const<T>(P.consts, s.a0 + i);
-      cx<T> a = ld_const<T>(P.consts, s.a1 + i);
-      cx<T> bb = ld_const<T>(P.consts, s.a2 + i);
-      m[i] = mk<T>(c0.x + cs * a.x + sn * bb.x, c0.y + cs * a.y + sn * bb.y);
-    }
   } else {  // QMLB_SRC_TABLE
-    const double2* row = reinterpret_cast<const double2*>(arg_row(R, s.a0, b)) + s.a1;
-    T sg = (s.flags & 1) ? (T)-1 : (T)1;
+    const double2* row = reinterpret_cast<const double2*>(arg_row(R, rows, s.a0)) + s.a1;
+    T sg = (s.flags & QMLB_FLAG_CONJ) ? (T)-1 : (T)1;
 #pragma unroll
     for (int i = 0; i < 4; ++i) m[i] = mk<T>((T)row[i].x, sg * (T)row[i].y);
   }
@@ -128,39 +151,82 @@ __device__ __forceinline__ void mul2_left(const cx<T> f[4], cx<T> m[4]) {
   for (int i = 0; i < 4; ++i) m[i] = r[i];
 }
 
-// Any k = 1 source (elementary or CHAIN) into registers.
-template <typename T>
-__device__ __forceinline__ void eval_2x2(const DevProg& P, const RunArgs& R, int sid,
-                                         int64_t b, cx<T> m[4]) {
+// k = 1 source made of elementary items only (elementary itself or a CHAIN of them)
+template <typename T, typename Rows>
+__device__ __forceinline__ void eval_2x2_base(const DevProg& P, const RunArgs& R,
+                                              const Rows& rows, int sid, cx<T> m[4]) {
   qmlb_source s = P.src[sid];
   if (s.kind != QMLB_SRC_CHAIN) {
-    eval_elem2<T>(P, R, s, b, m);
+    eval_elem2<T>(P, R, rows, s, m);
     return;
   }
-  eval_elem2<T>(P, R, P.src[P.items[s.a0]], b, m);
+  eval_elem2<T>(P, R, rows, P.src[P.items[s.a0]], m);
   for (int i = 1; i < s.a1; ++i) {
     cx<T> f[4];
-    eval_elem2<T>(P, R, P.src[P.items[s.a0 + i]], b, f);
+    eval_elem2<T>(P, R, rows, P.src[P.items[s.a0 + i]], f);
+    mul2_left<T>(f, m);
+  }
+}
+
+// one chain item: elementary, or a hoisted factor (table lookup / inline)
+template <typename T, typename Rows>
+__device__ __forceinline__ void eval_item2(const DevProg& P, const RunArgs& R,
+                                           const Rows& rows, const qmlb_source& s,
+                                           cx<T> m[4]) {
+  if (s.kind == QMLB_SRC_PRE) {
+    if (R.pre_on[s.a1]) {
+      const cx<T>* t = static_cast<const cx<T>*>(R.pre_tab[s.a1]) +
+                       ((int64_t)s.a0 * R.a[s.a1].mod + rows(s.a1)) * 4;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) m[i] = t[i];
+    } else {
+      eval_2x2_base<T>(P, R, rows, P.pre[s.a2].src, m);
+    }
+  } else {
+    eval_elem2<T>(P, R, rows, s, m);
+  }
+}
+
+// Any k = 1 source into registers.
+template <typename T, typename Rows>
+__device__ __forceinline__ void eval_2x2(const DevProg& P, const RunArgs& R, const Rows& rows,
+                                         int sid, cx<T> m[4]) {
+  qmlb_source s = P.src[sid];
+  if (s.kind != QMLB_SRC_CHAIN) {
+    eval_item2<T>(P, R, rows, s, m);
+    return;
+  }
+  eval_item2<T>(P, R, rows, P.src[P.items[s.a0]], m);
+  for (int i = 1; i < s.a1; ++i) {
+    cx<T> f[4];
+    eval_item2<T>(P, R, rows, P.src[P.items[s.a0 + i]], f);
     mul2_left<T>(f, m);
   }
 }
 
 // Generic source into memory `out` (4^k entries row-major, or 2^k for diagonal
 // sources).  Executed by ONE thread per source; `out` may be shared or local.
-template <typename T>
-__device__ void eval_source_mem(const DevProg& P, const RunArgs& R, int sid, int64_t b,
+template <typename T, typename Rows>
+__device__ void eval_source_mem(const DevProg& P, const RunArgs& R, const Rows& rows, int sid,
                                 cx<T>* out) {
   qmlb_source s = P.src[sid];
   const int d = 1 << s.k;
   switch (s.kind) {
     case QMLB_SRC_CONST: {
-      int n = (s.flags & 2) ? d : d * d;
+      int n = (s.flags & QMLB_FLAG_DIAGVEC) ? d : d * d;
       for (int i = 0; i < n; ++i) out[i] = ld_const<T>(P.consts, s.a0 + i);
       break;
     }
     case QMLB_SRC_TRIG: {
+      if (s.k == 1) {
+        cx<T> m[4];
+        eval_elem2<T>(P, R, rows, s, m);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) out[i] = m[i];
+        break;
+      }
       T sn, cs;
-      sincos_t((T)(eval_angle(P, R, s.angle, b) * s.kappa), &sn, &cs);
+      sincos_t((T)(eval_angle(P, R, rows, s.angle) * s.kappa), &sn, &cs);
       for (int i = 0; i < d * d; ++i) {
         cx<T> c0 = ld_const<T>(P.consts, s.a0 + i);
         cx<T> a = ld_const<T>(P.consts, s.a1 + i);
@@ -169,15 +235,16 @@ __device__ void eval_source_mem(const DevProg& P, const RunArgs& R, int sid, int
       }
       break;
     }
+    case QMLB_SRC_PRE:
     case QMLB_SRC_CHAIN: {
       cx<T> m[4];
-      eval_2x2<T>(P, R, sid, b, m);
+      eval_2x2<T>(P, R, rows, sid, m);
 #pragma unroll
       for (int i = 0; i < 4; ++i) out[i] = m[i];
       break;
     }
     case QMLB_SRC_DIAGPH: {
-      double th = eval_angle(P, R, s.angle, b);
+      double th = eval_angle(P, R, rows, s.angle);
       for (int i = 0; i < d; ++i) {
         T sn, cs;
         sincos_t((T)(-P.consts[s.a0 + i] * th), &sn, &cs);
@@ -186,8 +253,8 @@ __device__ void eval_source_mem(const DevProg& P, const RunArgs& R, int sid, int
       break;
     }
     case QMLB_SRC_TABLE: {
-      const double2* row = reinterpret_cast<const double2*>(arg_row(R, s.a0, b)) + s.a1;
-      T sg = (s.flags & 1) ? (T)-1 : (T)1;
+      const double2* row = reinterpret_cast<const double2*>(arg_row(R, rows, s.a0)) + s.a1;
+      T sg = (s.flags & QMLB_FLAG_CONJ) ? (T)-1 : (T)1;
       for (int i = 0; i < d * d; ++i) out[i] = mk<T>((T)row[i].x, sg * (T)row[i].y);
       break;
     }
@@ -204,7 +271,7 @@ __device__ void eval_source_mem(const DevProg& P, const RunArgs& R, int sid, int
           for (int i = 0; i < 16; ++i) F[i] = ld_const<T>(P.consts, P.src[id].a0 + i);
         } else {
           cx<T> u[4];
-          eval_2x2<T>(P, R, id, b, u);
+          eval_2x2<T>(P, R, rows, id, u);
           // (U (x) conj U)[(a,b),(c,d)] = U[a][c] * conj(U[b][d])
 #pragma unroll
           for (int a = 0; a < 2; ++a)
@@ -237,11 +304,31 @@ __device__ void eval_source_mem(const DevProg& P, const RunArgs& R, int sid, int
   }
 }
 
+// Precompute kernel: thread (j, idx) evaluates hoisted factor j of slot `slot` for
+// row idx and stores it at tab[(local_j * mod + idx) * 4].
+template <typename T>
+__global__ void k_pre(DevProg P, RunArgs R, int slot, const int32_t* __restrict__ ids,
+                      int n_ids, cx<T>* __restrict__ tab) {
+  const int64_t mod = R.a[slot].mod;
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= mod * n_ids) return;
+  const int j = (int)(t / mod);
+  const int64_t idx = t % mod;
+  const qmlb_pre pe = P.pre[ids[j]];
+  RowsDirect rows{R, idx * R.a[slot].div};
+  cx<T> m[4];
+  eval_2x2_base<T>(P, R, rows, pe.src, m);
+  cx<T>* o = tab + ((int64_t)pe.local * mod + idx) * 4;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) o[i] = m[i];
+}
+
 // number of complex entries a source writes
 __host__ __device__ __forceinline__ int source_entries(int kind, int k, int flags) {
   int d = 1 << k;
   if (kind == QMLB_SRC_DIAGPH) return d;
-  if (kind == QMLB_SRC_CONST && (flags & 2)) return d;
+  if (kind == QMLB_SRC_CONST && (flags & QMLB_FLAG_DIAGVEC)) return d;
+  if (kind == QMLB_SRC_PRE || kind == QMLB_SRC_CHAIN) return 4;
   return d * d;
 }
 

@@ -30,6 +30,9 @@ struct qmlb_program {
   std::vector<double> consts;
   std::vector<qmlb_obs> obs;
   std::vector<double> obs_consts;
+  std::vector<qmlb_pre> pre;
+  std::vector<int32_t> pre_ids[QMLB_MAX_ARGS];        // pre entries per argument slot
+  const int32_t* pre_ids_dev[QMLB_MAX_ARGS] = {};     // same, in the device blob
   int max_arg = -1;
 
   int strategy = 0;

@@ -127,14 +127,27 @@ __host__ inline bool reg_supports(const qmlb_op& op, const double* consts, int n
   return false;
 }
 
+// rows cached in shared memory: slot a of this thread at base[a * 128]
+struct RowsShared {
+  const int32_t* base;
+  __device__ __forceinline__ int64_t operator()(int a) const { return base[a * 128]; }
+};
+
 // mode: 0 -> write state, 1 -> probs, 2 -> Z-string expectation values
 template <typename T, int N>
-__global__ void __launch_bounds__(128) k_reg(DevProg P, RunArgs R, int mode,
+__global__ void __launch_bounds__(128) k_reg(DevProg P, RunArgs R, int mode, int n_args,
                                              void* __restrict__ out) {
   constexpr int D = 1 << N;
   const int64_t bl = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (bl >= R.batch) return;
   const int64_t b = bl + R.batch_offset;
+
+  // rows of the argument slots this element reads, computed once (64-bit div/mod)
+  __shared__ int32_t s_rows[QMLB_MAX_ARGS][128];
+#pragma unroll
+  for (int a = 0; a < QMLB_MAX_ARGS; ++a)
+    if (a < n_args) s_rows[a][threadIdx.x] = (int32_t)((b / R.a[a].div) % R.a[a].mod);
+  const RowsShared rows{&s_rows[0][threadIdx.x]};
 
   T re[D], im[D];
 #pragma unroll
@@ -173,7 +186,7 @@ __global__ void __launch_bounds__(128) k_reg(DevProg P, RunArgs R, int mode,
     if (op.kind == QMLB_OP_DIAG && op.k > 1) {  // all bits, MSB first
       const qmlb_source s = P.src[op.src];
       if (s.kind == QMLB_SRC_DIAGPH) {
-        const double th = eval_angle(P, R, s.angle, b);
+        const double th = eval_angle(P, R, rows, s.angle);
 #pragma unroll
         for (int i = 0; i < D; ++i) {
           T sn, cs;
@@ -200,7 +213,7 @@ __global__ void __launch_bounds__(128) k_reg(DevProg P, RunArgs R, int mode,
       m[1] = mk<T>(0, 0);
       m[2] = mk<T>(0, 0);
       if (s.kind == QMLB_SRC_DIAGPH) {
-        const double th = eval_angle(P, R, s.angle, b);
+        const double th = eval_angle(P, R, rows, s.angle);
         T sn, cs;
         sincos_t((T)(-P.consts[s.a0] * th), &sn, &cs);
         m[0] = mk<T>(cs, sn);
@@ -211,7 +224,7 @@ __global__ void __launch_bounds__(128) k_reg(DevProg P, RunArgs R, int mode,
         m[3] = ld_const<T>(P.consts, s.a0 + 1);
       }
     } else {
-      eval_2x2<T>(P, R, op.src, b, m);
+      eval_2x2<T>(P, R, rows, op.src, m);
     }
     if (op.kind == QMLB_OP_CTRL1) {
       dispatch2<T, N>(op.bits[0], op.bits[1], [&](auto CB, auto TB) {

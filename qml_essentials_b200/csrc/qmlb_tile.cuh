@@ -254,7 +254,8 @@ __global__ void __launch_bounds__(256) k_tile(DevProg P, RunArgs R, PassDev pass
       // prologue: one thread per op evaluates that op's matrix for element b
       for (int j = tlane; j < win.y; j += tsize) {
         const qmlb_op& op = pass.ops[win.x + j];
-        if (op.src >= 0) eval_source_mem<T>(P, R, op.src, b, mb + pass.matoff[win.x + j]);
+        if (op.src >= 0)
+          eval_source_mem<T>(P, R, RowsDirect{R, b}, op.src, mb + pass.matoff[win.x + j]);
       }
       team_sync<WARP_TEAM>();
       for (int j = 0; j < win.y; ++j) {
