@@ -198,59 +198,156 @@ void make_windows(const qmlb_program* p, QmlbPassHost& ps, int matw) {
   ps.matw = matw;
 }
 
-// Greedy pass construction for streamed execution: every pass owns the `m_low`
-// least-significant bits (contiguous -> coalesced) plus up to kt - m_low others.
-int schedule_passes(qmlb_program* p, int kt, int m_low) {
+// ---- strategy 2: pass construction for the streaming kernel -----------------------
+// Every pass owns a group of R state bits.  Greedy list scheduling: scan the
+// not-yet-done ops in program order; an op joins the pass if none of its bits is
+// blocked by an earlier op that had to be left out and the union of group bits
+// stays within R.  Diagonal ops act on global indices and need no group bits.
+// Ops on 3 or 4 bits pin their bits to register positions 0..k-1.
+int schedule_stream(qmlb_program* p, int R) {
   const int N = p->n_bits;
+  const int max_entries = 2048;  // matrix buffer entries per pass (<= 32 KB)
   std::vector<char> done(p->ops.size(), 0);
   size_t remaining = p->ops.size();
   bool first_pass = true;
+  const int sector_bits = p->dtype == QMLB_C128 ? 1 : 2;
+  const uint64_t sector_mask = (1ull << sector_bits) - 1;
   while (remaining > 0 || first_pass) {
-    uint64_t S = (m_low >= 64) ? ~0ull : ((1ull << m_low) - 1);
-    uint64_t blocked = 0;
-    QmlbPassHost ps;
+    uint64_t S = 0, blocked = 0;
+    std::vector<int> canon;  // ordered: register position j -> state bit (k >= 3 op)
     std::vector<size_t> picked;
+    int entries = 0;
     for (size_t i = 0; i < p->ops.size(); ++i) {
       if (done[i]) continue;
       const qmlb_op& o = p->ops[i];
       uint64_t bits = 0;
       for (int j = 0; j < o.k; ++j) bits |= 1ull << o.bits[j];
-      if (bits & blocked) {
+      // a 32-byte sector (state bits 0..1 in complex64, bit 0 in complex128) is owned by
+      // one thread: an op that touches a sector bit brings the whole sector into the group
+      uint64_t grp = bits;
+      if (o.kind != QMLB_OP_DIAG && (bits & sector_mask) && N >= R + 2 &&
+          __builtin_popcountll(bits | sector_mask) <= R)
+        grp |= sector_mask;
+      const int e = op_entries(p, o);
+      if ((bits & blocked) || entries + e > max_entries ||
+          (int)picked.size() >= STREAM_MAX_OPS) {
         blocked |= bits;
         continue;
       }
-      if (o.kind == QMLB_OP_DIAG) {  // applied on global indices: needs no tile bits
+      if (o.kind == QMLB_OP_DIAG) {
         picked.push_back(i);
+        entries += e;
         continue;
       }
-      uint64_t U = S | bits;
-      if (__builtin_popcountll(U) <= kt) {
-        S = U;
-        picked.push_back(i);
-      } else {
-        blocked |= bits;
+      if (o.k > R) return fail(QMLB_ERR_UNSUPPORTED, "operation wider than the register group");
+      const uint64_t U = S | grp;
+      bool ok = __builtin_popcountll(U) <= R;
+      if (ok && o.k >= 3) {
+        std::vector<int> want(o.k);
+        for (int j = 0; j < o.k; ++j) want[o.k - 1 - j] = o.bits[j];
+        if (canon.empty()) {
+          // earlier ops of this pass may sit anywhere: positions are assigned at the end
+          canon = want;
+        } else {
+          ok = want.size() <= canon.size() &&
+               std::equal(want.begin(), want.end(), canon.begin());
+        }
       }
+      if (!ok) {
+        blocked |= bits;
+        continue;
+      }
+      S = U;
+      picked.push_back(i);
+      entries += e;
     }
-    // pad the tile to kt bits with the lowest unused bits (keeps tiles large)
-    for (int g = 0; g < N && __builtin_popcountll(S) < std::min(kt, N); ++g) S |= 1ull << g;
+    if (picked.empty() && remaining > 0)
+      return fail(QMLB_ERR_UNSUPPORTED, "an operation does not fit a streaming pass");
+
+    QmlbStreamPassHost ps;
+    // register positions: pinned bits first, then the other group bits ascending, then pads
+    std::vector<int> gb(canon);
+    auto in_gb = [&](int g) { return std::find(gb.begin(), gb.end(), g) != gb.end(); };
+    // ascending: state bits 0 (and 1) land on register bits 0 (and 1) unless an op on
+    // 3-4 bits pinned other bits there -> the kernel moves 16-byte pairs
     for (int g = 0; g < N; ++g)
-      if (S >> g & 1) ps.tile_bits.push_back(g);
-    std::vector<int> local(N, -1);
-    for (size_t j = 0; j < ps.tile_bits.size(); ++j) local[ps.tile_bits[j]] = (int)j;
+      if ((S >> g & 1) && !in_gb(g)) gb.push_back(g);
+    // keep 32-byte sectors whole per thread: complete the lowest sector bits if one is present
+    bool touches_low = false;
+    for (int g : gb) touches_low = touches_low || g < sector_bits;
+    if (touches_low)
+      for (int g = 0; g < sector_bits && (int)gb.size() < R; ++g)
+        if (!in_gb(g)) gb.push_back(g);
+    for (int g = N - 1; g >= 0 && (int)gb.size() < R; --g)
+      if (!in_gb(g)) gb.push_back(g);
+    std::vector<int> pos(N, -1);
+    for (int j = 0; j < R; ++j) {
+      ps.gb[j] = gb[j];
+      pos[gb[j]] = j;
+    }
+    std::vector<int> sorted(gb.begin(), gb.begin() + R);
+    std::sort(sorted.begin(), sorted.end());
+    for (int j = 0; j < R; ++j) ps.sorted[j] = sorted[j];
+
+    int used = 0;
     for (size_t i : picked) {
       qmlb_op o = p->ops[i];
+      ps.matoff.push_back(used);
+      used += op_entries(p, o);
       if (o.kind != QMLB_OP_DIAG)
-        for (int j = 0; j < o.k; ++j) o.bits[j] = local[o.bits[j]];
+        for (int j = 0; j < o.k; ++j) o.bits[j] = pos[o.bits[j]];
+      if (o.kind == QMLB_OP_PERM) {
+        const int D = 1 << o.k;
+        std::vector<int> perm(D);
+        for (int v = 0; v < D; ++v) perm[v] = (int)p->consts[o.aux + v];
+        if (o.k == 2 && o.bits[0] < o.bits[1]) {  // canonical order JA > JB
+          auto sw = [](int v) { return ((v & 1) << 1) | (v >> 1); };
+          std::vector<int> q(4);
+          for (int v = 0; v < 4; ++v) q[sw(v)] = sw(perm[v]);
+          perm = q;
+          std::swap(o.bits[0], o.bits[1]);
+        }
+        unsigned long long packed = 0;
+        for (int v = 0; v < D; ++v) packed |= (unsigned long long)perm[v] << (o.k * v);
+        o.src = (int32_t)(uint32_t)(packed & 0xffffffffull);
+        o.aux = (int32_t)(uint32_t)(packed >> 32);
+      }
       ps.ops.push_back(o);
       done[i] = 1;
     }
     remaining -= picked.size();
-    ps.flags = QMLB_PASS_STORE | (first_pass ? QMLB_PASS_INIT : 0);
-    p->passes.push_back(std::move(ps));
+    ps.matw = std::max(used, 1);
+    ps.flags = first_pass ? QMLB_PASS_INIT : 0;
+    for (const qmlb_op& o : ps.ops)
+      if (o.kind != QMLB_OP_DIAG && o.k >= 3) ps.flags |= QMLB_PASS_HEAVY;
+    StreamPass& pd = ps.dev;
+    std::memset(&pd, 0, sizeof(pd));
+    pd.n_ops = (int)ps.ops.size();
+    pd.n_bits = N;
+    pd.flags = ps.flags;
+    pd.matw = ps.matw;
+    for (int j = 0; j < R; ++j) {
+      pd.gb[j] = ps.gb[j];
+      pd.sorted[j] = ps.sorted[j];
+    }
+    for (size_t i = 0; i < ps.ops.size(); ++i) {
+      const qmlb_op& o = ps.ops[i];
+      StreamOp& so = pd.ops[i];
+      so.kind = (uint8_t)o.kind;
+      so.k = (uint8_t)o.k;
+      so.b0 = (uint8_t)o.bits[0];
+      so.b1 = (uint8_t)(o.k > 1 ? o.bits[1] : 0);
+      so.src = o.kind == QMLB_OP_PERM ? -1 : o.src;
+      so.data = 0;
+      if (o.kind == QMLB_OP_PERM) {
+        so.data = ((uint64_t)(uint32_t)o.aux << 32) | (uint32_t)o.src;
+      } else if (o.kind == QMLB_OP_DIAG) {
+        for (int j = 0; j < o.k; ++j) so.data |= (uint64_t)o.bits[j] << (6 * j);
+      }
+      pd.matoff[i] = (uint16_t)ps.matoff[i];
+    }
+    p->stream_passes.push_back(std::move(ps));
     first_pass = false;
-    if (picked.empty() && remaining > 0)
-      return fail(QMLB_ERR_UNSUPPORTED,
-                  "an operation does not fit a tile (QMLB_TILE_BITS too small)");
   }
   return QMLB_OK;
 }
@@ -387,7 +484,8 @@ int plan(qmlb_program* p) {
   const int init_max = env_int("QMLB_SMEM_STATE_BITS", p->dtype == QMLB_C128 ? 13 : 14);
   p->direct_out = (p->out_type == QMLB_OUT_STATE) ||
                   (p->out_type == QMLB_OUT_DENSITY && p->density);
-  if ((N <= init_max && force != 2) || force == 1) {
+  const int stream_r = p->dtype == QMLB_C128 ? 4 : 5;
+  if ((N <= init_max && force != 2) || force == 1 || N < stream_r) {
     if (N > QMLB_MAX_TILE_BITS) return fail(QMLB_ERR_UNSUPPORTED, "state too large for smem");
     p->strategy = 1;
     QmlbPassHost ps;
@@ -414,32 +512,48 @@ int plan(qmlb_program* p) {
     return QMLB_OK;
   }
 
-  // ---- strategy 2: streamed tile passes -------------------------------------------
+  // ---- strategy 2: streamed register-group passes over HBM ------------------------
   p->strategy = 2;
-  int kt = env_int("QMLB_TILE_BITS", p->dtype == QMLB_C128 ? 12 : 13);
-  kt = std::min(kt, std::min(N, QMLB_MAX_TILE_BITS));
-  int m_low = std::min(env_int("QMLB_TILE_LOW_BITS", 5), kt);
-  if (kt < m_low + 4) m_low = std::max(0, kt - 4);  // every op (<= 4 bits) must fit a tile
-  {
-    int rc = schedule_passes(p, kt, m_low);
-    if (rc != QMLB_OK) return rc;
-  }
+  p->stream_r = p->dtype == QMLB_C128 ? 4 : 5;
   p->warp_team = false;
   p->teams = 1;
-  const int matw_cap = env_int("QMLB_TILE_MATW", 1024);
-  size_t smem = 0;
-  for (auto& ps : p->passes) {
-    int need = 0, biggest = 1;
-    for (const auto& o : ps.ops) {
-      need += op_entries(p, o);
-      biggest = std::max(biggest, op_entries(p, o));
-    }
-    int matw = std::max(1, std::min(need, std::max(matw_cap, biggest)));
-    make_windows(p, ps, matw);
-    smem = std::max(smem, (size_t(1) << ps.tile_bits.size()) * cs + (size_t)matw * cs);
+  p->smem = 0;
+  {
+    int rc = schedule_stream(p, p->stream_r);
+    if (rc != QMLB_OK) return rc;
   }
-  p->smem = smem;
+  if (env_int("QMLB_DUMP_PASSES", 0)) {
+    static const char* kinds[] = {"MAT", "CTRL1", "PERM", "DIAG"};
+    for (size_t i = 0; i < p->stream_passes.size(); ++i) {
+      const QmlbStreamPassHost& ps = p->stream_passes[i];
+      std::fprintf(stderr, "pass %zu flags=%d group=[", i, ps.flags);
+      for (int j = 0; j < p->stream_r; ++j) std::fprintf(stderr, "%d ", ps.gb[j]);
+      std::fprintf(stderr, "] ops:");
+      for (const qmlb_op& o : ps.ops) {
+        std::fprintf(stderr, " %s%d(", kinds[o.kind], o.k);
+        for (int j = 0; j < o.k; ++j) std::fprintf(stderr, j ? ",%d" : "%d", o.bits[j]);
+        std::fprintf(stderr, ")");
+      }
+      std::fprintf(stderr, "\n");
+    }
+  }
   return QMLB_OK;
+}
+
+// every observable is Z on one qubit of a pure state with >= 256 amplitudes
+bool z1_fast(const qmlb_program* p) {
+  if (p->out_type != QMLB_OUT_EXPVAL || p->density || p->n_qubits < 8 || p->n_qubits > 32)
+    return false;
+  for (const auto& o : p->obs)
+    if (o.kind != QMLB_OBS_ZSTRING || __builtin_popcountll((unsigned long long)o.zmask) != 1)
+      return false;
+  return true;
+}
+
+int z1_ctas(const qmlb_program* p, int64_t batch) {
+  const int64_t units = int64_t(1) << (p->n_qubits - 8);
+  const int64_t per = std::max<int64_t>(1, ((int64_t)p->sm_count * 8) / std::max<int64_t>(batch, 1));
+  return (int)std::max<int64_t>(1, std::min<int64_t>((units + 7) / 8, per));
 }
 
 int expval_chunks(const qmlb_program* p, int64_t batch) {
@@ -469,6 +583,18 @@ int launch_measure(const qmlb_program* p, const cx<T>* state, int64_t batch, voi
     g_launches.fetch_add(1, std::memory_order_relaxed);
     k_outer<T><<<std::max(grid, 1), 256, 0, st>>>(state, static_cast<cx<T>*>(out), batch,
                                                  p->n_qubits);
+  } else if (p->out_type == QMLB_OUT_EXPVAL && z1_fast(p)) {
+    const int ctas = z1_ctas(p, batch);
+    double* partial = reinterpret_cast<double*>(scratch);
+    const int64_t n_out = batch * (int64_t)p->obs.size();
+    g_launches.fetch_add(2, std::memory_order_relaxed);
+    for (int64_t b0 = 0; b0 < batch; b0 += 65535) {
+      const int64_t nb = std::min<int64_t>(65535, batch - b0);
+      k_expval_z1<T><<<dim3((unsigned)ctas, (unsigned)nb), 256, 0, st>>>(
+          state + ((size_t)b0 << p->n_qubits), partial + (size_t)b0 * ctas * 33, p->n_qubits);
+    }
+    k_expval_z1_final<T><<<(unsigned)((n_out + 255) / 256), 256, 0, st>>>(
+        p->dev, partial, static_cast<T*>(out), batch, ctas);
   } else if (p->out_type == QMLB_OUT_EXPVAL) {
     const int chunks = expval_chunks(p, batch);
     const int n_obs = (int)p->obs.size();
@@ -512,7 +638,9 @@ size_t state_layout(const qmlb_program* p, int64_t batch, size_t* part_off) {
   size_t need = p->direct_out ? 0 : (size_t)batch * (size_t(1) << p->n_bits) * cs_of(p->dtype);
   *part_off = (need + 255) & ~size_t(255);
   const int chunks = expval_chunks(p, batch);
-  if (!p->direct_out && chunks > 1)
+  if (!p->direct_out && z1_fast(p))
+    need = *part_off + (size_t)batch * z1_ctas(p, batch) * 33 * sizeof(double);
+  else if (!p->direct_out && chunks > 1)
     need = *part_off + (size_t)batch * p->obs.size() * chunks * rs_of(p->dtype);
   return (need + 255) & ~size_t(255);
 }
@@ -544,6 +672,21 @@ int run_typed(const qmlb_program* p, RunArgs& R, void* out, void* workspace, siz
   if (p->strategy == 0) {
     void* dst = p->direct_out ? out : static_cast<void*>(ws_state);
     CUDA_TRY((std::is_same<T, double>::value ? launch_reg_f64 : launch_reg_f32)(p, R, dst, st));
+  } else if (p->strategy == 2) {
+    const int64_t items = int64_t(1) << (p->n_bits - p->stream_r);
+    const int64_t ctas_x = (items + STREAM_THREADS - 1) / STREAM_THREADS;
+    const int64_t want = (int64_t)p->sm_count * 16;  // persistent: CTAs loop over items / elements
+    dim3 grid;
+    if (R.batch == 1) {
+      grid = dim3((unsigned)std::max<int64_t>(1, std::min(ctas_x, want)), 1, 1);
+    } else {
+      const int64_t gx = std::max<int64_t>(1, std::min<int64_t>(ctas_x, 64));
+      const int64_t gy = std::max<int64_t>(1, std::min<int64_t>(R.batch, std::max<int64_t>(1, want / gx)));
+      grid = dim3((unsigned)gx, (unsigned)std::min<int64_t>(gy, 65535), 1);
+    }
+    for (const QmlbStreamPassHost& ps : p->stream_passes)
+      CUDA_TRY((std::is_same<T, double>::value ? launch_stream_f64 : launch_stream_f32)(
+          p, R, ps.dev, grid, state, st));
   } else {
     for (const QmlbPassHost& ps : p->passes) {
       const int kt = (int)ps.tile_bits.size();
@@ -561,7 +704,7 @@ int run_typed(const qmlb_program* p, RunArgs& R, void* out, void* workspace, siz
 }
 
 int set_smem_attr(const qmlb_program* p) {
-  if (p->strategy == 0 || p->smem <= 48 * 1024) return QMLB_OK;
+  if (p->strategy != 1 || p->smem <= 48 * 1024) return QMLB_OK;
   CUDA_TRY(p->dtype == QMLB_C128 ? tile_set_smem_f64(p->smem) : tile_set_smem_f32(p->smem));
   return QMLB_OK;
 }
@@ -623,7 +766,10 @@ int qmlb_program_info(const qmlb_program* p, int32_t* strategy, int32_t* n_passe
                       int32_t* n_device_ops) {
   if (!p) return fail(QMLB_ERR_INVALID, "null program");
   if (strategy) *strategy = p->strategy;
-  if (n_passes) *n_passes = p->strategy == 0 ? 1 : (int32_t)p->passes.size();
+  if (n_passes)
+    *n_passes = p->strategy == 0 ? 1
+                                 : (p->strategy == 2 ? (int32_t)p->stream_passes.size()
+                                                     : (int32_t)p->passes.size());
   if (n_device_ops) *n_device_ops = (int32_t)p->ops.size();
   return QMLB_OK;
 }

@@ -8,6 +8,7 @@
 #include <vector>
 
 #include "qmlb_device.cuh"
+#include "qmlb_stream_types.h"
 #include "qmlb_tile_types.h"
 
 struct QmlbPassHost {
@@ -18,6 +19,16 @@ struct QmlbPassHost {
   int flags = 0;
   int matw = 0;
   qmlb::PassDev dev{};           // device view (pointers into the program blob)
+};
+
+struct QmlbStreamPassHost {
+  std::vector<qmlb_op> ops;      // register-position bits, packed PERM tables
+  std::vector<int32_t> matoff;
+  int gb[qmlb::STREAM_MAX_R] = {0, 0, 0, 0, 0};
+  int sorted[qmlb::STREAM_MAX_R] = {0, 0, 0, 0, 0};
+  int flags = 0;
+  int matw = 1;
+  qmlb::StreamPass dev{};
 };
 
 struct qmlb_program {
@@ -42,6 +53,8 @@ struct qmlb_program {
   int teams = 1;
   size_t smem = 0;
   std::vector<QmlbPassHost> passes;
+  std::vector<QmlbStreamPassHost> stream_passes;
+  int stream_r = 5;
   int sm_count = 148;
 
   void* blob = nullptr;
@@ -62,6 +75,10 @@ cudaError_t launch_tile_f32(const qmlb_program* p, const RunArgs& R, const PassD
                             unsigned grid, void* state, cudaStream_t st);
 cudaError_t launch_tile_f64(const qmlb_program* p, const RunArgs& R, const PassDev& pass,
                             unsigned grid, void* state, cudaStream_t st);
+cudaError_t launch_stream_f32(const qmlb_program* p, const RunArgs& R, const StreamPass& pass,
+                              dim3 grid, void* state, cudaStream_t st);
+cudaError_t launch_stream_f64(const qmlb_program* p, const RunArgs& R, const StreamPass& pass,
+                              dim3 grid, void* state, cudaStream_t st);
 cudaError_t tile_set_smem_f32(size_t bytes);
 cudaError_t tile_set_smem_f64(size_t bytes);
 

@@ -179,6 +179,86 @@ __global__ void __launch_bounds__(256) k_expval(DevProg P, const cx<T>* __restri
   }
 }
 
+// <Z_q> for every qubit of pure states in ONE sweep over the state (the generic kernel
+// above re-reads the state per group of 8 observables and spends ~20 instructions per
+// amplitude on signs).  A warp takes units of 256 consecutive amplitudes: lane l loads
+// amplitudes u*256 + j*32 + l (j = 0..7, coalesced).  The bit of each qubit is then either
+// a lane bit (0-4: resolved once at the end), an in-thread bit (5-7: three running sums) or
+// a bit of the unit index u (>= 8: one predicated add per unit).  Accumulation is in
+// double; the reduction order is fixed (thread -> warp tree -> warps in order -> CTAs in
+// order), so results do not depend on timing.
+// partial[(bl * ctas + c) * 33 + q] = sum of p over amplitudes with bit q set (q < n),
+// partial[... + 32] = total probability.   Grid: (ctas, batch).
+template <typename T>
+__global__ void __launch_bounds__(256) k_expval_z1(const cx<T>* __restrict__ st,
+                                                   double* __restrict__ partial, int n) {
+  __shared__ double red[8][33];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint64_t units = 1ull << (n - 8);
+  const cx<T>* s = st + ((size_t)blockIdx.y << n);
+  double tot = 0, a5 = 0, a6 = 0, a7 = 0;
+  double H[24];
+#pragma unroll
+  for (int q = 0; q < 24; ++q) H[q] = 0;
+  for (uint64_t u = (uint64_t)blockIdx.x * 8 + warp; u < units; u += (uint64_t)gridDim.x * 8) {
+    const cx<T>* p = s + (u << 8) + lane;
+    T pr[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const cx<T> a = p[j * 32];
+      pr[j] = a.x * a.x + a.y * a.y;
+    }
+    const double s5 = (double)(pr[1] + pr[3]) + (double)(pr[5] + pr[7]);
+    const double s6 = (double)(pr[2] + pr[3]) + (double)(pr[6] + pr[7]);
+    const double s7 = (double)(pr[4] + pr[5]) + (double)(pr[6] + pr[7]);
+    const double t = (double)(pr[0] + pr[1]) + (double)(pr[2] + pr[3]) + s7;
+    tot += t;
+    a5 += s5;
+    a6 += s6;
+    a7 += s7;
+#pragma unroll
+    for (int q = 0; q < 24; ++q)
+      if (q + 8 < n && ((u >> q) & 1ull)) H[q] += t;
+  }
+  // per-thread vector -> CTA sums
+#pragma unroll
+  for (int q = 0; q < 33; ++q) {
+    double v;
+    if (q < 5) v = ((lane >> q) & 1) ? tot : 0.0;
+    else if (q == 5) v = a5;
+    else if (q == 6) v = a6;
+    else if (q == 7) v = a7;
+    else if (q < 32) v = H[q - 8];
+    else v = tot;
+    v = warp_sum(v);
+    if (lane == 0) red[warp][q] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < 33) {
+    double r = 0;
+    for (int w = 0; w < 8; ++w) r += red[w][threadIdx.x];
+    partial[((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 33 + threadIdx.x] = r;
+  }
+}
+
+// out[bl][j] = total - 2 * S_{bit(j)} summed over CTAs in index order
+template <typename T>
+__global__ void k_expval_z1_final(DevProg P, const double* __restrict__ partial,
+                                  T* __restrict__ out, int64_t batch, int ctas) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= batch * P.n_obs) return;
+  const int64_t bl = i / P.n_obs;
+  const int j = (int)(i % P.n_obs);
+  const int bit = 63 - __clzll((unsigned long long)P.obs[j].zmask);
+  double tot = 0, sq = 0;
+  for (int c = 0; c < ctas; ++c) {
+    const double* row = partial + ((size_t)bl * ctas + c) * 33;
+    tot += row[32];
+    sq += row[bit];
+  }
+  out[i] = (T)(tot - 2.0 * sq);
+}
+
 // out[i] = sum_c partial[i * chunks + c] in index order
 template <typename T>
 __global__ void k_sum_chunks(const T* __restrict__ partial, T* __restrict__ out,

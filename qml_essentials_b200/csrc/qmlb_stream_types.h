@@ -1,0 +1,35 @@
+// Pass descriptor of the streaming kernel, shared by host scheduling and device code.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/qmlb200.h"
+#include "qmlb_tile_types.h"
+
+namespace qmlb {
+
+constexpr int STREAM_THREADS = 128;
+constexpr int STREAM_MAX_R = 5;
+constexpr int STREAM_MIN_CTAS = 3;  // resident CTAs per SM the lean kernel is compiled for
+
+constexpr int STREAM_MAX_OPS = 40;
+
+// Compact op of a streaming pass; lives in the kernel parameters (constant bank), so
+// decoding it costs uniform loads only.
+struct StreamOp {
+  uint8_t kind, k, b0, b1;  // b0/b1: register positions of bits[0]/bits[1] (k <= 2)
+  int32_t src;              // matrix source (prologue only), -1 for PERM
+  uint64_t data;            // PERM: table packed k bits/entry; DIAG: global bits, 6 bits each
+};
+
+struct StreamPass {
+  StreamOp ops[STREAM_MAX_OPS];
+  uint16_t matoff[STREAM_MAX_OPS];  // per op: offset (complex entries) into the matrix buffer
+  int32_t n_ops;
+  int32_t n_bits;          // total state bits
+  int32_t flags;           // QMLB_PASS_INIT | QMLB_PASS_HEAVY
+  int32_t matw;            // matrix buffer entries
+  int32_t gb[STREAM_MAX_R];      // register bit j -> state bit
+  int32_t sorted[STREAM_MAX_R];  // the same bits ascending
+};
+
+}  // namespace qmlb

@@ -83,19 +83,22 @@ def test_noisy_density_sizes(n):
 
 
 def test_streamed_strategy_matches_resident_strategy():
-    """Force the HBM-streamed tile passes on small states (separate processes: the
-    strategy is an environment switch read at program creation)."""
+    """Force the HBM-streaming register-group passes (k_stream) on small states, both
+    precisions (separate processes: the strategy is an environment switch read at
+    program creation).  Covers lean passes (1-qubit chains, CRX, CX, 4x4 superoperators)
+    and heavy ones (16x16 two-qubit channel, CCX / CSWAP permutations)."""
     code = ("import sys; sys.path.insert(0, 'tests'); import parity_cases as pc; "
-            "e = max(pc.case_model(7, 2, 'Hardware_Efficient', 2, 3, 'state'),"
-            " pc.case_model(8, 1, 'Circuit_19', 2, 2, 'expval'),"
-            " pc.case_model(3, 2, 'Strongly_Entangling', 2, 2, 'density',"
+            "P = sys.argv[1]; tol = pc.TOL[P]; "
+            "e = max(pc.case_model(7, 2, 'Hardware_Efficient', 2, 3, 'state', precision=P),"
+            " pc.case_model(8, 1, 'Circuit_19', 2, 2, 'expval', precision=P),"
+            " pc.case_model(3, 2, 'Strongly_Entangling', 2, 2, 'density', precision=P,"
             " noise={'Depolarizing': 0.01, 'AmplitudeDamping': 0.02}),"
-            " pc.case_model(4, 1, 'Circuit_6', 1, 2, 'probs', noise={'BitFlip': 0.1,"
-            " 'MultiQubitDepolarizing': 0.05})); print('ERR', e); assert e < 1e-10")
-    for kt, low in (("6", "2"), ("5", "1"), ("7", "5")):
-        env = dict(os.environ, QMLB_FORCE_STRATEGY="2", QMLB_TILE_BITS=kt,
-                   QMLB_TILE_LOW_BITS=low, QMLB_TILE_MATW="40")
-        r = subprocess.run([sys.executable, "-c", code], cwd=ROOT, env=env,
+            " pc.case_model(4, 1, 'Circuit_6', 1, 2, 'probs', precision=P, noise={'BitFlip': 0.1,"
+            " 'MultiQubitDepolarizing': 0.05}),"
+            " max(pc.case_every_gate(P, n=6).values())); print('ERR', e); assert e < tol")
+    for prec in ("complex128", "complex64"):
+        env = dict(os.environ, QMLB_FORCE_STRATEGY="2")
+        r = subprocess.run([sys.executable, "-c", code, prec], cwd=ROOT, env=env,
                            capture_output=True, text=True)
         assert r.returncode == 0, r.stdout + r.stderr
 
