@@ -206,9 +206,11 @@ int qmlb_run(const qmlb_program* prog, const qmlb_arg* args, int32_t n_args, int
 int qmlb_sample(const void* probs, int dtype, const double* uniforms, int64_t batch,
                 int32_t n_qubits, int64_t shots, int32_t* counts, void* stream);
 
-/* Per-qubit purities Tr(rho_q^2) of the single-qubit reduced states of `batch`
- * pure states (is_density = 0, (batch, 2^n)) or density matrices (is_density = 1):
- * out[b][q], real of the given precision (entanglement.py:86-103). */
+/* Meyer-Wallach purities out[b][q] = Tr[(Tr_q rho_b)^2] - the purity of the state
+ * with qubit q traced out (entanglement.py:86-103) - of `batch` pure states
+ * (is_density = 0, (batch, 2^n); computed from the single-qubit reduced state, which
+ * has the same purity) or density matrices (is_density = 1, (batch, 2^n, 2^n)).
+ * out: (batch, n_qubits) real of the given precision. */
 int qmlb_purity(const void* states, int dtype, int is_density, int64_t batch,
                 int32_t n_qubits, void* out, void* stream);
 

@@ -187,7 +187,14 @@ class DeviceCall:
         return self.out
 
     def result(self) -> np.ndarray:
-        return self.out.cpu().numpy()
+        """Device -> host through a pinned staging buffer (torch's caching host
+        allocator recycles it); the returned array owns that buffer."""
+        import torch
+
+        host = torch.empty(self.out.shape, dtype=self.out.dtype, pin_memory=True)
+        host.copy_(self.out, non_blocking=True)
+        torch.cuda.current_stream(self.ex.device).synchronize()
+        return host.numpy()
 
 
 class CudaExecutor:
@@ -238,21 +245,26 @@ class CudaExecutor:
                               batch_offset)
 
     # -- Script-facing entry points -----------------------------------------------
-    def execute(self, plan, host_args, batch: int, chunk: Optional[int] = None) -> np.ndarray:
+    def execute(self, plan, host_args, batch: int, chunk: Optional[int] = None,
+                to_host: bool = True):
+        """Run the plan over the batch (in HBM-sized chunks if needed).  Returns a
+        NumPy array, or the device tensor when ``to_host`` is False."""
         chunk = batch if not chunk else min(chunk, batch)
         with self.torch.cuda.device(self.device):
             if chunk >= batch:
                 call = self.stage(plan, host_args, batch)
-                call.launch()
-                return call.result()
+                out = call.launch()
+                return call.result() if to_host else out
             dev_args = self.to_device(host_args)
             handle = self.handle_for(plan)
             parts = []
             for lo in range(0, batch, chunk):
                 call = DeviceCall(self, handle, dev_args, min(chunk, batch - lo), lo)
-                call.launch()
-                parts.append(call.result())
-            return np.concatenate(parts, axis=0)
+                out = call.launch()
+                parts.append(call.result() if to_host else out)
+            if to_host:
+                return np.concatenate(parts, axis=0)
+            return self.torch.cat(parts, dim=0)
 
     def execute_shots(self, plan, host_args, batch: int, uniforms: np.ndarray,
                       chunk: Optional[int] = None) -> np.ndarray:

@@ -1,0 +1,388 @@
+"""Fourier coefficients of a model and their correlation (FCC / Fourier fingerprint).
+
+Host-side mirror of the callers of the hot path in the reference's
+``qml_essentials/coefficients.py``: ``Coefficients`` (lines 23-238) and ``FCC``
+(966-1650).  Same names, arguments and results; NumPy instead of jax.numpy.  The
+circuit evaluations - all the time - go through ``Model.__call__`` and therefore
+through the CUDA backend; the FFT over a few hundred grid points and the K x K
+correlation stay on the host ("next" rows of SURVEY section 8(f)).
+
+Multi-GPU (one process per GPU, ``torch.distributed`` initialised): the sample
+axis is sharded across ranks, every rank transforms its own columns, and the
+correlation is formed from additive sufficient statistics that cross ranks in ONE
+small all-reduce (``nobs``, ``sum x``, ``sum conj(x_i) x_j`` ... - K x K numbers).
+Spearman needs global ranks, so its coefficients are all-gathered instead.
+
+``FourierTree`` (the analytic Pauli-propagation path, coefficients.py:240-964) does
+no state evolution and is outside the B200 backend's scope.
+"""
+
+from __future__ import annotations
+
+import logging
+import math
+from functools import reduce
+from typing import Any, List, Optional, Tuple, Union
+
+import numpy as np
+
+from . import parallel
+from .model import Model
+
+log = logging.getLogger(__name__)
+
+
+class Coefficients:
+    @classmethod
+    def get_spectrum(cls, model: Model, mfs: int = 1, mts: int = 1, shift=False, trim=False,
+                     numerical_cap: Optional[float] = -1, **kwargs) -> Tuple[np.ndarray, Any]:
+        """FFT-based spectrum of ``model`` (coefficients.py:25-107).  Returns
+        ``(coeffs, freqs)``; ``coeffs`` keeps a trailing axis per parameter sample."""
+        kwargs.setdefault("force_mean", True)
+        kwargs.setdefault("execution_type", "expval")
+
+        coeffs, freqs = cls._fourier_transform(model, mfs=mfs, mts=mts, **kwargs)
+
+        if not np.isclose(np.sum(coeffs).imag, 0.0, atol=1.0e-6):
+            raise ValueError(
+                f"Spectrum is not real. Imaginary part of coefficients is: {np.sum(coeffs).imag}")
+
+        if trim:
+            for ax in range(model.n_input_feat):
+                if coeffs.shape[ax] % 2 == 0:
+                    mid = len(coeffs) // 2  # same index rule as coefficients.py:76-77
+                    coeffs = np.delete(coeffs, mid, axis=ax)
+                    freqs = [np.delete(f, len(f) // 2, axis=ax) for f in freqs]
+
+        if shift:
+            coeffs = np.fft.fftshift(coeffs, axes=list(range(model.n_input_feat)))
+            freqs = list(np.fft.fftshift(np.asarray(freqs)))
+
+        if numerical_cap is not None and numerical_cap > 0:
+            coeffs = np.where(np.abs(coeffs) < numerical_cap, np.zeros_like(coeffs), coeffs)
+            if model.n_input_feat == 1:
+                if coeffs.ndim == 1:
+                    alive = coeffs != 0
+                else:
+                    alive = np.any(coeffs != 0, axis=tuple(range(1, coeffs.ndim)))
+                coeffs = coeffs[alive]
+                freqs = [np.asarray(freqs[0])[alive]]
+
+        if len(freqs) == 1:
+            freqs = freqs[0]
+        return coeffs, freqs
+
+    @classmethod
+    def _fourier_transform(cls, model: Model, mfs: int, mts: int, **kwargs: Any):
+        """Sample the model on an equidistant grid and transform
+        (coefficients.py:109-150).  The grid length follows ``arange`` exactly as the
+        reference does (SURVEY 8(c) hazard (v))."""
+        F = model.n_input_feat
+        n_freqs = np.array([mfs * model.degree[i] for i in range(F)])
+        stop, step = 2 * mts * np.pi, 2 * np.pi / n_freqs
+        axes = [np.arange(0, stop, step[i]) for i in range(F)]
+        grid = np.array(np.meshgrid(*axes)).T.reshape(-1, F)
+
+        out = np.asarray(model(inputs=grid, **kwargs))
+        out = out.reshape(*[a.shape[0] for a in axes], -1).squeeze()
+        coeffs = np.fft.fftn(out, axes=list(range(F)))
+        freqs = [np.fft.fftfreq(int(mts * n_freqs[i]), 1 / n_freqs[i]) for i in range(F)]
+        return coeffs / math.prod(out.shape[0:F]), freqs
+
+    @classmethod
+    def get_psd(cls, coeffs: np.ndarray) -> np.ndarray:
+        """Power spectral density (coefficients.py:152-170)."""
+        c = np.asarray(coeffs)
+        return (2.0 / (len(c) ** 2)) * (c.real ** 2 + c.imag ** 2)
+
+    @classmethod
+    def evaluate_Fourier_series(cls, coefficients, frequencies,
+                                inputs: Union[np.ndarray, list, float]):
+        """Value(s) of the Fourier series at ``inputs`` (coefficients.py:172-236)."""
+        c = np.asarray(coefficients)
+
+        def flatten(freq_axes):
+            fa = [np.asarray(f) for f in freq_axes]
+            fgrid = np.stack(np.meshgrid(*fa, indexing="ij"), axis=-1).reshape(-1, len(fa))
+            return c.reshape(fgrid.shape[0], *c.shape[len(fa):]), fgrid
+
+        if isinstance(frequencies, list):
+            fc, ff = flatten(frequencies)
+        else:
+            fr = np.asarray(frequencies)
+            if fr.ndim == 1:
+                ff = fr[:, None]
+                fc = c.reshape(ff.shape[0], *c.shape[1:])
+            else:
+                n_feat, n_axis = fr.shape
+                if c.shape[:n_feat] == (n_axis,) * n_feat:
+                    fc, ff = flatten(list(fr))
+                else:
+                    ff = fr
+                    fc = c.reshape(ff.shape[0], *c.shape[1:])
+
+        x = np.asarray(inputs, dtype=float)
+        if x.ndim == 0:
+            x = x.reshape(1, 1)
+        elif x.ndim == 1:
+            if ff.shape[1] == 1:
+                x = x[:, None]
+            elif x.shape[0] == ff.shape[1]:
+                x = x[None, :]
+            else:
+                x = np.repeat(x[:, None], ff.shape[1], axis=1)
+        waves = np.exp(1j * (x @ ff.T))
+        return np.squeeze(np.real(np.tensordot(waves, fc, axes=([1], [0]))))
+
+
+class FourierTree:
+    """Analytic coefficient tree (coefficients.py:240-964): symbolic Pauli
+    bookkeeping without state evolution - not part of the B200 backend."""
+
+    def __init__(self, *a, **k):
+        raise NotImplementedError(
+            "FourierTree is outside the scope of the B200 circuit-execution backend")
+
+
+class _Stats:
+    """Additive sufficient statistics of the pairwise (missing-value tolerant)
+    correlation estimators of coefficients.py:1346-1498 for an (N, K) sample."""
+
+    FIELDS = ("nobs", "sum_x", "sum_y", "sum_cxy", "sum_ax2", "sum_ay2")
+
+    def __init__(self, mat: np.ndarray):
+        mat = np.asarray(mat)
+        mask = np.isfinite(mat)
+        fm = mask.astype(np.float64)
+        safe = np.where(mask, mat, 0.0)
+        self.nobs = fm.T @ fm
+        self.sum_x = safe.T @ fm
+        self.sum_y = fm.T @ safe
+        self.sum_cxy = np.conj(safe).T @ safe
+        a2 = np.abs(safe) ** 2
+        self.sum_ax2 = a2.T @ fm
+        self.sum_ay2 = fm.T @ a2
+
+    def allreduce(self) -> "_Stats":
+        """One all-reduce of the concatenated K x K blocks across ranks."""
+        if parallel.world()[1] == 1:
+            return self
+        K = self.nobs.shape[0]
+        buf = np.stack([np.asarray(getattr(self, f), dtype=np.complex128)
+                        for f in self.FIELDS])
+        buf = parallel.allreduce_sum(buf)
+        for f, blk in zip(self.FIELDS, buf):
+            keep_c = f in ("sum_x", "sum_y", "sum_cxy") and np.iscomplexobj(getattr(self, f))
+            setattr(self, f, blk.reshape(K, K) if keep_c else blk.real.reshape(K, K))
+        return self
+
+    def covariance(self, minp: int) -> np.ndarray:
+        n_safe = np.where(self.nobs > 0, self.nobs, 1.0)
+        sxy = self.sum_cxy - (np.conj(self.sum_x) * self.sum_y) / n_safe
+        with np.errstate(invalid="ignore", divide="ignore"):
+            res = sxy / np.where(self.nobs > 1, self.nobs - 1, np.nan)
+        return np.where(self.nobs < minp, np.nan, res)
+
+    def complex_pearson(self, minp: int) -> np.ndarray:
+        n_safe = np.where(self.nobs > 0, self.nobs, 1.0)
+        ssx = self.sum_ax2 - np.abs(self.sum_x) ** 2 / n_safe
+        ssy = self.sum_ay2 - np.abs(self.sum_y) ** 2 / n_safe
+        sxy = self.sum_cxy - (np.conj(self.sum_x) * self.sum_y) / n_safe
+        with np.errstate(invalid="ignore", divide="ignore"):
+            den = np.sqrt(ssx * ssy)
+            res = np.where(den > 0, sxy / den, np.nan)
+            mag = np.abs(res)
+            res = np.where(mag > 1.0, res / mag, res)
+        return np.where(self.nobs < minp, np.nan, res)
+
+
+class FCC:
+    @classmethod
+    def get_fcc(cls, model: Model, n_samples: int, random_key=None,
+                method: Optional[str] = "pearson", scale: Optional[bool] = False,
+                weight: Optional[bool] = False, trim_redundant: Optional[bool] = True,
+                **kwargs) -> float:
+        """Fourier coefficient correlation: mean |correlation| over the strict lower
+        triangle of the non-negative-frequency block (coefficients.py:968-1037)."""
+        if trim_redundant and not weight:
+            _, coeffs, freqs = cls._calculate_coefficients(model, n_samples, random_key, scale,
+                                                           **kwargs)
+            pos = cls._calculate_mask(freqs)
+            sub = coeffs.reshape(-1, coeffs.shape[-1])[pos]
+            fp = cls._correlate(sub.transpose(), method=method)
+            afp = np.abs(fp)
+            diag = np.abs(np.diagonal(fp))
+            lower_sum = (np.nansum(afp) - np.nansum(diag)) / 2.0
+            lower_cnt = (np.sum(np.isfinite(afp)) - np.sum(np.isfinite(diag))) / 2.0
+            return lower_sum / lower_cnt
+        fp, _ = cls.get_fourier_fingerprint(model, n_samples, random_key, method, scale, weight,
+                                            trim_redundant=trim_redundant, **kwargs)
+        return cls.calculate_fcc(fp)
+
+    @classmethod
+    def get_fourier_fingerprint(cls, model: Model, n_samples: int, random_key=None,
+                                method: Optional[str] = "pearson",
+                                scale: Optional[bool] = False, weight: Optional[bool] = False,
+                                trim_redundant: Optional[bool] = True,
+                                nan_to_one: Optional[bool] = False, **kwargs: Any):
+        """Correlation matrix of the coefficients over parameter samples
+        (coefficients.py:1039-1160)."""
+        _, coeffs, freqs = cls._calculate_coefficients(model, n_samples, random_key, scale,
+                                                       **kwargs)
+
+        def lower_block(fp, pos_freqs):
+            M = fp.shape[0]
+            fp = np.where(np.tri(M, k=-1, dtype=bool), fp, np.nan)
+            rows = np.any(np.isfinite(fp), axis=1)
+            cols = np.any(np.isfinite(fp), axis=0)
+            return fp[rows][:, cols], (pos_freqs[rows], pos_freqs[cols])
+
+        if trim_redundant and not weight:
+            pos = cls._calculate_mask(freqs)
+            pos_freqs = cls._flat_frequencies(freqs)[pos]
+            sub = coeffs.reshape(-1, coeffs.shape[-1])[pos]
+            fp = cls._correlate(sub.transpose(), method=method)
+            if nan_to_one:
+                fp = np.where(np.isnan(fp), 1.0, fp)
+            return lower_block(fp, pos_freqs)
+
+        fp = cls._correlate(coeffs.reshape(-1, coeffs.shape[-1]).transpose(), method=method)
+        if nan_to_one:
+            fp = np.where(np.isnan(fp), 1.0, fp)
+        if weight:
+            fp = cls._weighting_mean(fp, coeffs)
+        if trim_redundant:
+            pos = cls._calculate_mask(freqs)
+            pos_freqs = cls._flat_frequencies(freqs)[pos]
+            return lower_block(fp[pos][:, pos], pos_freqs)
+        return fp, freqs
+
+    @classmethod
+    def calculate_fcc(cls, fourier_fingerprint: np.ndarray) -> float:
+        return np.nanmean(np.abs(fourier_fingerprint))
+
+    @classmethod
+    def _calculate_coefficients(cls, model: Model, n_samples: int, random_key=None,
+                                scale: bool = False, **kwargs: Any):
+        """Coefficients for ``n_samples`` random parameter sets
+        (coefficients.py:1257-1298).  Distributed: this rank evaluates its slice of
+        the sample axis only; the returned coefficient array holds the local columns."""
+        if n_samples > 0:
+            total = int(2 ** model.n_qubits * n_samples * model.n_input_feat) if scale \
+                else n_samples
+            model.initialize_params(random_key, repeat=total)
+        rank, size = parallel.world()
+        if size > 1 and model.params.shape[0] > 1:
+            lo, hi = parallel.shard_bounds(model.params.shape[0], rank, size)
+            kwargs = dict(kwargs, params=model.params[lo:hi])
+        coeffs, freqs = Coefficients.get_spectrum(model, shift=True, trim=True, **kwargs)
+        return model.params, coeffs, freqs
+
+    @classmethod
+    def _calculate_mask(cls, freqs) -> np.ndarray:
+        """Flat indices of the non-negative-frequency rows (coefficients.py:1180-1226)."""
+        fa = np.asarray(freqs)
+        if fa.ndim == 1:
+            return np.where(fa >= 0)[0]
+        n_axes = fa.shape[0]
+        masks = []
+        for i in range(n_axes):
+            shape = [1] * n_axes
+            shape[i] = fa.shape[1]
+            masks.append((fa[i] >= 0).reshape(shape))
+        return np.where(reduce(np.logical_and, masks).flatten())[0]
+
+    @classmethod
+    def _flat_frequencies(cls, freqs) -> np.ndarray:
+        fa = np.asarray(freqs)
+        if fa.ndim == 1:
+            return fa
+        grids = np.meshgrid(*[fa[i] for i in range(fa.shape[0])], indexing="ij")
+        return np.stack(grids, axis=-1).reshape(-1, fa.shape[0])
+
+    # -- correlation estimators (rows = samples, columns = coefficients) ----------------
+    @classmethod
+    def _correlate(cls, mat: np.ndarray, method: str = "pearson") -> np.ndarray:
+        min_periods = 1
+        if method == "pearson":
+            return cls._pearson(mat, min_periods)
+        if method == "complex_pearson":
+            return cls._complex_pearson(mat, min_periods)
+        if method == "spearman":
+            return cls._spearman(mat, min_periods)
+        if method == "covariance":
+            return cls._covariance(mat, min_periods)
+        raise ValueError(
+            f"Unknown method: {method}. Must be 'pearson', 'complex_pearson', 'spearman' "
+            "or 'covariance'.")
+
+    @classmethod
+    def _covariance(cls, mat: np.ndarray, minp: Optional[int] = 1) -> np.ndarray:
+        """Hermitian sample covariance between columns (coefficients.py:1346-1398)."""
+        return _Stats(mat).allreduce().covariance(minp)
+
+    @classmethod
+    def _complex_pearson(cls, mat: np.ndarray, minp: Optional[int] = 1) -> np.ndarray:
+        return _Stats(mat).allreduce().complex_pearson(minp)
+
+    @classmethod
+    def _pearson(cls, mat: np.ndarray, minp: Optional[int] = 1) -> np.ndarray:
+        """Pearson correlation; complex samples contribute their real and imaginary
+        parts as separate observations (coefficients.py:1456-1498)."""
+        mat = np.asarray(mat)
+        if np.iscomplexobj(mat):
+            mat = np.concatenate([mat.real, mat.imag], axis=0)
+        cov = _Stats(mat).allreduce().covariance(minp)
+        with np.errstate(invalid="ignore", divide="ignore"):
+            std = np.sqrt(np.diagonal(cov))
+            den = std[:, None] * std[None, :]
+            res = np.where(den > 0, cov / den, np.nan)
+        return np.clip(np.real(res), -1.0, 1.0)
+
+    @classmethod
+    def _spearman(cls, mat: np.ndarray, minp: Optional[int] = 1) -> np.ndarray:
+        """Rank correlation (coefficients.py:1500-1580): ranks are global, so the
+        samples of all ranks are gathered first."""
+        from scipy.stats import rankdata
+
+        mat = parallel.allgather_concat(np.asarray(mat), axis=0)
+        if np.iscomplexobj(mat):
+            mat = np.concatenate([mat.real, mat.imag], axis=0)
+        N, K = mat.shape
+        if N < minp:
+            return np.full((K, K), np.nan)
+        mask = np.isfinite(mat)
+        ranks = np.full((N, K), np.nan)
+        for j in range(K):
+            if mask[:, j].any():
+                ranks[mask[:, j], j] = rankdata(mat[mask[:, j], j], method="average")
+        st = _Stats(ranks)  # already global: no all-reduce
+        res = np.real(st.complex_pearson(minp))
+        return np.clip(res, -1.0, 1.0)
+
+    @classmethod
+    def _weighting_linear(cls, fp: np.ndarray) -> np.ndarray:
+        """Tent weighting peaking at zero frequency (coefficients.py:1582-1617)."""
+        assert fp.shape[0] % 2 != 0 and fp.shape[1] % 2 != 0, (
+            "Correlation matrix must have odd dimensions. "
+            "Hint: use `trim` argument when calling `get_spectrum`.")
+        assert fp.shape[0] == fp.shape[1], "Correlation matrix must be square."
+        N = fp.shape[0]
+        c = N // 2
+        u = (c - np.abs(np.arange(N) - c)) / (2 * c)
+        return fp * (u[:, None] + u[None, :])
+
+    @classmethod
+    def _weighting_mean(cls, fp: np.ndarray, coeffs: np.ndarray) -> np.ndarray:
+        """Weight by |mean coefficient| of both partners (coefficients.py:1619-1650)."""
+        assert fp.shape[0] == fp.shape[1], "Correlation matrix must be square."
+        assert len(coeffs.shape) >= 2, (
+            "Coefficient matrix must contain coefficient axes and a sample axis.")
+        stats = np.stack([np.sum(coeffs, axis=-1).T.reshape(-1),
+                          np.full(int(np.prod(coeffs.shape[:-1])), coeffs.shape[-1],
+                                  dtype=np.complex128)])
+        stats = parallel.allreduce_sum(stats)
+        w = np.abs(stats[0] / stats[1])
+        assert fp.shape[0] == w.shape[0], (
+            "Correlation matrix size must match the number of Fourier coefficients.")
+        return fp * w[:, None] * w[None, :]

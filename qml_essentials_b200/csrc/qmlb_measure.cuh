@@ -307,8 +307,13 @@ __global__ void __launch_bounds__(256) k_sample(const T* __restrict__ probs,
   }
 }
 
-// Single-qubit reduced purities Tr(rho_q^2) (entanglement.py:86-103).
-// One CTA per element; out[b][q].
+// Meyer-Wallach purities (entanglement.py:86-103): out[b][q] = Tr[(Tr_q rho)^2], the
+// purity of the state with qubit q traced out.
+//  * pure states: equals the purity of the single-qubit reduced state of qubit q
+//    (Schmidt decomposition), which is a 2x2 reduction over the statevector;
+//  * density matrices: sum over (a, c) in the remaining register of
+//    |rho[(a,0),(c,0)] + rho[(a,1),(c,1)]|^2.
+// One CTA per element.
 template <typename T>
 __global__ void __launch_bounds__(256) k_purity(const cx<T>* __restrict__ st, int density,
                                                 int n_qubits, T* __restrict__ out) {
@@ -318,31 +323,40 @@ __global__ void __launch_bounds__(256) k_purity(const cx<T>* __restrict__ st, in
   const cx<T>* s = st + (size_t)b * (density ? dim * dim : dim);
   for (int q = 0; q < n_qubits; ++q) {
     const int bit = n_qubits - 1 - q;
-    // reduced 2x2: r00, r11 real, r01 complex
-    T r00 = 0, r11 = 0, xr = 0, xi = 0;
-    for (int64_t g = threadIdx.x; g < dim / 2; g += blockDim.x) {
-      const int64_t low = g & (((int64_t)1 << bit) - 1);
-      const int64_t i0 = ((g >> bit) << (bit + 1)) | low, i1 = i0 | ((int64_t)1 << bit);
-      if (density) {
-        r00 += s[i0 * dim + i0].x;
-        r11 += s[i1 * dim + i1].x;
-        const cx<T> c = s[i0 * dim + i1];
-        xr += c.x;
-        xi += c.y;
-      } else {
+    const int64_t lowmask = ((int64_t)1 << bit) - 1;
+    if (density) {
+      const int64_t half = dim / 2;
+      T acc = 0;
+      for (int64_t g = threadIdx.x; g < half * half; g += blockDim.x) {
+        const int64_t ga = g / half, gc = g % half;
+        const int64_t a0 = ((ga >> bit) << (bit + 1)) | (ga & lowmask);
+        const int64_t c0 = ((gc >> bit) << (bit + 1)) | (gc & lowmask);
+        const int64_t a1 = a0 | ((int64_t)1 << bit), c1 = c0 | ((int64_t)1 << bit);
+        const cx<T> x = s[a0 * dim + c0], y = s[a1 * dim + c1];
+        const T re = x.x + y.x, im = x.y + y.y;
+        acc += re * re + im * im;
+      }
+      acc = block_sum<T>(acc, red);
+      if (threadIdx.x == 0) out[b * n_qubits + q] = acc;
+    } else {
+      // reduced 2x2 of qubit q: r00, r11 real, r01 complex
+      T r00 = 0, r11 = 0, xr = 0, xi = 0;
+      for (int64_t g = threadIdx.x; g < dim / 2; g += blockDim.x) {
+        const int64_t i0 = ((g >> bit) << (bit + 1)) | (g & lowmask);
+        const int64_t i1 = i0 | ((int64_t)1 << bit);
         const cx<T> a = s[i0], c = s[i1];
         r00 += a.x * a.x + a.y * a.y;
         r11 += c.x * c.x + c.y * c.y;
         xr += a.x * c.x + a.y * c.y;  // a * conj(c)
         xi += a.y * c.x - a.x * c.y;
       }
+      r00 = block_sum<T>(r00, red);
+      r11 = block_sum<T>(r11, red);
+      xr = block_sum<T>(xr, red);
+      xi = block_sum<T>(xi, red);
+      if (threadIdx.x == 0)
+        out[b * n_qubits + q] = r00 * r00 + r11 * r11 + (T)2 * (xr * xr + xi * xi);
     }
-    r00 = block_sum<T>(r00, red);
-    r11 = block_sum<T>(r11, red);
-    xr = block_sum<T>(xr, red);
-    xi = block_sum<T>(xi, red);
-    if (threadIdx.x == 0)
-      out[b * n_qubits + q] = r00 * r00 + r11 * r11 + (T)2 * (xr * xr + xi * xi);
   }
 }
 

@@ -670,9 +670,15 @@ class Model:
                              noise_params=noise_params, execution_type=execution_type,
                              force_mean=force_mean, gate_mode=gate_mode)
 
+    def device_result(self, **call_kwargs):
+        """Extension for the analysis callers: same arguments as ``__call__``, but
+        the raw batched result ((B, ...) in flat batch order, full register, no
+        post-processing) stays on the GPU as a ``torch`` tensor."""
+        return self._forward(_device=True, **call_kwargs)
+
     def _forward(self, params=None, inputs=None, pulse_params=None, enc_params=None,
                  data_reupload=None, noise_params=None, execution_type=None,
-                 force_mean: bool = False, gate_mode: str = "unitary"):
+                 force_mean: bool = False, gate_mode: str = "unitary", _device: bool = False):
         """Validate, batch, dispatch, reshape (model.py:1572-1737)."""
         if noise_params is not None:
             self.noise_params = noise_params
@@ -713,12 +719,17 @@ class Model:
             result = self.script.execute(
                 type=meas_type, obs=obs,
                 args=(params, inputs, pulse_params, keys, enc_params),
-                kwargs=exec_kwargs, in_axes=in_axes, shots=self.shots, key=shot_key)
+                kwargs=exec_kwargs, in_axes=in_axes, shots=self.shots, key=shot_key,
+                device_result=_device)
         else:
             result = self.script.execute(
                 type=meas_type, obs=obs,
                 args=(params, inputs, pulse_params, sub_key, enc_params),
-                kwargs=exec_kwargs, shots=self.shots, key=shot_key)
+                kwargs=exec_kwargs, shots=self.shots, key=shot_key, device_result=_device)
+            if _device:
+                result = result[None]
+        if _device:
+            return result
 
         result = self._postprocess_res(result)
         if self.execution_type == "density" and not self.all_qubit_measurement:

@@ -185,8 +185,13 @@ class Script:
         in_axes: Optional[Tuple] = None,
         shots: Optional[int] = None,
         key=None,
+        device_result: bool = False,
     ):
         """Execute the circuit and measure (script.py:137-219).
+
+        ``device_result=True`` (extension, used by the analysis callers) returns the
+        batched result as a device-resident ``torch`` tensor instead of copying it to
+        the host, so reductions (purities, pair fidelities) can run on the GPU.
 
         ``type``: ``"expval"`` | ``"probs"`` | ``"state"`` | ``"density"``.  Without
         ``in_axes`` the result has the bare measurement shape; with ``in_axes`` (one
@@ -208,7 +213,7 @@ class Script:
             in_axes = (None,) * len(args)
         batch = self._batch_size(args, in_axes)
         result = self._execute_batched(type, obs, args, kwargs, tuple(in_axes), batch,
-                                       shots, key)
+                                       shots, key, device_result)
         return result if batched else result[0]
 
     # -- helpers ----------------------------------------------------------------
@@ -415,7 +420,8 @@ class Script:
             self._jit_cache[mem_key] = chunk
         return chunk
 
-    def _execute_batched(self, type, obs, args, kwargs, in_axes, batch, shots=None, key=None):
+    def _execute_batched(self, type, obs, args, kwargs, in_axes, batch, shots=None, key=None,
+                         device_result=False):
         for_shots = shots is not None and type in ("probs", "expval")
         # the set of baked (value-keyed) arguments is discovered on the first build
         probe_key = ("_baked", type, tuple(
@@ -447,6 +453,8 @@ class Script:
                 return est
             diags = np.stack([_lifted_diag(o, plan.n_qubits) for o in obs])
             return np.real(est @ diags.T)  # simulation.py:367-372
+        if device_result:
+            return ex.execute(plan, host_args, batch, chunk, to_host=False)
         return ex.execute(plan, host_args, batch, chunk)
 
     # -- drawing (host only; rendering back ends are out of scope) -------------------

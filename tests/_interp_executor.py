@@ -18,7 +18,7 @@ class InterpExecutor:
         args = [(a[0], a[1], a[2]) if a is not None else (None, 1, 1) for a in host_args]
         return pi.Interp(plan.program, args, batch).run()
 
-    def execute(self, plan, host_args, batch, chunk=None):
+    def execute(self, plan, host_args, batch, chunk=None, to_host=True):
         st = self._states(plan, host_args, batch)
         out = pi.measure(plan.program, st, _NAMES[plan.out_type], plan.obs_recs,
                          plan.obs_pool)
@@ -35,3 +35,34 @@ class InterpExecutor:
             idx = np.minimum(osim.choice_indices(probs[b], uniforms[b]), dim - 1)
             np.add.at(counts[b], idx, 1)
         return counts
+
+    # analysis reductions (device kernels qmlb_purity / qmlb_overlap_fidelity in the product)
+    def purities(self, states, n_qubits, is_density):
+        st = np.asarray(states)
+        B, dim = st.shape[0], 2 ** n_qubits
+        rho = st.reshape(B, dim, dim) if is_density else np.einsum("bi,bj->bij", st, st.conj())
+        out = np.zeros((B, n_qubits))
+        t = rho.reshape((B,) + (2,) * (2 * n_qubits))
+        for q in range(n_qubits):
+            red = np.trace(t, axis1=1 + q, axis2=1 + n_qubits + q)
+            red = red.reshape(B, dim // 2, dim // 2)
+            out[:, q] = np.real(np.einsum("bij,bji->b", red, red))
+        return _Host(out)
+
+    def overlap_fidelities(self, states, n_qubits):
+        st = np.asarray(states)
+        half = st.shape[0] // 2
+        return _Host(np.abs(np.einsum("bi,bi->b", st[:half].conj(), st[half:])) ** 2)
+
+
+class _Host:
+    """numpy array with the ``.cpu().numpy()`` surface of a torch tensor."""
+
+    def __init__(self, a):
+        self.a = a
+
+    def cpu(self):
+        return self
+
+    def numpy(self):
+        return self.a

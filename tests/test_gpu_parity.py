@@ -189,3 +189,39 @@ def test_device_side_purity_and_overlap_reductions():
                        atol=1e-12)
     rho_b = torch.from_numpy(np.einsum("bi,bj->bij", st, st.conj())).to(ex.device)
     assert np.allclose(ex.purities(rho_b, n, True).cpu().numpy(), pur, atol=1e-12)
+
+
+def test_analysis_callers_through_device_reductions():
+    """Coefficients / Expressibility / Entanglement on the GPU: states stay in HBM,
+    purities and pair fidelities are reduced by qmlb_purity / qmlb_overlap_fidelity."""
+    from qml_essentials_b200.coefficients import FCC, Coefficients
+    from qml_essentials_b200.entanglement import Entanglement
+    from qml_essentials_b200.expressibility import Expressibility
+
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        m = Model(4, 2, "Hardware_Efficient")
+        coeffs, freqs = Coefficients.get_spectrum(m, shift=True)
+        x = np.array([0.4, 2.2, 5.1])
+        want = np.asarray(m(inputs=x.reshape(-1, 1), force_mean=True)).reshape(-1)
+        assert np.allclose(Coefficients.evaluate_Fourier_series(coeffs, freqs, x), want,
+                           atol=1e-10)
+        assert 0 <= FCC.get_fcc(model=m, n_samples=64) <= 1
+
+        m6 = Model(6, 3, "Circuit_15")
+        mw = Entanglement.meyer_wallach(m6, n_samples=200)
+        rho = m6(params=m6.params, inputs=None, execution_type="density")
+        assert abs(mw - Entanglement._compute_meyer_wallach_meas(rho, 6).mean()) < 1e-10
+        noise = {"Depolarizing": 0.02}
+        m3 = Model(3, 2, "Strongly_Entangling")
+        mwn = Entanglement.meyer_wallach(m3, n_samples=20, noise_params=dict(noise))
+        rho = m3(params=m3.params, inputs=None, execution_type="density",
+                 noise_params=dict(noise))
+        assert abs(mwn - Entanglement._compute_meyer_wallach_meas(rho, 3).mean()) < 1e-10
+
+        fid = Expressibility._sample_state_fidelities(m6, 500, kwargs={})
+        rho = m6(params=m6.params, execution_type="density")
+        ref = np.abs(np.einsum("bij,bji->b", rho[:500], rho[500:]))
+        assert np.allclose(fid, ref, atol=1e-10)
+        kl = Expressibility.kl_divergence_to_haar(model=m6, n_samples=2000, n_bins=75)
+        assert np.isfinite(kl).all() and kl.mean() >= 0
