@@ -115,6 +115,68 @@ def oracle_cpu_evals_per_s(params, inputs, n_param_sample, threads, repeats=2):
     return B / best, ev.reshape(B_I, B_P, N_QUBITS), f"{B_I} grid points x {B_P} param sets"
 
 
+def gate_pass_leg(ex, n_qubits, reps, dev):
+    """BASELINE configs[4] / SURVEY 8(d) cfg 5: Model(n, 8, 'Hardware_Efficient'), complex64,
+    one circuit, expval on all qubits; the state lives in HBM and every launch of k_stream is
+    one fused gate pass (read + write of the 2^n amplitudes).  Returns the bench object with
+    the average HBM GB/s per pass (CUDA events around qmlb_run, state larger than L2)."""
+    import torch
+
+    from qml_essentials_b200 import config, script
+    from qml_essentials_b200.model import Model
+
+    prev = config.get_precision()
+    config.set_precision("complex64")
+    try:
+        model = Model(n_qubits=n_qubits, n_layers=8, circuit_type="Hardware_Efficient")
+        rng = np.random.default_rng(1000)
+        params = rng.uniform(0.0, 2 * np.pi, (1, *model._params_shape))
+        inputs = np.array([[0.5]])
+        ev = model(params=params, inputs=inputs)  # plan + first run
+        plan = [p for p in model.script._jit_cache.values()
+                if hasattr(p, "program") and p.device][-1]
+        handle = list(plan.device.values())[0]
+        args = (model._params_validation(params), model._inputs_validation(inputs),
+                model.pulse_params, model.random_key, model.enc_params)
+        host_args = model.script._device_args(plan, args, (None,) * 5, 1)
+        call = ex.stage(plan, host_args, 1)
+        call.launch()
+        torch.cuda.synchronize()
+        times = []
+        for _ in range(reps):
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            out = call.launch()
+            e.record()
+            torch.cuda.synchronize()
+            times.append(s.elapsed_time(e))
+        ms = float(np.mean(times))
+        state_bytes = 8 * 2 ** n_qubits
+        passes = handle.n_passes
+        # first pass does not read; the <Z_q> sweep adds one read of the state
+        algo_bytes = 2 * passes * state_bytes
+        norm_ok = bool(np.all(np.abs(out.cpu().numpy()) <= 1 + 1e-4))
+        same = bool(np.allclose(out.cpu().numpy().reshape(-1), np.asarray(ev).reshape(-1),
+                                atol=1e-6))
+        return {"workload": f"Model({n_qubits},8,'Hardware_Efficient') complex64 expval, "
+                            "1 circuit, state in HBM", "n_qubits": n_qubits,
+                "state_gib": state_bytes / 2 ** 30, "passes": passes,
+                "device_ops": handle.n_device_ops, "ms_per_circuit": ms,
+                "ms_per_pass": ms / passes, "bytes_per_pass": 2 * state_bytes,
+                "achieved_gbs": algo_bytes / (ms * 1e-3) / 1e9, "kernel": "k_stream<float,5>",
+                "checks": {"abs_expval_le_1": norm_ok, "repeatable": same}}
+    finally:
+        config.set_precision(prev)
+
+
+def hbm_peak_gbs():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -158,6 +220,9 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--precision", default="complex128", choices=["complex128", "complex64"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--gate-pass-qubits", type=int, default=-1,
+                    help="n for the HBM gate-pass leg (default: 32 on 1 GPU, 30 per rank "
+                         "otherwise; 0 disables)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -254,12 +319,24 @@ def main():
         res = model(params=params, inputs=inputs)
     barrier()
     e2e_s = time.perf_counter() - t0
-    clocks = sampler.stop() if rank == 0 else None
 
-    t = torch.tensor([dev_ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
+    # ---- HBM-streaming regime: GB/s per fused gate pass (every rank: its own state) ----
+    gp = None
+    gp_n = args.gate_pass_qubits if args.gate_pass_qubits >= 0 else (32 if world == 1 else 30)
+    if gp_n > 0:
+        del flush
+        torch.cuda.empty_cache()
+        try:
+            gp = gate_pass_leg(ex, gp_n, 2, dev)
+        except Exception as exc:  # noqa: BLE001  (e.g. not enough free HBM on a shared box)
+            gp = {"error": f"{type(exc).__name__}: {exc}"[:300], "n_qubits": gp_n}
+    clocks = sampler.stop() if rank == 0 else None
+    gp_ms = gp.get("ms_per_circuit", 0.0) if gp else 0.0
+
+    t = torch.tensor([dev_ms, e2e_s * 1e3, gp_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dev_ms, e2e_ms = float(t[0]), float(t[1])
+    dev_ms, e2e_ms, gp_ms = float(t[0]), float(t[1]), float(t[2])
 
     if rank == 0:
         total_evals = B * world * args.steps
@@ -299,6 +376,14 @@ def main():
                         "this GPU (no FMA figure in MEASURED_PEAKS.json)",
             },
         }
+        if gp is not None and "error" not in gp:
+            peak, src = hbm_peak_gbs()
+            agg = world * 2 * gp["passes"] * 8 * 2 ** gp["n_qubits"] / (gp_ms * 1e-3) / 1e9
+            gp.update({"achieved_gbs": agg, "per_gpu_gbs": agg / world, "peak_gbs": peak,
+                       "peak_source": src, "frac": agg / world / peak, "n_gpus": world,
+                       "ms_per_circuit": gp_ms, "ms_per_pass": gp_ms / gp["passes"]})
+        if gp is not None:
+            line["gate_pass"] = gp
         if not args.no_cpu_baseline and world == 1:
             cores = os.cpu_count() or 1
             cpu_v, cpu_ev, sample = oracle_cpu_evals_per_s(params, inputs, 256, cores)

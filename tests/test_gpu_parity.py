@@ -225,3 +225,31 @@ def test_analysis_callers_through_device_reductions():
         assert np.allclose(fid, ref, atol=1e-10)
         kl = Expressibility.kl_divergence_to_haar(model=m6, n_samples=2000, n_bins=75)
         assert np.isfinite(kl).all() and kl.mean() >= 0
+
+
+def test_streamed_statevector_n18_matches_oracle():
+    """Natural strategy 2 (state in HBM, k_stream passes + one-sweep <Z_q>): 2^18
+    amplitudes against the oracle, both precisions."""
+    assert pc.case_model(18, 2, "Hardware_Efficient", 1, 1, "expval") < 1e-10
+    assert pc.case_model(18, 1, "Circuit_19", 2, 1, "expval", precision="complex64") < 1e-5
+    assert pc.case_model(15, 2, "Strongly_Entangling", 1, 2, "probs") < 1e-10
+
+
+def test_large_n_product_state_invariant():
+    """n = 27 (1 GiB state, complex64): a circuit without entanglers leaves a product
+    state, so <Z_q> of qubits 3g..3g+2 equals the 3-qubit model run with the same
+    parameters (register kernel, oracle-checked above) - a size-independent check of
+    pass scheduling, 32-bit index arithmetic and the one-sweep reduction."""
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        n = 27
+        m = Model(n, 1, "No_Entangling", precision="complex64")
+        p = np.random.default_rng(5).uniform(0, 2 * np.pi, (1, *m._params_shape))
+        x = np.array([[0.7]])
+        ev = np.asarray(m(params=p, inputs=x)).reshape(-1)
+        per = p.reshape(m._params_shape[0], n, -1)  # (layers', qubits, params per qubit)
+        small = Model(3, 1, "No_Entangling")
+        want = np.concatenate([
+            np.asarray(small(params=per[:, g:g + 3].reshape(1, per.shape[0], -1),
+                             inputs=x)).reshape(-1) for g in range(0, n, 3)])
+    assert np.allclose(ev, want, atol=2e-5)
