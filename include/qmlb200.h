@@ -99,6 +99,9 @@ extern "C" {
 #define QMLB_FLAG_DIAGVEC 2  /* CONST: 2^k diagonal entries instead of a matrix       */
 #define QMLB_FLAG_ROT_SHIFT 2 /* TRIG, k = 1: bits 2-3 = 1/2/3 -> exactly RX/RY/RZ    */
 
+/* qmlb_program_desc.reserved flags */
+#define QMLB_DESC_FORCE_STREAM 1 /* always plan HBM-streaming passes (qmlb_evolve) */
+
 #define QMLB_MAX_OP_BITS 8
 #define QMLB_MAX_ARGS 8
 
@@ -196,6 +199,27 @@ size_t qmlb_workspace_bytes(const qmlb_program* prog, const qmlb_arg* args, int3
 int qmlb_run(const qmlb_program* prog, const qmlb_arg* args, int32_t n_args, int64_t batch,
              int64_t batch_offset, void* out, void* workspace, size_t workspace_bytes,
              void* stream);
+
+/* Building blocks of the qubit-sharded statevector (nothing in the
+ * reference corresponds - it cannot hold a state beyond host RAM).  A rank keeps one
+ * shard of 2^n_bits amplitudes; the program (created with QMLB_DESC_FORCE_STREAM) holds
+ * the ops of one epoch between two global<->local exchanges, on local bits.
+ *
+ * qmlb_evolve applies the program's fused gate passes IN PLACE to `state`
+ * ((batch, 2^n_bits) complex of the program precision).  init_mode: 0 = continue from
+ * the amplitudes in `state`, 1 = start from |0..0>, 2 = start from the zero vector (a
+ * shard that does not contain index 0).  workspace: qmlb_workspace_bytes(...) bytes. */
+int qmlb_evolve(const qmlb_program* prog, const qmlb_arg* args, int32_t n_args, int64_t batch,
+                int64_t batch_offset, void* state, int32_t init_mode, void* workspace,
+                size_t workspace_bytes, void* stream);
+
+/* One sweep over pure states: out[b][q] = sum of |amp|^2 over indices with bit q set
+ * (q < n_bits), out[b][32] = total probability; double, (batch, 33).  <Z> of the qubit
+ * on bit q is out[32] - 2 out[q]; a sharded state adds the per-rank tables (and `total`
+ * for the rank-index bits that are set).  8 <= n_bits <= 32. */
+size_t qmlb_zsums_workspace_bytes(int64_t batch, int32_t n_bits);
+int qmlb_zsums(const void* state, int dtype, int64_t batch, int32_t n_bits, double* out,
+               void* workspace, size_t workspace_bytes, void* stream);
 
 /* Shot bookkeeping of simulation.py:352-357 for `batch` probability vectors of
  * length 2^n_qubits (float64 when dtype == QMLB_C128, else float32):

@@ -103,10 +103,14 @@ class Interp:
             loc |= ((v >> (k - 1 - j)) & 1) << b
         return base[:, None] | loc[None, :]
 
-    def run(self):
+    def run(self, state=None):
+        """Evolve |0..0> (or ``state``, shape (B, 2^n_bits), continued in place)."""
         p = self.p
-        st = np.zeros((self.B, 2**p.n_bits), dtype=np.complex128)
-        st[:, 0] = 1.0
+        if state is None:
+            st = np.zeros((self.B, 2**p.n_bits), dtype=np.complex128)
+            st[:, 0] = 1.0
+        else:
+            st = state
         for op in p.ops:
             k = op["k"]
             bits = list(op["bits"][:k])

@@ -119,6 +119,21 @@ def measure_state(state, n_qubits, type, obs=()):
     if type == "probs":
         return np.abs(state) ** 2
     if type == "expval":
+        if n_qubits > 10:
+            # the reference's fast path (simulation.py:251-261): 1-qubit diagonal
+            # observables from marginal probabilities.  Used here only where the dense
+            # lifted matrices (4^n entries) no longer fit; below that the dense path is
+            # kept as the independent restatement.
+            probs = (np.abs(state) ** 2).reshape((2,) * n_qubits)
+            out = []
+            for ob in obs:
+                name, wires, params, extra = _entry(ob)
+                O = G.unitary_matrix(name, wires, params, extra)
+                if len(wires) != 1 or np.count_nonzero(O - np.diag(np.diag(O))):
+                    raise ValueError("oracle: only 1-qubit diagonal observables beyond 10 qubits")
+                marg = probs.sum(axis=tuple(a for a in range(n_qubits) if a != wires[0]))
+                out.append(float(np.real(np.diag(O)) @ marg))
+            return np.array(out)
         mats = [lifted_matrix(ob, n_qubits) for ob in obs]
         return np.array([np.real(np.conj(state) @ (O @ state)) for O in mats])
     raise ValueError(f"Unknown measurement type: {type!r}")

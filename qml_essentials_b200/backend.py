@@ -31,7 +31,9 @@ EXPORTED_SYMBOLS = (
     "qmlb_version", "qmlb_launch_count", "qmlb_last_error", "qmlb_program_create",
     "qmlb_program_destroy", "qmlb_program_info", "qmlb_workspace_bytes", "qmlb_run",
     "qmlb_sample", "qmlb_purity", "qmlb_overlap_fidelity", "qmlb_fma_peak",
+    "qmlb_evolve", "qmlb_zsums", "qmlb_zsums_workspace_bytes",
 )
+QMLB_DESC_FORCE_STREAM = 1
 
 
 class BackendUnavailable(RuntimeError):
@@ -90,6 +92,12 @@ def load_library(path: str = LIB_PATH) -> C.CDLL:
     lib.qmlb_overlap_fidelity.argtypes = [C.c_void_p, C.c_int, C.c_int64, C.c_int32,
                                           C.c_void_p, C.c_void_p]
     lib.qmlb_fma_peak.argtypes = [C.c_int, C.POINTER(C.c_double)]
+    lib.qmlb_evolve.argtypes = [C.c_void_p, C.POINTER(_Arg), C.c_int32, C.c_int64, C.c_int64,
+                                C.c_void_p, C.c_int32, C.c_void_p, C.c_size_t, C.c_void_p]
+    lib.qmlb_zsums_workspace_bytes.argtypes = [C.c_int64, C.c_int32]
+    lib.qmlb_zsums_workspace_bytes.restype = C.c_size_t
+    lib.qmlb_zsums.argtypes = [C.c_void_p, C.c_int, C.c_int64, C.c_int32, C.c_void_p,
+                               C.c_void_p, C.c_size_t, C.c_void_p]
     return lib
 
 
@@ -100,7 +108,8 @@ def _np_ptr(a: np.ndarray) -> Optional[int]:
 class ProgramHandle:
     """Owns one ``qmlb_program*`` (created on the current CUDA device)."""
 
-    def __init__(self, lib, prog: Program, out_type: int, obs_recs, obs_pool, precision: str):
+    def __init__(self, lib, prog: Program, out_type: int, obs_recs, obs_pool, precision: str,
+                 flags: int = 0):
         self.lib = lib
         self.ptr = C.c_void_p()
         dt = QMLB_C128 if precision == "complex128" else QMLB_C64
@@ -110,7 +119,7 @@ class ProgramHandle:
             prog.pre if prog.pre is not None else np.zeros(0, dtype=compiler.PRE_DTYPE))]
         d = _Desc(
             n_qubits=prog.n_qubits, n_bits=prog.n_bits, density=int(prog.density), dtype=dt,
-            out_type=int(out_type), reserved=0,
+            out_type=int(out_type), reserved=int(flags),
             ops=_np_ptr(keep[0]), n_ops=len(keep[0]),
             sources=_np_ptr(keep[1]), n_sources=len(keep[1]),
             items=_np_ptr(keep[2]), n_items=len(keep[2]),

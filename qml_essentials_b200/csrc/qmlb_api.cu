@@ -457,7 +457,7 @@ int plan(qmlb_program* p) {
   }
   const size_t cs = cs_of(p->dtype);
   const int N = p->n_bits;
-  const int force = env_int("QMLB_FORCE_STRATEGY", -1);
+  const int force = p->force_stream ? 2 : env_int("QMLB_FORCE_STRATEGY", -1);
 
   // ---- strategy 0: registers --------------------------------------------------
   bool reg_ok = !p->density && N <= REG_MAX_BITS;
@@ -645,14 +645,14 @@ size_t state_layout(const qmlb_program* p, int64_t batch, size_t* part_off) {
   return (need + 255) & ~size_t(255);
 }
 
+// fills the hoisted-factor tables at the start of `workspace`; returns their size
 template <typename T>
-int run_typed(const qmlb_program* p, RunArgs& R, void* out, void* workspace, size_t ws_bytes,
-              cudaStream_t st) {
+int prepare_tables(const qmlb_program* p, RunArgs& R, void* workspace, size_t ws_bytes,
+                   cudaStream_t st, size_t* tab_bytes_out) {
   bool on[QMLB_MAX_ARGS];
-  size_t toff[QMLB_MAX_ARGS], part_off = 0;
+  size_t toff[QMLB_MAX_ARGS];
   const size_t tab_bytes = pre_layout(p, R.a, R.batch, on, toff);
-  const size_t need = tab_bytes + state_layout(p, R.batch, &part_off);
-  if (need > ws_bytes) return fail(QMLB_ERR_WORKSPACE, "workspace too small");
+  if (tab_bytes > ws_bytes) return fail(QMLB_ERR_WORKSPACE, "workspace too small");
   unsigned char* wsb = static_cast<unsigned char*>(workspace);
   for (int s = 0; s < QMLB_MAX_ARGS; ++s) {
     R.pre_on[s] = on[s];
@@ -666,27 +666,62 @@ int run_typed(const qmlb_program* p, RunArgs& R, void* out, void* workspace, siz
     k_pre<T><<<(unsigned)((total + 127) / 128), 128, 0, st>>>(
         p->dev, R, s, p->pre_ids_dev[s], n_ids, reinterpret_cast<cx<T>*>(wsb + toff[s]));
   }
-  unsigned char* ws_state = wsb + tab_bytes;
+  *tab_bytes_out = tab_bytes;
+  return QMLB_OK;
+}
+
+// the streamed gate passes over `state`; init_mode 1: |0..0>, 2: zero vector, 0: continue
+template <typename T>
+int evolve_stream(const qmlb_program* p, const RunArgs& R, void* state, int init_mode,
+                  cudaStream_t st) {
+  const int64_t items = int64_t(1) << (p->n_bits - p->stream_r);
+  const int64_t ctas_x = (items + STREAM_THREADS - 1) / STREAM_THREADS;
+  const int64_t want = (int64_t)p->sm_count * 16;  // persistent: CTAs loop over items / elements
+  dim3 grid;
+  if (R.batch == 1) {
+    grid = dim3((unsigned)std::max<int64_t>(1, std::min(ctas_x, want)), 1, 1);
+  } else {
+    const int64_t gx = std::max<int64_t>(1, std::min<int64_t>(ctas_x, 64));
+    const int64_t gy =
+        std::max<int64_t>(1, std::min<int64_t>(R.batch, std::max<int64_t>(1, want / gx)));
+    grid = dim3((unsigned)gx, (unsigned)std::min<int64_t>(gy, 65535), 1);
+  }
+  for (const QmlbStreamPassHost& ps : p->stream_passes) {
+    StreamPass pass = ps.dev;
+    if (pass.flags & QMLB_PASS_INIT) {
+      if (init_mode == 0) pass.flags &= ~QMLB_PASS_INIT;
+      if (init_mode == 2) pass.flags |= QMLB_PASS_INIT_ZERO;
+    }
+    CUDA_TRY((std::is_same<T, double>::value ? launch_stream_f64 : launch_stream_f32)(
+        p, R, pass, grid, state, st));
+  }
+  return QMLB_OK;
+}
+
+template <typename T>
+int run_typed(const qmlb_program* p, RunArgs& R, void* out, void* workspace, size_t ws_bytes,
+              cudaStream_t st) {
+  size_t tab_bytes = 0, part_off = 0;
+  {
+    bool on[QMLB_MAX_ARGS];
+    size_t toff[QMLB_MAX_ARGS];
+    const size_t need =
+        pre_layout(p, R.a, R.batch, on, toff) + state_layout(p, R.batch, &part_off);
+    if (need > ws_bytes) return fail(QMLB_ERR_WORKSPACE, "workspace too small");
+  }
+  {
+    int rc = prepare_tables<T>(p, R, workspace, ws_bytes, st, &tab_bytes);
+    if (rc != QMLB_OK) return rc;
+  }
+  unsigned char* ws_state = static_cast<unsigned char*>(workspace) + tab_bytes;
   cx<T>* state = p->direct_out ? static_cast<cx<T>*>(out) : reinterpret_cast<cx<T>*>(ws_state);
 
   if (p->strategy == 0) {
     void* dst = p->direct_out ? out : static_cast<void*>(ws_state);
     CUDA_TRY((std::is_same<T, double>::value ? launch_reg_f64 : launch_reg_f32)(p, R, dst, st));
   } else if (p->strategy == 2) {
-    const int64_t items = int64_t(1) << (p->n_bits - p->stream_r);
-    const int64_t ctas_x = (items + STREAM_THREADS - 1) / STREAM_THREADS;
-    const int64_t want = (int64_t)p->sm_count * 16;  // persistent: CTAs loop over items / elements
-    dim3 grid;
-    if (R.batch == 1) {
-      grid = dim3((unsigned)std::max<int64_t>(1, std::min(ctas_x, want)), 1, 1);
-    } else {
-      const int64_t gx = std::max<int64_t>(1, std::min<int64_t>(ctas_x, 64));
-      const int64_t gy = std::max<int64_t>(1, std::min<int64_t>(R.batch, std::max<int64_t>(1, want / gx)));
-      grid = dim3((unsigned)gx, (unsigned)std::min<int64_t>(gy, 65535), 1);
-    }
-    for (const QmlbStreamPassHost& ps : p->stream_passes)
-      CUDA_TRY((std::is_same<T, double>::value ? launch_stream_f64 : launch_stream_f32)(
-          p, R, ps.dev, grid, state, st));
+    int rc = evolve_stream<T>(p, R, state, 1, st);
+    if (rc != QMLB_OK) return rc;
   } else {
     for (const QmlbPassHost& ps : p->passes) {
       const int kt = (int)ps.tile_bits.size();
@@ -733,6 +768,7 @@ int qmlb_program_create(const qmlb_program_desc* d, qmlb_program** out) {
   p->density = d->density;
   p->dtype = d->dtype;
   p->out_type = d->out_type;
+  p->force_stream = (d->reserved & QMLB_DESC_FORCE_STREAM) != 0;
   p->ops.assign(d->ops, d->ops + d->n_ops);
   p->sources.assign(d->sources, d->sources + d->n_sources);
   p->items.assign(d->items, d->items + d->n_items);
@@ -789,14 +825,10 @@ size_t qmlb_workspace_bytes(const qmlb_program* p, const qmlb_arg* args, int32_t
   return pre_layout(p, a, batch, on, toff) + state_layout(p, batch, &part_off);
 }
 
-int qmlb_run(const qmlb_program* p, const qmlb_arg* args, int32_t n_args, int64_t batch,
-             int64_t batch_offset, void* out, void* workspace, size_t workspace_bytes,
-             void* stream) {
-  if (!p || !out) return fail(QMLB_ERR_INVALID, "null program or output");
-  if (batch <= 0) return QMLB_OK;
+static int fill_run_args(const qmlb_program* p, const qmlb_arg* args, int32_t n_args,
+                         int64_t batch, int64_t batch_offset, RunArgs& R) {
   if (n_args < 0 || n_args > QMLB_MAX_ARGS) return fail(QMLB_ERR_INVALID, "bad n_args");
   if (p->max_arg >= n_args) return fail(QMLB_ERR_INVALID, "program needs more arguments");
-  RunArgs R;
   std::memset(&R, 0, sizeof(R));
   for (int i = 0; i < QMLB_MAX_ARGS; ++i) {
     R.a[i].div = 1;
@@ -811,6 +843,71 @@ int qmlb_run(const qmlb_program* p, const qmlb_arg* args, int32_t n_args, int64_
     if (!R.a[t.arg].ptr) return fail(QMLB_ERR_INVALID, "program reads a NULL argument");
   R.batch = batch;
   R.batch_offset = batch_offset;
+  return QMLB_OK;
+}
+
+int qmlb_evolve(const qmlb_program* p, const qmlb_arg* args, int32_t n_args, int64_t batch,
+                int64_t batch_offset, void* state, int32_t init_mode, void* workspace,
+                size_t workspace_bytes, void* stream) {
+  if (!p || !state) return fail(QMLB_ERR_INVALID, "null program or state");
+  if (p->strategy != 2)
+    return fail(QMLB_ERR_INVALID, "qmlb_evolve needs a streaming program (QMLB_DESC_FORCE_STREAM)");
+  if (init_mode < 0 || init_mode > 2) return fail(QMLB_ERR_INVALID, "bad init_mode");
+  if (batch <= 0) return QMLB_OK;
+  RunArgs R;
+  int rc = fill_run_args(p, args, n_args, batch, batch_offset, R);
+  if (rc != QMLB_OK) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  size_t tab = 0;
+  if (p->dtype == QMLB_C128) {
+    rc = prepare_tables<double>(p, R, workspace, workspace_bytes, st, &tab);
+    return rc != QMLB_OK ? rc : evolve_stream<double>(p, R, state, init_mode, st);
+  }
+  rc = prepare_tables<float>(p, R, workspace, workspace_bytes, st, &tab);
+  return rc != QMLB_OK ? rc : evolve_stream<float>(p, R, state, init_mode, st);
+}
+
+size_t qmlb_zsums_workspace_bytes(int64_t batch, int32_t n_bits) {
+  if (batch <= 0 || n_bits < 8) return 0;
+  const int64_t units = int64_t(1) << (n_bits - 8);
+  const int64_t per = std::max<int64_t>(1, (148 * 8) / batch);
+  const int64_t ctas = std::max<int64_t>(1, std::min<int64_t>((units + 7) / 8, per));
+  return (size_t)batch * ctas * 33 * sizeof(double);
+}
+
+int qmlb_zsums(const void* state, int dtype, int64_t batch, int32_t n_bits, double* out,
+               void* workspace, size_t workspace_bytes, void* stream) {
+  if (!state || !out) return fail(QMLB_ERR_INVALID, "null argument");
+  if (n_bits < 8 || n_bits > 32) return fail(QMLB_ERR_UNSUPPORTED, "qmlb_zsums needs 8..32 bits");
+  if (batch <= 0) return QMLB_OK;
+  if (batch > 65535) return fail(QMLB_ERR_UNSUPPORTED, "qmlb_zsums batch > 65535");
+  const size_t need = qmlb_zsums_workspace_bytes(batch, n_bits);
+  if (need > workspace_bytes || !workspace) return fail(QMLB_ERR_WORKSPACE, "workspace too small");
+  const int ctas = (int)(need / ((size_t)batch * 33 * sizeof(double)));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  double* partial = static_cast<double*>(workspace);
+  g_launches.fetch_add(2, std::memory_order_relaxed);
+  if (dtype == QMLB_C128)
+    k_expval_z1<double><<<dim3((unsigned)ctas, (unsigned)batch), 256, 0, st>>>(
+        static_cast<const cx<double>*>(state), partial, n_bits);
+  else
+    k_expval_z1<float><<<dim3((unsigned)ctas, (unsigned)batch), 256, 0, st>>>(
+        static_cast<const cx<float>*>(state), partial, n_bits);
+  k_zsums_final<<<(unsigned)((batch * 33 + 255) / 256), 256, 0, st>>>(partial, out, batch, ctas);
+  CUDA_TRY(cudaGetLastError());
+  return QMLB_OK;
+}
+
+int qmlb_run(const qmlb_program* p, const qmlb_arg* args, int32_t n_args, int64_t batch,
+             int64_t batch_offset, void* out, void* workspace, size_t workspace_bytes,
+             void* stream) {
+  if (!p || !out) return fail(QMLB_ERR_INVALID, "null program or output");
+  if (batch <= 0) return QMLB_OK;
+  RunArgs R;
+  {
+    int rc = fill_run_args(p, args, n_args, batch, batch_offset, R);
+    if (rc != QMLB_OK) return rc;
+  }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (p->dtype == QMLB_C128) return run_typed<double>(p, R, out, workspace, workspace_bytes, st);
   return run_typed<float>(p, R, out, workspace, workspace_bytes, st);

@@ -45,6 +45,7 @@ struct qmlb_program {
   std::vector<int32_t> pre_ids[QMLB_MAX_ARGS];        // pre entries per argument slot
   const int32_t* pre_ids_dev[QMLB_MAX_ARGS] = {};     // same, in the device blob
   int max_arg = -1;
+  bool force_stream = false;
 
   int strategy = 0;
   bool direct_out = false;   // evolution kernel writes the final result itself

@@ -259,6 +259,18 @@ __global__ void k_expval_z1_final(DevProg P, const double* __restrict__ partial,
   out[i] = (T)(tot - 2.0 * sq);
 }
 
+// out[bl][q] = sum over CTAs (index order) of partial[(bl * ctas + c) * 33 + q]
+__global__ void k_zsums_final(const double* __restrict__ partial, double* __restrict__ out,
+                              int64_t batch, int ctas) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= batch * 33) return;
+  const int64_t bl = i / 33;
+  const int q = (int)(i % 33);
+  double r = 0;
+  for (int c = 0; c < ctas; ++c) r += partial[((size_t)bl * ctas + c) * 33 + q];
+  out[i] = r;
+}
+
 // out[i] = sum_c partial[i * chunks + c] in index order
 template <typename T>
 __global__ void k_sum_chunks(const T* __restrict__ partial, T* __restrict__ out,

@@ -229,7 +229,7 @@ __global__ void __launch_bounds__(STREAM_THREADS, HEAVY ? 1 : STREAM_MIN_CTAS)
       if (pass.flags & QMLB_PASS_INIT) {
 #pragma unroll
         for (int v = 0; v < D; ++v) {
-          re[v] = (base == 0 && v == 0) ? (T)1 : (T)0;
+          re[v] = (base == 0 && v == 0 && !(pass.flags & QMLB_PASS_INIT_ZERO)) ? (T)1 : (T)0;
           im[v] = (T)0;
         }
       } else if (paired) {

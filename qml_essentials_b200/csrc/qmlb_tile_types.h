@@ -8,6 +8,7 @@ namespace qmlb {
 
 #define QMLB_PASS_INIT 1   // tile starts as |0..0> instead of being loaded
 #define QMLB_PASS_STORE 2  // tile is written back to global memory
+#define QMLB_PASS_INIT_ZERO 8  // with INIT: start from the zero vector (a shard without index 0)
 #define QMLB_PASS_HEAVY 4  // streaming pass with a dense / permutation op on 3-4 bits
 #define QMLB_MAX_TILE_BITS 14
 

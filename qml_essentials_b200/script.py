@@ -159,6 +159,9 @@ class Script:
         # hashable extra cache-key component for state the circuit function reads
         # besides its arguments (Model: zero-input shortcut, re-upload mask, ...)
         self.cache_salt = None
+        # optional executor for this Script only (e.g. sharded.ShardedExecutor); None ->
+        # the process-wide CUDA executor
+        self.executor = None
         self._jit_cache: dict = {}
 
     # -- recording ------------------------------------------------------------
@@ -440,7 +443,7 @@ class Script:
             if plan.table is None:  # per-element fallback plans depend on the values
                 self._jit_cache[cache_key] = plan
 
-        ex = get_executor()
+        ex = self.executor or get_executor()
         host_args = self._device_args(plan, args, in_axes, batch)
         chunk = self._chunk_size(cache_key, plan, "probs" if for_shots else type,
                                  len(obs), batch)

@@ -66,3 +66,49 @@ class _Host:
 
     def numpy(self):
         return self.a
+
+
+class InterpShardEngine:
+    """Shard-local work of sharded.ShardedExecutor on NumPy (oracle interpreter) and the
+    exchange over whatever torch.distributed backend the test initialised (gloo)."""
+
+    def make(self, prog, precision):
+        return prog
+
+    def alloc(self, nl, precision):
+        return np.zeros(2 ** nl, dtype=np.complex128)
+
+    def stage_args(self, host_args):
+        return [(a[0], a[1], a[2]) if a is not None else (None, 1, 1) for a in host_args]
+
+    def evolve(self, prog, staged, state, init_mode):
+        if init_mode:
+            state[:] = 0
+            if init_mode == 1:
+                state[0] = 1.0
+        return pi.Interp(prog, staged, 1).run(state[None, :])[0]
+
+    def exchange(self, state, g):
+        """all_to_all_single semantics (chunk s -> rank s) emulated with all_gather:
+        gloo has no alltoall."""
+        import torch
+        import torch.distributed as dist
+
+        size, rank = dist.get_world_size(), dist.get_rank()
+        t = torch.from_numpy(np.ascontiguousarray(state).view(np.float64).copy())
+        every = [torch.empty_like(t) for _ in range(size)]
+        dist.all_gather(every, t)
+        return np.concatenate([e.numpy().view(np.complex128).reshape(size, -1)[rank]
+                               for e in every])
+
+    def zsums(self, state, nl):
+        p = np.abs(state) ** 2
+        idx = np.arange(2 ** nl)
+        out = np.zeros(33)
+        for q in range(nl):
+            out[q] = p[(idx >> q) & 1 == 1].sum()
+        out[32] = p.sum()
+        return out
+
+    def to_host(self, state):
+        return state
