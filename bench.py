@@ -169,6 +169,44 @@ def gate_pass_leg(ex, n_qubits, reps, dev):
         config.set_precision(prev)
 
 
+def sharded_leg(world, rank, local_bits=30):
+    """Qubit-sharded statevector over all ranks: Model(local_bits + log2(N), 8,
+    'Hardware_Efficient') complex64, top log2(N) state bits = rank index, global<->local
+    swaps as NCCL all_to_all_single, <Z_q> all-reduced.  Wall time between barriers."""
+    import torch
+    import torch.distributed as dist
+
+    from qml_essentials_b200 import config
+    from qml_essentials_b200.model import Model
+    from qml_essentials_b200.sharded import ShardedExecutor
+
+    g = int(np.log2(world))
+    if 2 ** g != world:
+        return {"skipped": "needs a power-of-two rank count"}
+    n = local_bits + g
+    prev = config.get_precision()
+    config.set_precision("complex64")
+    try:
+        model = Model(n_qubits=n, n_layers=8, circuit_type="Hardware_Efficient")
+        params = np.random.default_rng(1000).uniform(0.0, 2 * np.pi, (1, *model._params_shape))
+        inputs = np.array([[0.5]])
+        se = ShardedExecutor()
+        model.script.executor = se
+        model(params=params, inputs=inputs)  # plan, epoch programs, NCCL warm-up
+        torch.cuda.synchronize()
+        dist.barrier()
+        t0 = time.perf_counter()
+        ev = np.asarray(model(params=params, inputs=inputs)).reshape(-1)
+        torch.cuda.synchronize()
+        dist.barrier()
+        dt = time.perf_counter() - t0
+        return {"workload": f"Model({n},8,'Hardware_Efficient') complex64 expval, qubit-sharded "
+                            f"over {world} GPUs ({local_bits} local bits)", "n_qubits": n,
+                "seconds": dt, **se.stats, "abs_expval_le_1": bool(np.all(np.abs(ev) <= 1 + 1e-4))}
+    finally:
+        config.set_precision(prev)
+
+
 def hbm_peak_gbs():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -220,6 +258,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--precision", default="complex128", choices=["complex128", "complex64"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly")
     ap.add_argument("--gate-pass-qubits", type=int, default=-1,
                     help="n for the HBM gate-pass leg (default: 32 on 1 GPU, 30 per rank "
                          "otherwise; 0 disables)")
@@ -284,6 +323,33 @@ def main():
         step_device()
     barrier()
 
+    # The step is launch-bound at this size (k_pre x2 + k_reg + the statistics kernels + one
+    # small NCCL all-reduce): capture it once in a CUDA graph and replay it.
+    eager_step, graph, launches_per_step = step_device, None, None
+    if not args.no_graph:
+        try:
+            l0 = ex.launch_count()
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                step_device()
+            torch.cuda.current_stream().wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            l0 = ex.launch_count()
+            with torch.cuda.graph(graph):
+                graph_out = step_device()
+            launches_per_step = ex.launch_count() - l0
+            graph.replay()
+            torch.cuda.synchronize()
+
+            def step_device():  # noqa: F811
+                graph.replay()
+                return graph_out
+        except Exception as exc:  # noqa: BLE001
+            print(f"[bench] CUDA graph capture failed ({exc}); running eagerly", file=sys.stderr)
+            graph, step_device = None, eager_step
+    barrier()
+
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -298,6 +364,8 @@ def main():
     barrier()
     dev_ms = sum(s.elapsed_time(e) for s, e in ev)
     launches = ex.launch_count() - launches0
+    if graph is not None:
+        launches = launches_per_step * args.steps  # replayed: counted once at capture
 
     # kernel-only duration of the dominant kernel (one launch per step)
     kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
@@ -330,6 +398,13 @@ def main():
             gp = gate_pass_leg(ex, gp_n, 2, dev)
         except Exception as exc:  # noqa: BLE001  (e.g. not enough free HBM on a shared box)
             gp = {"error": f"{type(exc).__name__}: {exc}"[:300], "n_qubits": gp_n}
+    sh = None
+    if world > 1 and gp_n > 0:
+        torch.cuda.empty_cache()
+        try:
+            sh = sharded_leg(world, rank, min(gp_n, 30))
+        except Exception as exc:  # noqa: BLE001
+            sh = {"error": f"{type(exc).__name__}: {exc}"[:300]}
     clocks = sampler.stop() if rank == 0 else None
     gp_ms = gp.get("ms_per_circuit", 0.0) if gp else 0.0
 
@@ -357,6 +432,7 @@ def main():
                             "(default_rng(1000+rank)) x 264-point input grid per GPU",
                 "evals_per_step_per_gpu": B, "cache": "L2 flushed (512 MiB write) between "
                 "timed iterations", "parallelism": f"batch-sharded x{world}",
+                "launch": "CUDA graph replay" if graph is not None else "eager",
             },
             "e2e": {"value": e2e_value, "unit": "evals/s",
                     "h2d_bytes_per_step": int(params.nbytes + inputs.nbytes),
@@ -384,6 +460,8 @@ def main():
                        "ms_per_circuit": gp_ms, "ms_per_pass": gp_ms / gp["passes"]})
         if gp is not None:
             line["gate_pass"] = gp
+        if sh is not None:
+            line["qubit_sharded"] = sh
         if not args.no_cpu_baseline and world == 1:
             cores = os.cpu_count() or 1
             cpu_v, cpu_ev, sample = oracle_cpu_evals_per_s(params, inputs, 256, cores)

@@ -484,7 +484,7 @@ int plan(qmlb_program* p) {
   const int init_max = env_int("QMLB_SMEM_STATE_BITS", p->dtype == QMLB_C128 ? 13 : 14);
   p->direct_out = (p->out_type == QMLB_OUT_STATE) ||
                   (p->out_type == QMLB_OUT_DENSITY && p->density);
-  const int stream_r = p->dtype == QMLB_C128 ? 4 : 5;
+  const int stream_r = 4;
   if ((N <= init_max && force != 2) || force == 1 || N < stream_r) {
     if (N > QMLB_MAX_TILE_BITS) return fail(QMLB_ERR_UNSUPPORTED, "state too large for smem");
     p->strategy = 1;
@@ -514,7 +514,7 @@ int plan(qmlb_program* p) {
 
   // ---- strategy 2: streamed register-group passes over HBM ------------------------
   p->strategy = 2;
-  p->stream_r = p->dtype == QMLB_C128 ? 4 : 5;
+  p->stream_r = 4;  // register group: 16 amplitudes per thread (see qmlb_stream.cuh)
   p->warp_team = false;
   p->teams = 1;
   p->smem = 0;
@@ -681,7 +681,10 @@ int evolve_stream(const qmlb_program* p, const RunArgs& R, void* state, int init
   if (R.batch == 1) {
     grid = dim3((unsigned)std::max<int64_t>(1, std::min(ctas_x, want)), 1, 1);
   } else {
-    const int64_t gx = std::max<int64_t>(1, std::min<int64_t>(ctas_x, 64));
+    // every CTA evaluates the pass' matrices for its element once: give it enough items
+    // to amortise that (>= 8 trips) as long as the batch alone fills the GPU
+    int64_t gx = std::max<int64_t>(1, std::min<int64_t>(ctas_x, 64));
+    while (gx > 1 && R.batch * (gx / 2) >= want && ctas_x / gx < 8) gx /= 2;
     const int64_t gy =
         std::max<int64_t>(1, std::min<int64_t>(R.batch, std::max<int64_t>(1, want / gx)));
     grid = dim3((unsigned)gx, (unsigned)std::min<int64_t>(gy, 65535), 1);

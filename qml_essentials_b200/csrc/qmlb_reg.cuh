@@ -13,55 +13,122 @@
 
 #include "qmlb_device.cuh"
 
+#ifndef QMLB_REG_MIN_CTAS
+#define QMLB_REG_MIN_CTAS 3
+#endif
+
 namespace qmlb {
+
+// Register-resident state of 2^N amplitudes.  double: separate re / im arrays.  float:
+// amplitudes 2k and 2k+1 share one float2 (an aligned 64-bit register pair), which is
+// what lets the hot 2x2 updates issue packed fma.rn.f32x2 (FFMA2) on Blackwell.
+template <typename T, int N>
+struct RegState {
+  T r[1 << N], i[1 << N];
+  __device__ __forceinline__ T& re(int k) { return r[k]; }
+  __device__ __forceinline__ T& im(int k) { return i[k]; }
+};
+template <int N>
+struct RegState<float, N> {
+  static constexpr int H = (1 << N) >= 2 ? (1 << N) / 2 : 1;
+  float2 r2[H], i2[H];
+  __device__ __forceinline__ float& re(int k) { return (k & 1) ? r2[k >> 1].y : r2[k >> 1].x; }
+  __device__ __forceinline__ float& im(int k) { return (k & 1) ? i2[k >> 1].y : i2[k >> 1].x; }
+};
 
 template <int N, int BIT>
 __device__ __forceinline__ constexpr int pair_i0(int g) {
   return ((g >> BIT) << (BIT + 1)) | (g & ((1 << BIT) - 1));
 }
 
+// Packed FP32 2x2 update (Blackwell fma.rn.f32x2 / FFMA2: two FMAs per issue slot).  For a
+// target bit >= 1 the amplitudes 2k and 2k+1 play the same role, so one float2 of real
+// parts and one of imaginary parts go through the update together against lane-broadcast
+// matrix entries: 16 packed instructions per four amplitudes instead of 32 scalar ones.
+template <int N>
+__device__ __forceinline__ void f2_update(RegState<float, N>& S, int k0, int k1,
+                                          const cx<float> (&m)[4]) {
+  const float2 ar = S.r2[k0], ai = S.i2[k0], br = S.r2[k1], bi = S.i2[k1];
+  auto bc = [](float v) { return make_float2(v, v); };
+  float2 xr = __fmul2_rn(bc(m[0].x), ar);
+  xr = __ffma2_rn(bc(-m[0].y), ai, xr);
+  xr = __ffma2_rn(bc(m[1].x), br, xr);
+  xr = __ffma2_rn(bc(-m[1].y), bi, xr);
+  float2 xi = __fmul2_rn(bc(m[0].x), ai);
+  xi = __ffma2_rn(bc(m[0].y), ar, xi);
+  xi = __ffma2_rn(bc(m[1].x), bi, xi);
+  xi = __ffma2_rn(bc(m[1].y), br, xi);
+  float2 yr = __fmul2_rn(bc(m[2].x), ar);
+  yr = __ffma2_rn(bc(-m[2].y), ai, yr);
+  yr = __ffma2_rn(bc(m[3].x), br, yr);
+  yr = __ffma2_rn(bc(-m[3].y), bi, yr);
+  float2 yi = __fmul2_rn(bc(m[2].x), ai);
+  yi = __ffma2_rn(bc(m[2].y), ar, yi);
+  yi = __ffma2_rn(bc(m[3].x), bi, yi);
+  yi = __ffma2_rn(bc(m[3].y), br, yi);
+  S.r2[k0] = xr;
+  S.i2[k0] = xi;
+  S.r2[k1] = yr;
+  S.i2[k1] = yi;
+}
+
 template <typename T, int N, int BIT>
-__device__ __forceinline__ void reg_mat1(T (&re)[1 << N], T (&im)[1 << N], const cx<T> (&m)[4]) {
+__device__ __forceinline__ void reg_mat1(RegState<T, N>& S, const cx<T> (&m)[4]) {
+  if constexpr (std::is_same<T, float>::value && BIT >= 1) {
 #pragma unroll
-  for (int g = 0; g < (1 << (N - 1)); ++g) {
-    const int i0 = pair_i0<N, BIT>(g), i1 = i0 | (1 << BIT);
-    const T ar = re[i0], ai = im[i0], br = re[i1], bi = im[i1];
-    re[i0] = m[0].x * ar - m[0].y * ai + m[1].x * br - m[1].y * bi;
-    im[i0] = m[0].x * ai + m[0].y * ar + m[1].x * bi + m[1].y * br;
-    re[i1] = m[2].x * ar - m[2].y * ai + m[3].x * br - m[3].y * bi;
-    im[i1] = m[2].x * ai + m[2].y * ar + m[3].x * bi + m[3].y * br;
+    for (int h = 0; h < (1 << (N - 2)); ++h) {  // pairs of float2 that differ in bit BIT-1
+      const int k0 = ((h >> (BIT - 1)) << BIT) | (h & ((1 << (BIT - 1)) - 1));
+      f2_update<N>(S, k0, k0 | (1 << (BIT - 1)), m);
+    }
+  } else {
+#pragma unroll
+    for (int g = 0; g < (1 << (N - 1)); ++g) {
+      const int i0 = pair_i0<N, BIT>(g), i1 = i0 | (1 << BIT);
+      const T ar = S.re(i0), ai = S.im(i0), br = S.re(i1), bi = S.im(i1);
+      S.re(i0) = m[0].x * ar - m[0].y * ai + m[1].x * br - m[1].y * bi;
+      S.im(i0) = m[0].x * ai + m[0].y * ar + m[1].x * bi + m[1].y * br;
+      S.re(i1) = m[2].x * ar - m[2].y * ai + m[3].x * br - m[3].y * bi;
+      S.im(i1) = m[2].x * ai + m[2].y * ar + m[3].x * bi + m[3].y * br;
+    }
   }
 }
 
 // 2x2 on TB where CB is set
 template <typename T, int N, int CB, int TB>
-__device__ __forceinline__ void reg_ctrl1(T (&re)[1 << N], T (&im)[1 << N],
-                                          const cx<T> (&m)[4]) {
+__device__ __forceinline__ void reg_ctrl1(RegState<T, N>& S, const cx<T> (&m)[4]) {
+  if constexpr (std::is_same<T, float>::value && CB >= 1 && TB >= 1) {
 #pragma unroll
-  for (int g = 0; g < (1 << (N - 1)); ++g) {
-    const int i0 = pair_i0<N, TB>(g), i1 = i0 | (1 << TB);
-    if (i0 & (1 << CB)) {
-      const T ar = re[i0], ai = im[i0], br = re[i1], bi = im[i1];
-      re[i0] = m[0].x * ar - m[0].y * ai + m[1].x * br - m[1].y * bi;
-      im[i0] = m[0].x * ai + m[0].y * ar + m[1].x * bi + m[1].y * br;
-      re[i1] = m[2].x * ar - m[2].y * ai + m[3].x * br - m[3].y * bi;
-      im[i1] = m[2].x * ai + m[2].y * ar + m[3].x * bi + m[3].y * br;
+    for (int h = 0; h < (1 << (N - 2)); ++h) {
+      const int k0 = ((h >> (TB - 1)) << TB) | (h & ((1 << (TB - 1)) - 1));
+      if (k0 & (1 << (CB - 1))) f2_update<N>(S, k0, k0 | (1 << (TB - 1)), m);
+    }
+  } else {
+#pragma unroll
+    for (int g = 0; g < (1 << (N - 1)); ++g) {
+      const int i0 = pair_i0<N, TB>(g), i1 = i0 | (1 << TB);
+      if (i0 & (1 << CB)) {
+        const T ar = S.re(i0), ai = S.im(i0), br = S.re(i1), bi = S.im(i1);
+        S.re(i0) = m[0].x * ar - m[0].y * ai + m[1].x * br - m[1].y * bi;
+        S.im(i0) = m[0].x * ai + m[0].y * ar + m[1].x * bi + m[1].y * br;
+        S.re(i1) = m[2].x * ar - m[2].y * ai + m[3].x * br - m[3].y * bi;
+        S.im(i1) = m[2].x * ai + m[2].y * ar + m[3].x * bi + m[3].y * br;
+      }
     }
   }
 }
 
 // CX: swap the target pair where the control bit is set (pure register moves)
 template <typename T, int N, int CB, int TB>
-__device__ __forceinline__ void reg_cx(T (&re)[1 << N], T (&im)[1 << N]) {
+__device__ __forceinline__ void reg_cx(RegState<T, N>& S) {
 #pragma unroll
   for (int g = 0; g < (1 << (N - 1)); ++g) {
     const int i0 = pair_i0<N, TB>(g), i1 = i0 | (1 << TB);
     if (i0 & (1 << CB)) {
-      const T r = re[i0], q = im[i0];
-      re[i0] = re[i1];
-      im[i0] = im[i1];
-      re[i1] = r;
-      im[i1] = q;
+      const T r = S.re(i0), q = S.im(i0);
+      S.re(i0) = S.re(i1);
+      S.im(i0) = S.im(i1);
+      S.re(i1) = r;
+      S.im(i1) = q;
     }
   }
 }
@@ -134,8 +201,16 @@ struct RowsShared {
 };
 
 // mode: 0 -> write state, 1 -> probs, 2 -> Z-string expectation values
+// Resident CTAs per SM the kernel is compiled for: the state takes 2 * 2^N * sizeof(T) / 4
+// registers; up to 64 of them (c128 n <= 4, c64 n <= 5) leave room for 3 CTAs (168
+// registers / thread), which is what hides the table-lookup latency.
 template <typename T, int N>
-__global__ void __launch_bounds__(128) k_reg(DevProg P, RunArgs R, int mode, int n_args,
+constexpr int reg_min_ctas() {
+  return (2 * (1 << N) * (int)sizeof(T) / 4 <= 64) ? QMLB_REG_MIN_CTAS : 1;
+}
+
+template <typename T, int N>
+__global__ void __launch_bounds__(128, reg_min_ctas<T, N>()) k_reg(DevProg P, RunArgs R, int mode, int n_args,
                                              void* __restrict__ out) {
   constexpr int D = 1 << N;
   const int64_t bl = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -149,13 +224,13 @@ __global__ void __launch_bounds__(128) k_reg(DevProg P, RunArgs R, int mode, int
     if (a < n_args) s_rows[a][threadIdx.x] = (int32_t)((b / R.a[a].div) % R.a[a].mod);
   const RowsShared rows{&s_rows[0][threadIdx.x]};
 
-  T re[D], im[D];
+  RegState<T, N> S;
 #pragma unroll
   for (int i = 0; i < D; ++i) {
-    re[i] = (T)0;
-    im[i] = (T)0;
+    S.re(i) = (T)0;
+    S.im(i) = (T)0;
   }
-  re[0] = (T)1;
+  S.re(0) = (T)1;
 
   for (int o = 0; o < P.n_ops; ++o) {
     const qmlb_op op = P.ops[o];
@@ -166,11 +241,11 @@ __global__ void __launch_bounds__(128) k_reg(DevProg P, RunArgs R, int mode, int
 #pragma unroll
           for (int g = 0; g < (1 << (N - 1)); ++g) {
             const int i0 = pair_i0<N, BIT>(g), i1 = i0 | (1 << BIT);
-            const T r = re[i0], q = im[i0];
-            re[i0] = re[i1];
-            im[i0] = im[i1];
-            re[i1] = r;
-            im[i1] = q;
+            const T r = S.re(i0), q = S.im(i0);
+            S.re(i0) = S.re(i1);
+            S.im(i0) = S.im(i1);
+            S.re(i1) = r;
+            S.im(i1) = q;
           }
         });
       } else {
@@ -178,7 +253,7 @@ __global__ void __launch_bounds__(128) k_reg(DevProg P, RunArgs R, int mode, int
         const bool c0 = (int)P.consts[op.aux + 1] == 1;
         const int cb = c0 ? op.bits[0] : op.bits[1], tb = c0 ? op.bits[1] : op.bits[0];
         dispatch2<T, N>(cb, tb, [&](auto CB, auto TB) {
-          reg_cx<T, N, decltype(CB)::value, decltype(TB)::value>(re, im);
+          reg_cx<T, N, decltype(CB)::value, decltype(TB)::value>(S);
         });
       }
       continue;
@@ -191,17 +266,17 @@ __global__ void __launch_bounds__(128) k_reg(DevProg P, RunArgs R, int mode, int
         for (int i = 0; i < D; ++i) {
           T sn, cs;
           sincos_t((T)(-P.consts[s.a0 + i] * th), &sn, &cs);
-          const T r = re[i], q = im[i];
-          re[i] = cs * r - sn * q;
-          im[i] = cs * q + sn * r;
+          const T r = S.re(i), q = S.im(i);
+          S.re(i) = cs * r - sn * q;
+          S.im(i) = cs * q + sn * r;
         }
       } else {
 #pragma unroll
         for (int i = 0; i < D; ++i) {
           const cx<T> c = ld_const<T>(P.consts, s.a0 + i);
-          const T r = re[i], q = im[i];
-          re[i] = c.x * r - c.y * q;
-          im[i] = c.x * q + c.y * r;
+          const T r = S.re(i), q = S.im(i);
+          S.re(i) = c.x * r - c.y * q;
+          S.im(i) = c.x * q + c.y * r;
         }
       }
       continue;
@@ -228,11 +303,11 @@ __global__ void __launch_bounds__(128) k_reg(DevProg P, RunArgs R, int mode, int
     }
     if (op.kind == QMLB_OP_CTRL1) {
       dispatch2<T, N>(op.bits[0], op.bits[1], [&](auto CB, auto TB) {
-        reg_ctrl1<T, N, decltype(CB)::value, decltype(TB)::value>(re, im, m);
+        reg_ctrl1<T, N, decltype(CB)::value, decltype(TB)::value>(S, m);
       });
     } else {
       dispatch1<T, N>(op.bits[0], [&](auto B) {
-        reg_mat1<T, N, decltype(B)::value>(re, im, m);
+        reg_mat1<T, N, decltype(B)::value>(S, m);
       });
     }
   }
@@ -240,15 +315,15 @@ __global__ void __launch_bounds__(128) k_reg(DevProg P, RunArgs R, int mode, int
   if (mode == 0) {
     cx<T>* o = reinterpret_cast<cx<T>*>(out) + bl * D;
 #pragma unroll
-    for (int i = 0; i < D; ++i) o[i] = mk<T>(re[i], im[i]);
+    for (int i = 0; i < D; ++i) o[i] = mk<T>(S.re(i), S.im(i));
   } else if (mode == 1) {
     T* o = reinterpret_cast<T*>(out) + bl * D;
 #pragma unroll
-    for (int i = 0; i < D; ++i) o[i] = re[i] * re[i] + im[i] * im[i];
+    for (int i = 0; i < D; ++i) o[i] = S.re(i) * S.re(i) + S.im(i) * S.im(i);
   } else {
     T p[D];
 #pragma unroll
-    for (int i = 0; i < D; ++i) p[i] = re[i] * re[i] + im[i] * im[i];
+    for (int i = 0; i < D; ++i) p[i] = S.re(i) * S.re(i) + S.im(i) * S.im(i);
     T* o = reinterpret_cast<T*>(out) + bl * P.n_obs;
     for (int j = 0; j < P.n_obs; ++j) {
       const int mask = (int)P.obs[j].zmask;

@@ -26,43 +26,96 @@
 
 namespace qmlb {
 
+// cp.async (LDGSTS): global -> shared without staging registers
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(
+                   (unsigned)__cvta_generic_to_shared(smem)),
+               "l"(gmem));
+}
+template <typename T>
+__device__ __forceinline__ void cp_async_elem(cx<T>* smem, const cx<T>* gmem) {
+  if constexpr (sizeof(T) == 8) {
+    cp_async16(smem, gmem);
+  } else {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(
+                     (unsigned)__cvta_generic_to_shared(smem)),
+                 "l"(gmem));
+  }
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n"); }
+__device__ __forceinline__ void cp_async_wait_all_but_one() {
+  asm volatile("cp.async.wait_group 1;\n" ::: "memory");
+}
+
 // dense 4x4 (row-major, local value v = (bit JA << 1) | bit JB) on register bits JA > JB
 template <typename T, int N, int JA, int JB>
-__device__ __forceinline__ void reg_mat2(T (&re)[1 << N], T (&im)[1 << N],
-                                         const cx<T>* __restrict__ m) {
+__device__ __forceinline__ void reg_mat2(RegState<T, N>& S, const cx<T>* __restrict__ m) {
   static_assert(JA > JB, "canonical order");
+  if constexpr (std::is_same<T, float>::value && JB >= 1) {
+    // packed FP32: both bits >= 1, so amplitudes 2k / 2k+1 share their role (see reg_mat1)
+    constexpr int A = JA - 1, B = JB - 1;
 #pragma unroll
-  for (int g = 0; g < (1 << (N - 2)); ++g) {
-    // insert zeros at JB then JA
-    const int t = ((g >> JB) << (JB + 1)) | (g & ((1 << JB) - 1));
-    const int i00 = ((t >> JA) << (JA + 1)) | (t & ((1 << JA) - 1));
-    const int idx[4] = {i00, i00 | (1 << JB), i00 | (1 << JA), i00 | (1 << JA) | (1 << JB)};
-    T ar[4], ai[4];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      ar[u] = re[idx[u]];
-      ai[u] = im[idx[u]];
-    }
-#pragma unroll
-    for (int v = 0; v < 4; ++v) {
-      T xr = (T)0, xi = (T)0;
+    for (int g = 0; g < (1 << (N - 3)); ++g) {
+      const int t = ((g >> B) << (B + 1)) | (g & ((1 << B) - 1));
+      const int k00 = ((t >> A) << (A + 1)) | (t & ((1 << A) - 1));
+      const int idx[4] = {k00, k00 | (1 << B), k00 | (1 << A), k00 | (1 << A) | (1 << B)};
+      float2 ar[4], ai[4];
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
-        const cx<T> c = m[v * 4 + u];  // shared memory, broadcast
-        xr = fma(c.x, ar[u], xr);
-        xr = fma(-c.y, ai[u], xr);
-        xi = fma(c.x, ai[u], xi);
-        xi = fma(c.y, ar[u], xi);
+        ar[u] = S.r2[idx[u]];
+        ai[u] = S.i2[idx[u]];
       }
-      re[idx[v]] = xr;
-      im[idx[v]] = xi;
+#pragma unroll
+      for (int v = 0; v < 4; ++v) {
+        float2 xr = make_float2(0.f, 0.f), xi = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const cx<float> c = m[v * 4 + u];  // shared memory, broadcast
+          const float2 cr = make_float2(c.x, c.x), ci = make_float2(c.y, c.y);
+          const float2 nci = make_float2(-c.y, -c.y);
+          xr = __ffma2_rn(cr, ar[u], xr);
+          xr = __ffma2_rn(nci, ai[u], xr);
+          xi = __ffma2_rn(cr, ai[u], xi);
+          xi = __ffma2_rn(ci, ar[u], xi);
+        }
+        S.r2[idx[v]] = xr;
+        S.i2[idx[v]] = xi;
+      }
+    }
+  } else {
+#pragma unroll
+    for (int g = 0; g < (1 << (N - 2)); ++g) {
+      // insert zeros at JB then JA
+      const int t = ((g >> JB) << (JB + 1)) | (g & ((1 << JB) - 1));
+      const int i00 = ((t >> JA) << (JA + 1)) | (t & ((1 << JA) - 1));
+      const int idx[4] = {i00, i00 | (1 << JB), i00 | (1 << JA), i00 | (1 << JA) | (1 << JB)};
+      T ar[4], ai[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        ar[u] = S.re(idx[u]);
+        ai[u] = S.im(idx[u]);
+      }
+#pragma unroll
+      for (int v = 0; v < 4; ++v) {
+        T xr = (T)0, xi = (T)0;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const cx<T> c = m[v * 4 + u];  // shared memory, broadcast
+          xr = fma(c.x, ar[u], xr);
+          xr = fma(-c.y, ai[u], xr);
+          xi = fma(c.x, ai[u], xi);
+          xi = fma(c.y, ar[u], xi);
+        }
+        S.re(idx[v]) = xr;
+        S.im(idx[v]) = xi;
+      }
     }
   }
 }
 
 // dense 2^K x 2^K on register bits K-1..0 (local value = low K bits of the register index)
 template <typename T, int N, int K>
-__device__ __forceinline__ void reg_matk(T (&re)[1 << N], T (&im)[1 << N],
+__device__ __forceinline__ void reg_matk(RegState<T, N>& S,
                                          const cx<T>* __restrict__ m) {
   constexpr int D = 1 << K;
 #pragma unroll
@@ -70,8 +123,8 @@ __device__ __forceinline__ void reg_matk(T (&re)[1 << N], T (&im)[1 << N],
     T ar[D], ai[D];
 #pragma unroll
     for (int u = 0; u < D; ++u) {
-      ar[u] = re[(blk << K) | u];
-      ai[u] = im[(blk << K) | u];
+      ar[u] = S.re((blk << K) | u);
+      ai[u] = S.im((blk << K) | u);
     }
 #pragma unroll 1
     for (int v = 0; v < D; ++v) {
@@ -88,8 +141,8 @@ __device__ __forceinline__ void reg_matk(T (&re)[1 << N], T (&im)[1 << N],
 #pragma unroll
       for (int w = 0; w < D; ++w)
         if (w == v) {
-          re[(blk << K) | w] = xr;  // safe: row v only reads the ar/ai copies
-          im[(blk << K) | w] = xi;
+          S.re((blk << K) | w) = xr;  // safe: row v only reads the ar/ai copies
+          S.im((blk << K) | w) = xi;
         }
     }
   }
@@ -97,7 +150,7 @@ __device__ __forceinline__ void reg_matk(T (&re)[1 << N], T (&im)[1 << N],
 
 // permutation of the low K register bits: new[v] = old[p[v]], p packed K bits per entry
 template <typename T, int N, int K>
-__device__ __forceinline__ void reg_permk(T (&re)[1 << N], T (&im)[1 << N],
+__device__ __forceinline__ void reg_permk(RegState<T, N>& S,
                                           unsigned long long packed) {
   constexpr int D = 1 << K;
 #pragma unroll
@@ -105,8 +158,8 @@ __device__ __forceinline__ void reg_permk(T (&re)[1 << N], T (&im)[1 << N],
     T ar[D], ai[D];
 #pragma unroll
     for (int u = 0; u < D; ++u) {
-      ar[u] = re[(blk << K) | u];
-      ai[u] = im[(blk << K) | u];
+      ar[u] = S.re((blk << K) | u);
+      ai[u] = S.im((blk << K) | u);
     }
 #pragma unroll
     for (int v = 0; v < D; ++v) {
@@ -118,21 +171,21 @@ __device__ __forceinline__ void reg_permk(T (&re)[1 << N], T (&im)[1 << N],
           xr = ar[u];
           xi = ai[u];
         }
-      re[(blk << K) | v] = xr;
-      im[(blk << K) | v] = xi;
+      S.re((blk << K) | v) = xr;
+      S.im((blk << K) | v) = xi;
     }
   }
 }
 
 // 2-bit permutation on register bits JA > JB (v = (bit JA << 1) | bit JB), p packed 2 bits/entry
 template <typename T, int N, int JA, int JB>
-__device__ __forceinline__ void reg_perm2(T (&re)[1 << N], T (&im)[1 << N], unsigned packed) {
+__device__ __forceinline__ void reg_perm2(RegState<T, N>& S, unsigned packed) {
   if (packed == 0xB4u) {  // (0,1,3,2): CX, control JA, target JB
-    reg_cx<T, N, JA, JB>(re, im);
+    reg_cx<T, N, JA, JB>(S);
     return;
   }
   if (packed == 0x6Cu) {  // (0,3,2,1): CX, control JB, target JA
-    reg_cx<T, N, JB, JA>(re, im);
+    reg_cx<T, N, JB, JA>(S);
     return;
   }
 #pragma unroll
@@ -143,8 +196,8 @@ __device__ __forceinline__ void reg_perm2(T (&re)[1 << N], T (&im)[1 << N], unsi
     T ar[4], ai[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
-      ar[u] = re[idx[u]];
-      ai[u] = im[idx[u]];
+      ar[u] = S.re(idx[u]);
+      ai[u] = S.im(idx[u]);
     }
 #pragma unroll
     for (int v = 0; v < 4; ++v) {
@@ -156,8 +209,8 @@ __device__ __forceinline__ void reg_perm2(T (&re)[1 << N], T (&im)[1 << N], unsi
           xr = ar[u];
           xi = ai[u];
         }
-      re[idx[v]] = xr;
-      im[idx[v]] = xi;
+      S.re(idx[v]) = xr;
+      S.im(idx[v]) = xi;
     }
   }
 }
@@ -167,7 +220,7 @@ __device__ __forceinline__ void reg_perm2(T (&re)[1 << N], T (&im)[1 << N], unsi
 // IDX = uint32_t when every amplitude index of the launch fits 32 bits (one element of at
 // most 32 state bits), else uint64_t.
 template <typename T, int R, bool HEAVY, typename IDX>
-__global__ void __launch_bounds__(STREAM_THREADS, HEAVY ? 1 : STREAM_MIN_CTAS)
+__global__ void __launch_bounds__(STREAM_THREADS, HEAVY ? 1 : (sizeof(T) == 4 ? 4 : STREAM_MIN_CTAS))
     k_stream(DevProg P, RunArgs A, const __grid_constant__ StreamPass pass,
              cx<T>* __restrict__ gstate) {
   constexpr int D = 1 << R;
@@ -176,7 +229,10 @@ __global__ void __launch_bounds__(STREAM_THREADS, HEAVY ? 1 : STREAM_MIN_CTAS)
   // thread owns whole 32-byte sectors)
   constexpr bool CAN_PAIR = sizeof(T) == 4;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  cx<T>* mb = reinterpret_cast<cx<T>*>(smem_raw);
+  // [2 stages x 2^R x STREAM_THREADS amplitudes | matrices of the pass]
+  cx<T>* stg = reinterpret_cast<cx<T>*>(smem_raw);
+  cx<T>* mb = stg + 2 * D * STREAM_THREADS;
+  const bool init_pass = pass.flags & QMLB_PASS_INIT;
 
   const int N = pass.n_bits;
   const IDX items = (IDX)1 << (N - R);
@@ -217,38 +273,73 @@ __global__ void __launch_bounds__(STREAM_THREADS, HEAVY ? 1 : STREAM_MIN_CTAS)
     __syncthreads();
 
     cx<T>* gs = gstate + (size_t)bl * ((size_t)1 << N);
-    for (IDX w = (IDX)blockIdx.x * blockDim.x + threadIdx.x; w < items;
-         w += (IDX)gridDim.x * blockDim.x) {
+    const IDX stride = (IDX)gridDim.x * blockDim.x;
+    auto base_of = [&](IDX w) -> IDX {
       IDX base = w;
 #pragma unroll
       for (int j = 0; j < R; ++j) {
         const int pbit = pass.sorted[j];
         base = ((base >> pbit) << (pbit + 1)) | (base & (((IDX)1 << pbit) - (IDX)1));
       }
-      T re[D], im[D];
-      if (pass.flags & QMLB_PASS_INIT) {
+      return base;
+    };
+    // Software pipeline: the 2^R amplitudes of the NEXT work item travel global -> shared
+    // with cp.async (LDGSTS, no registers held, thread-private slots so no barrier) while
+    // the current item is in the arithmetic; with ~12 resident warps per SM that is what
+    // keeps HBM requests in flight during the compute phase.
+    auto prefetch = [&](IDX w, int stage) {
+      if (w < items && !init_pass) {
+        const IDX base = base_of(w);
+        cx<T>* slot = stg + (size_t)stage * D * STREAM_THREADS + threadIdx.x;
+        if (paired) {
+          if constexpr (CAN_PAIR) {
+            float4* slot4 = reinterpret_cast<float4*>(stg) +
+                            (size_t)stage * (D / 2) * STREAM_THREADS + threadIdx.x;
+#pragma unroll
+            for (int v = 0; v < D; v += 2)
+              cp_async16(slot4 + (v >> 1) * STREAM_THREADS, gs + (base | offv(v)));
+          }
+        } else {
+#pragma unroll
+          for (int v = 0; v < D; ++v)
+            cp_async_elem<T>(slot + v * STREAM_THREADS, gs + (base | offv(v)));
+        }
+      }
+      cp_async_commit();
+    };
+
+    const IDX w_first = (IDX)blockIdx.x * blockDim.x + threadIdx.x;
+    prefetch(w_first, 0);
+    int stage = 0;
+    for (IDX w = w_first; w < items; w += stride, stage ^= 1) {
+      prefetch(w + stride < w ? items : w + stride, stage ^ 1);  // (overflow-safe)
+      cp_async_wait_all_but_one();
+      const IDX base = base_of(w);
+      RegState<T, R> S;
+      if (init_pass) {
 #pragma unroll
         for (int v = 0; v < D; ++v) {
-          re[v] = (base == 0 && v == 0 && !(pass.flags & QMLB_PASS_INIT_ZERO)) ? (T)1 : (T)0;
-          im[v] = (T)0;
+          S.re(v) = (base == 0 && v == 0 && !(pass.flags & QMLB_PASS_INIT_ZERO)) ? (T)1 : (T)0;
+          S.im(v) = (T)0;
         }
       } else if (paired) {
         if constexpr (CAN_PAIR) {
+          const float4* slot4 = reinterpret_cast<const float4*>(stg) +
+                                (size_t)stage * (D / 2) * STREAM_THREADS + threadIdx.x;
 #pragma unroll
           for (int v = 0; v < D; v += 2) {
-            const float4 a = *reinterpret_cast<const float4*>(gs + (base | offv(v)));
-            re[v] = a.x;
-            im[v] = a.y;
-            re[v + 1] = a.z;
-            im[v + 1] = a.w;
+            const float4 a = slot4[(v >> 1) * STREAM_THREADS];
+            S.r2[v >> 1] = make_float2(a.x, a.z);
+            S.i2[v >> 1] = make_float2(a.y, a.w);
           }
         }
       } else {
+        const cx<T>* slot = stg + (size_t)stage * D * STREAM_THREADS + threadIdx.x;
 #pragma unroll
         for (int v = 0; v < D; ++v) {
-          const cx<T> a = gs[base | offv(v)];
-          re[v] = a.x;
-          im[v] = a.y;
+          const cx<T> a = slot[v * STREAM_THREADS];
+          S.re(v) = a.x;
+          S.im(v) = a.y;
         }
       }
 
@@ -262,18 +353,18 @@ __global__ void __launch_bounds__(STREAM_THREADS, HEAVY ? 1 : STREAM_MIN_CTAS)
 #pragma unroll
               for (int i = 0; i < 4; ++i) mm[i] = m[i];
               dispatch1<T, R>(op.b0, [&](auto B) {
-                reg_mat1<T, R, decltype(B)::value>(re, im, mm);
+                reg_mat1<T, R, decltype(B)::value>(S, mm);
               });
             } else if (op.k == 2) {
               const int ja = max(op.b0, op.b1), jb = min(op.b0, op.b1);
               dispatch2<T, R>(ja, jb, [&](auto JA, auto JB) {
                 if constexpr (decltype(JA)::value > decltype(JB)::value)
-                  reg_mat2<T, R, decltype(JA)::value, decltype(JB)::value>(re, im, m);
+                  reg_mat2<T, R, decltype(JA)::value, decltype(JB)::value>(S, m);
               });
             } else if (HEAVY && op.k == 3) {
-              reg_matk<T, R, 3>(re, im, m);
+              reg_matk<T, R, 3>(S, m);
             } else if (HEAVY) {
-              reg_matk<T, R, 4>(re, im, m);
+              reg_matk<T, R, 4>(S, m);
             }
             break;
           case QMLB_OP_CTRL1: {
@@ -281,7 +372,7 @@ __global__ void __launch_bounds__(STREAM_THREADS, HEAVY ? 1 : STREAM_MIN_CTAS)
 #pragma unroll
             for (int i = 0; i < 4; ++i) mm[i] = m[i];
             dispatch2<T, R>(op.b0, op.b1, [&](auto CB, auto TB) {
-              reg_ctrl1<T, R, decltype(CB)::value, decltype(TB)::value>(re, im, mm);
+              reg_ctrl1<T, R, decltype(CB)::value, decltype(TB)::value>(S, mm);
             });
             break;
           }
@@ -292,23 +383,23 @@ __global__ void __launch_bounds__(STREAM_THREADS, HEAVY ? 1 : STREAM_MIN_CTAS)
 #pragma unroll
                 for (int g = 0; g < (1 << (R - 1)); ++g) {
                   const int i0 = pair_i0<R, BIT>(g), i1 = i0 | (1 << BIT);
-                  const T r = re[i0], q = im[i0];
-                  re[i0] = re[i1];
-                  im[i0] = im[i1];
-                  re[i1] = r;
-                  im[i1] = q;
+                  const T r = S.re(i0), q = S.im(i0);
+                  S.re(i0) = S.re(i1);
+                  S.im(i0) = S.im(i1);
+                  S.re(i1) = r;
+                  S.im(i1) = q;
                 }
               });
             } else if (op.k == 2) {
               dispatch2<T, R>(op.b0, op.b1, [&](auto JA, auto JB) {
                 if constexpr (decltype(JA)::value > decltype(JB)::value)
-                  reg_perm2<T, R, decltype(JA)::value, decltype(JB)::value>(re, im,
+                  reg_perm2<T, R, decltype(JA)::value, decltype(JB)::value>(S,
                                                                             (unsigned)op.data);
               });
             } else if (HEAVY && op.k == 3) {
-              reg_permk<T, R, 3>(re, im, op.data);
+              reg_permk<T, R, 3>(S, op.data);
             } else if (HEAVY) {
-              reg_permk<T, R, 4>(re, im, op.data);
+              reg_permk<T, R, 4>(S, op.data);
             }
             break;
           }
@@ -321,9 +412,9 @@ __global__ void __launch_bounds__(STREAM_THREADS, HEAVY ? 1 : STREAM_MIN_CTAS)
               for (int j = 0; j < op.k; ++j)
                 loc |= (int)((gi >> ((op.data >> (6 * j)) & 63)) & 1ull) << (op.k - 1 - j);
               const cx<T> d = m[loc];
-              const T r = re[v], q = im[v];
-              re[v] = d.x * r - d.y * q;
-              im[v] = d.x * q + d.y * r;
+              const T r = S.re(v), q = S.im(v);
+              S.re(v) = d.x * r - d.y * q;
+              S.im(v) = d.x * q + d.y * r;
             }
             break;
           }
@@ -335,11 +426,11 @@ __global__ void __launch_bounds__(STREAM_THREADS, HEAVY ? 1 : STREAM_MIN_CTAS)
 #pragma unroll
           for (int v = 0; v < D; v += 2)
             *reinterpret_cast<float4*>(gs + (base | offv(v))) =
-                make_float4(re[v], im[v], re[v + 1], im[v + 1]);
+                make_float4(S.r2[v >> 1].x, S.i2[v >> 1].x, S.r2[v >> 1].y, S.i2[v >> 1].y);
         }
       } else {
 #pragma unroll
-        for (int v = 0; v < D; ++v) gs[base | offv(v)] = mk<T>(re[v], im[v]);
+        for (int v = 0; v < D; ++v) gs[base | offv(v)] = mk<T>(S.re(v), S.im(v));
       }
     }
   }

@@ -195,6 +195,9 @@ class CudaShardEngine:
     def to_host(self, state) -> np.ndarray:
         return state.cpu().numpy()
 
+    def sync(self):
+        self.torch.cuda.synchronize(self.ex.device)
+
 
 class ShardedExecutor:
     """Drop-in for ``Script.executor``: runs one statevector circuit split over all ranks
@@ -205,6 +208,7 @@ class ShardedExecutor:
 
     def __init__(self, engine=None):
         self.engine = engine
+        self._default_engine = None
         self.stats = {}
 
     def _world(self) -> Tuple[int, int, int]:
@@ -218,29 +222,51 @@ class ShardedExecutor:
                 to_host: bool = True):
         if batch != 1 or plan.program.density:
             raise ValueError("qubit sharding runs one statevector circuit at a time")
-        eng = self.engine or CudaShardEngine()
+        if self.engine is None and self._default_engine is None:
+            self._default_engine = CudaShardEngine()
+        eng = self.engine or self._default_engine
         rank, size, g = self._world()
         prog = plan.program
         n, nl = prog.n_bits, prog.n_bits - g
-        steps, pos, consts = plan_epochs(prog, g)
+        # epochs and their device programs are built once per plan and rank count
+        key = ("sharded", size, id(eng))
+        cached = plan.device.get(key)
+        if cached is None:
+            steps, pos, consts = plan_epochs(prog, g)
+            compiled = []
+            for st in steps:
+                if st[0] == "exchange":
+                    compiled.append(("exchange", None))
+                elif len(st[1]) or not compiled:
+                    compiled.append(("ops", eng.make(epoch_program(prog, st[1], consts, nl),
+                                                     plan.precision)))
+            cached = plan.device[key] = (compiled, pos)
+        compiled, pos = cached
         staged = eng.stage_args(host_args)
+
+        import time
 
         state = eng.alloc(nl, plan.precision)
         first, n_exchange, n_epochs = True, 0, 0
-        for st in steps:
-            if st[0] == "exchange":
+        t_ex = 0.0
+        timed = getattr(eng, "sync", None)
+        for kind, handle in compiled:
+            if kind == "exchange":
+                if timed:
+                    timed()
+                    t0 = time.perf_counter()
                 state = eng.exchange(state, g)
+                if timed:
+                    timed()
+                    t_ex += time.perf_counter() - t0
                 n_exchange += 1
                 continue
-            if len(st[1]) == 0 and not first:
-                continue
-            handle = eng.make(epoch_program(prog, st[1], consts, nl), plan.precision)
             init = (1 if rank == 0 else 2) if first else 0
             state = eng.evolve(handle, staged, state, init)
             first = False
             n_epochs += 1
         self.stats = {"exchanges": n_exchange, "epochs": n_epochs, "local_bits": nl,
-                      "ranks": size, "bytes_sent_per_exchange":
+                      "ranks": size, "exchange_seconds": t_ex, "bytes_sent_per_exchange":
                       (size - 1) * (2 ** nl // size) * (16 if plan.precision == "complex128"
                                                         else 8)}
 
