@@ -367,6 +367,34 @@ int upload(qmlb_program* p) {
          o_terms = place(off, p->terms), o_consts = place(off, p->consts),
          o_obs = place(off, p->obs), o_oc = place(off, p->obs_consts),
          o_pre = place(off, p->pre);
+  // register kernel: which ops read their matrix from one / two hoisted-factor tables
+  std::vector<RegFast> fast;
+  if (p->strategy == 0) {
+    fast.assign(p->ops.size(), RegFast{});
+    for (size_t i = 0; i < p->ops.size(); ++i) {
+      const qmlb_op& o = p->ops[i];
+      if (o.kind != QMLB_OP_MAT && o.kind != QMLB_OP_CTRL1) continue;
+      const qmlb_source& s = p->sources[o.src];
+      RegFast f{};
+      if (s.kind == QMLB_SRC_PRE) {
+        f.n = 1;
+        f.slot0 = s.a1;
+        f.local0 = s.a0;
+      } else if (s.kind == QMLB_SRC_CHAIN && s.a1 == 2 &&
+                 p->sources[p->items[s.a0]].kind == QMLB_SRC_PRE &&
+                 p->sources[p->items[s.a0 + 1]].kind == QMLB_SRC_PRE) {
+        const qmlb_source& a = p->sources[p->items[s.a0]];
+        const qmlb_source& b = p->sources[p->items[s.a0 + 1]];
+        f.n = 2;
+        f.slot0 = a.a1;
+        f.local0 = a.a0;
+        f.slot1 = b.a1;
+        f.local1 = b.a0;
+      }
+      fast[i] = f;
+    }
+  }
+  const size_t o_fast = place(off, fast);
   size_t o_ids[QMLB_MAX_ARGS];
   for (int a = 0; a < QMLB_MAX_ARGS; ++a) o_ids[a] = place(off, p->pre_ids[a]);
   struct PO {
@@ -392,6 +420,7 @@ int upload(qmlb_program* p) {
   put(o_obs, p->obs.data(), p->obs.size() * sizeof(qmlb_obs));
   put(o_oc, p->obs_consts.data(), p->obs_consts.size() * sizeof(double));
   put(o_pre, p->pre.data(), p->pre.size() * sizeof(qmlb_pre));
+  put(o_fast, fast.data(), fast.size() * sizeof(RegFast));
   for (int a = 0; a < QMLB_MAX_ARGS; ++a)
     put(o_ids[a], p->pre_ids[a].data(), p->pre_ids[a].size() * sizeof(int32_t));
   for (size_t i = 0; i < p->passes.size(); ++i) {
@@ -413,6 +442,7 @@ int upload(qmlb_program* p) {
   d.obs_consts = reinterpret_cast<const double*>(base + o_oc);
   d.pre = reinterpret_cast<const qmlb_pre*>(base + o_pre);
   d.n_pre = (int)p->pre.size();
+  d.fast = fast.empty() ? nullptr : reinterpret_cast<const RegFast*>(base + o_fast);
   for (int a = 0; a < QMLB_MAX_ARGS; ++a)
     p->pre_ids_dev[a] = reinterpret_cast<const int32_t*>(base + o_ids[a]);
   d.n_ops = (int)p->ops.size();

@@ -45,6 +45,12 @@ __device__ __forceinline__ cx<T> cadd(cx<T> a, cx<T> b) {
 __device__ __forceinline__ void sincos_t(double a, double* s, double* c) { sincos(a, s, c); }
 __device__ __forceinline__ void sincos_t(float a, float* s, float* c) { sincosf(a, s, c); }
 
+// Register kernel: per op, the hoisted factors its 2x2 matrix is made of when the source
+// is one SRC_PRE or a chain of two (matrix = factor1 * factor0), else n = 0.
+struct RegFast {
+  int32_t n, slot0, local0, slot1, local1, pad0, pad1, pad2;
+};
+
 // Device copy of a program (all pointers are device pointers into one blob).
 struct DevProg {
   const qmlb_op* ops;
@@ -56,6 +62,7 @@ struct DevProg {
   const qmlb_obs* obs;
   const double* obs_consts;
   const qmlb_pre* pre;
+  const RegFast* fast;  // strategy 0 only, else nullptr
   int32_t n_ops, n_obs, n_bits, n_qubits, density, out_type, n_pre, pad;
 };
 

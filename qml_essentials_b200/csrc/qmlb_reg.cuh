@@ -206,7 +206,7 @@ struct RowsShared {
 // registers / thread), which is what hides the table-lookup latency.
 template <typename T, int N>
 constexpr int reg_min_ctas() {
-  return (2 * (1 << N) * (int)sizeof(T) / 4 <= 64) ? QMLB_REG_MIN_CTAS : 1;
+  return (2 * (1 << N) * (int)sizeof(T) / 4 <= 64) ? (sizeof(T) == 8 ? 2 : QMLB_REG_MIN_CTAS) : 1;
 }
 
 template <typename T, int N>
@@ -232,8 +232,41 @@ __global__ void __launch_bounds__(128, reg_min_ctas<T, N>()) k_reg(DevProg P, Ru
   }
   S.re(0) = (T)1;
 
+  // Software pipeline over the op stream: the hoisted-factor table rows of op o+1 are
+  // requested (plain loads into registers) before op o is applied, so their L2 latency
+  // overlaps the arithmetic instead of stalling every gate (ncu: long-scoreboard was the
+  // top stall with 8-12 resident warps per SM).
+  cx<T> nf0[4], nf1[4];
+  int nfn = 0;
+  auto fetch = [&](int o) {
+    nfn = 0;
+    if (o >= P.n_ops || P.fast == nullptr) return;
+    const RegFast d = P.fast[o];
+    if (d.n < 1 || !R.pre_on[d.slot0] || (d.n == 2 && !R.pre_on[d.slot1])) return;
+    nfn = d.n;
+    const cx<T>* t0 = static_cast<const cx<T>*>(R.pre_tab[d.slot0]) +
+                      ((int64_t)d.local0 * R.a[d.slot0].mod + rows(d.slot0)) * 4;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) nf0[i] = t0[i];
+    if (d.n == 2) {
+      const cx<T>* t1 = static_cast<const cx<T>*>(R.pre_tab[d.slot1]) +
+                        ((int64_t)d.local1 * R.a[d.slot1].mod + rows(d.slot1)) * 4;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) nf1[i] = t1[i];
+    }
+  };
+  fetch(0);
+
   for (int o = 0; o < P.n_ops; ++o) {
     const qmlb_op op = P.ops[o];
+    cx<T> m[4];
+    const bool have_m = nfn > 0;
+    if (have_m) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) m[i] = nf0[i];
+      if (nfn == 2) mul2_left<T>(nf1, m);
+    }
+    fetch(o + 1);
     if (op.kind == QMLB_OP_PERM) {
       if (op.k == 1) {  // the only non-identity 1-bit permutation is X
         dispatch1<T, N>(op.bits[0], [&](auto B) {
@@ -282,7 +315,6 @@ __global__ void __launch_bounds__(128, reg_min_ctas<T, N>()) k_reg(DevProg P, Ru
       continue;
     }
     // remaining kinds take one 2x2 matrix
-    cx<T> m[4];
     if (op.kind == QMLB_OP_DIAG) {
       const qmlb_source s = P.src[op.src];
       m[1] = mk<T>(0, 0);
@@ -298,7 +330,7 @@ __global__ void __launch_bounds__(128, reg_min_ctas<T, N>()) k_reg(DevProg P, Ru
         m[0] = ld_const<T>(P.consts, s.a0);
         m[3] = ld_const<T>(P.consts, s.a0 + 1);
       }
-    } else {
+    } else if (!have_m) {
       eval_2x2<T>(P, R, rows, op.src, m);
     }
     if (op.kind == QMLB_OP_CTRL1) {
