@@ -558,13 +558,6 @@ class _Lowerer:
         factors = spec.factors if isinstance(spec, ProductMat) else [spec]
         ket = [self.ket_bit(w) for w in wires]
         for f in factors:
-            if self.density and isinstance(f, ConstMat) and 2 * len(wires) <= 4:
-                perm = _permutation_of(f.matrix)
-                if perm is not None and not _is_identity(f.matrix):
-                    # U (x) conj(U) of a permutation is one permutation of 2k bits
-                    big = np.kron(f.matrix, f.matrix.conj())
-                    self.emit_const(ket + [self.bra_bit(w) for w in wires], big)
-                    continue
             self.emit_elementary(ket, f)
             if self.density:
                 self.emit_elementary([self.bra_bit(w) for w in wires], _conj_spec(f))

@@ -210,8 +210,6 @@ int schedule_stream(qmlb_program* p, int R) {
   std::vector<char> done(p->ops.size(), 0);
   size_t remaining = p->ops.size();
   bool first_pass = true;
-  const int sector_bits = p->dtype == QMLB_C128 ? 1 : 2;
-  const uint64_t sector_mask = (1ull << sector_bits) - 1;
   while (remaining > 0 || first_pass) {
     uint64_t S = 0, blocked = 0;
     std::vector<int> canon;  // ordered: register position j -> state bit (k >= 3 op)
@@ -222,12 +220,14 @@ int schedule_stream(qmlb_program* p, int R) {
       const qmlb_op& o = p->ops[i];
       uint64_t bits = 0;
       for (int j = 0; j < o.k; ++j) bits |= 1ull << o.bits[j];
-      // a 32-byte sector (state bits 0..1 in complex64, bit 0 in complex128) is owned by
-      // one thread: an op that touches a sector bit brings the whole sector into the group
+      // complex64: a group that holds state bit 1 but not bit 0 would touch only every
+      // other 8 bytes of each line; bringing bit 0 along makes the thread move whole
+      // 16-byte pairs (bit 0 alone is fine: lanes then cover consecutive pairs).  complex128
+      // amplitudes are 16 bytes already.
       uint64_t grp = bits;
-      if (o.kind != QMLB_OP_DIAG && (bits & sector_mask) && N >= R + 2 &&
-          __builtin_popcountll(bits | sector_mask) <= R)
-        grp |= sector_mask;
+      if (o.kind != QMLB_OP_DIAG && p->dtype != QMLB_C128 && (bits & 2ull) && N >= R + 2 &&
+          __builtin_popcountll(bits | 1ull) <= R)
+        grp |= 1ull;
       const int e = op_entries(p, o);
       if ((bits & blocked) || entries + e > max_entries ||
           (int)picked.size() >= STREAM_MAX_OPS) {
@@ -272,12 +272,7 @@ int schedule_stream(qmlb_program* p, int R) {
     // 3-4 bits pinned other bits there -> the kernel moves 16-byte pairs
     for (int g = 0; g < N; ++g)
       if ((S >> g & 1) && !in_gb(g)) gb.push_back(g);
-    // keep 32-byte sectors whole per thread: complete the lowest sector bits if one is present
-    bool touches_low = false;
-    for (int g : gb) touches_low = touches_low || g < sector_bits;
-    if (touches_low)
-      for (int g = 0; g < sector_bits && (int)gb.size() < R; ++g)
-        if (!in_gb(g)) gb.push_back(g);
+    if (p->dtype != QMLB_C128 && in_gb(1) && !in_gb(0) && (int)gb.size() < R) gb.push_back(0);
     for (int g = N - 1; g >= 0 && (int)gb.size() < R; --g)
       if (!in_gb(g)) gb.push_back(g);
     std::vector<int> pos(N, -1);
@@ -395,6 +390,7 @@ int upload(qmlb_program* p) {
     }
   }
   const size_t o_fast = place(off, fast);
+  const size_t o_matlist = place(off, p->stream_matlist);
   size_t o_ids[QMLB_MAX_ARGS];
   for (int a = 0; a < QMLB_MAX_ARGS; ++a) o_ids[a] = place(off, p->pre_ids[a]);
   struct PO {
@@ -421,6 +417,7 @@ int upload(qmlb_program* p) {
   put(o_oc, p->obs_consts.data(), p->obs_consts.size() * sizeof(double));
   put(o_pre, p->pre.data(), p->pre.size() * sizeof(qmlb_pre));
   put(o_fast, fast.data(), fast.size() * sizeof(RegFast));
+  put(o_matlist, p->stream_matlist.data(), p->stream_matlist.size() * sizeof(StreamMatOp));
   for (int a = 0; a < QMLB_MAX_ARGS; ++a)
     put(o_ids[a], p->pre_ids[a].data(), p->pre_ids[a].size() * sizeof(int32_t));
   for (size_t i = 0; i < p->passes.size(); ++i) {
@@ -443,6 +440,7 @@ int upload(qmlb_program* p) {
   d.pre = reinterpret_cast<const qmlb_pre*>(base + o_pre);
   d.n_pre = (int)p->pre.size();
   d.fast = fast.empty() ? nullptr : reinterpret_cast<const RegFast*>(base + o_fast);
+  p->stream_matlist_dev = reinterpret_cast<const StreamMatOp*>(base + o_matlist);
   for (int a = 0; a < QMLB_MAX_ARGS; ++a)
     p->pre_ids_dev[a] = reinterpret_cast<const int32_t*>(base + o_ids[a]);
   d.n_ops = (int)p->ops.size();
@@ -551,6 +549,24 @@ int plan(qmlb_program* p) {
   {
     int rc = schedule_stream(p, p->stream_r);
     if (rc != QMLB_OK) return rc;
+  }
+  {
+    int row = 0;
+    for (QmlbStreamPassHost& ps : p->stream_passes) {
+      ps.dev.mat_base = row;
+      for (size_t i = 0; i < ps.ops.size(); ++i) {
+        const qmlb_op& o = ps.ops[i];
+        if (o.kind == QMLB_OP_PERM) continue;
+        StreamMatOp mo{};
+        mo.src = o.src;
+        mo.off = row + ps.matoff[i];
+        mo.swap2 = (o.kind == QMLB_OP_MAT && o.k == 2 && o.bits[0] < o.bits[1]) ? 1 : 0;
+        p->stream_matlist.push_back(mo);
+      }
+      row += ps.matw;
+    }
+    p->stream_mat_row = row;
+    for (QmlbStreamPassHost& ps : p->stream_passes) ps.dev.mat_row = row;
   }
   if (env_int("QMLB_DUMP_PASSES", 0)) {
     static const char* kinds[] = {"MAT", "CTRL1", "PERM", "DIAG"};
@@ -664,6 +680,12 @@ size_t pre_layout(const qmlb_program* p, const qmlb_arg* a, int64_t batch, bool 
   return total;
 }
 
+// batched streaming runs keep a table of every (element, op) matrix
+size_t premats_bytes(const qmlb_program* p, int64_t batch) {
+  if (p->strategy != 2 || batch <= 1) return 0;
+  return ((size_t)batch * p->stream_mat_row * cs_of(p->dtype) + 255) & ~size_t(255);
+}
+
 size_t state_layout(const qmlb_program* p, int64_t batch, size_t* part_off) {
   size_t need = p->direct_out ? 0 : (size_t)batch * (size_t(1) << p->n_bits) * cs_of(p->dtype);
   *part_off = (need + 255) & ~size_t(255);
@@ -672,7 +694,7 @@ size_t state_layout(const qmlb_program* p, int64_t batch, size_t* part_off) {
     need = *part_off + (size_t)batch * z1_ctas(p, batch) * 33 * sizeof(double);
   else if (!p->direct_out && chunks > 1)
     need = *part_off + (size_t)batch * p->obs.size() * chunks * rs_of(p->dtype);
-  return (need + 255) & ~size_t(255);
+  return ((need + 255) & ~size_t(255)) + premats_bytes(p, batch);
 }
 
 // fills the hoisted-factor tables at the start of `workspace`; returns their size
@@ -703,7 +725,10 @@ int prepare_tables(const qmlb_program* p, RunArgs& R, void* workspace, size_t ws
 // the streamed gate passes over `state`; init_mode 1: |0..0>, 2: zero vector, 0: continue
 template <typename T>
 int evolve_stream(const qmlb_program* p, const RunArgs& R, void* state, int init_mode,
-                  cudaStream_t st) {
+                  void* premats, cudaStream_t st) {
+  if (premats)
+    CUDA_TRY((std::is_same<T, double>::value ? launch_stream_mats_f64 : launch_stream_mats_f32)(
+        p, R, premats, st));
   const int64_t items = int64_t(1) << (p->n_bits - p->stream_r);
   const int64_t ctas_x = (items + STREAM_THREADS - 1) / STREAM_THREADS;
   const int64_t want = (int64_t)p->sm_count * 16;  // persistent: CTAs loop over items / elements
@@ -726,7 +751,7 @@ int evolve_stream(const qmlb_program* p, const RunArgs& R, void* state, int init
       if (init_mode == 2) pass.flags |= QMLB_PASS_INIT_ZERO;
     }
     CUDA_TRY((std::is_same<T, double>::value ? launch_stream_f64 : launch_stream_f32)(
-        p, R, pass, grid, state, st));
+        p, R, pass, grid, state, premats, st));
   }
   return QMLB_OK;
 }
@@ -753,7 +778,12 @@ int run_typed(const qmlb_program* p, RunArgs& R, void* out, void* workspace, siz
     void* dst = p->direct_out ? out : static_cast<void*>(ws_state);
     CUDA_TRY((std::is_same<T, double>::value ? launch_reg_f64 : launch_reg_f32)(p, R, dst, st));
   } else if (p->strategy == 2) {
-    int rc = evolve_stream<T>(p, R, state, 1, st);
+    // [tables | state + partials | premats]
+    void* premats = nullptr;
+    if (premats_bytes(p, R.batch))
+      premats = static_cast<unsigned char*>(workspace) + tab_bytes +
+                (state_layout(p, R.batch, &part_off) - premats_bytes(p, R.batch));
+    int rc = evolve_stream<T>(p, R, state, 1, premats, st);
     if (rc != QMLB_OK) return rc;
   } else {
     for (const QmlbPassHost& ps : p->passes) {
@@ -894,10 +924,10 @@ int qmlb_evolve(const qmlb_program* p, const qmlb_arg* args, int32_t n_args, int
   size_t tab = 0;
   if (p->dtype == QMLB_C128) {
     rc = prepare_tables<double>(p, R, workspace, workspace_bytes, st, &tab);
-    return rc != QMLB_OK ? rc : evolve_stream<double>(p, R, state, init_mode, st);
+    return rc != QMLB_OK ? rc : evolve_stream<double>(p, R, state, init_mode, nullptr, st);
   }
   rc = prepare_tables<float>(p, R, workspace, workspace_bytes, st, &tab);
-  return rc != QMLB_OK ? rc : evolve_stream<float>(p, R, state, init_mode, st);
+  return rc != QMLB_OK ? rc : evolve_stream<float>(p, R, state, init_mode, nullptr, st);
 }
 
 size_t qmlb_zsums_workspace_bytes(int64_t batch, int32_t n_bits) {

@@ -55,7 +55,10 @@ struct qmlb_program {
   size_t smem = 0;
   std::vector<QmlbPassHost> passes;
   std::vector<QmlbStreamPassHost> stream_passes;
-  int stream_r = 5;
+  int stream_r = 4;
+  std::vector<qmlb::StreamMatOp> stream_matlist;         // every matrix of every pass
+  const qmlb::StreamMatOp* stream_matlist_dev = nullptr;
+  int stream_mat_row = 0;                                // entries per element
   int sm_count = 148;
 
   void* blob = nullptr;
@@ -77,9 +80,13 @@ cudaError_t launch_tile_f32(const qmlb_program* p, const RunArgs& R, const PassD
 cudaError_t launch_tile_f64(const qmlb_program* p, const RunArgs& R, const PassDev& pass,
                             unsigned grid, void* state, cudaStream_t st);
 cudaError_t launch_stream_f32(const qmlb_program* p, const RunArgs& R, const StreamPass& pass,
-                              dim3 grid, void* state, cudaStream_t st);
+                              dim3 grid, void* state, const void* premats, cudaStream_t st);
 cudaError_t launch_stream_f64(const qmlb_program* p, const RunArgs& R, const StreamPass& pass,
-                              dim3 grid, void* state, cudaStream_t st);
+                              dim3 grid, void* state, const void* premats, cudaStream_t st);
+cudaError_t launch_stream_mats_f32(const qmlb_program* p, const RunArgs& R, void* out,
+                                   cudaStream_t st);
+cudaError_t launch_stream_mats_f64(const qmlb_program* p, const RunArgs& R, void* out,
+                                   cudaStream_t st);
 cudaError_t tile_set_smem_f32(size_t bytes);
 cudaError_t tile_set_smem_f64(size_t bytes);
 

@@ -215,6 +215,33 @@ __device__ __forceinline__ void reg_perm2(RegState<T, N>& S, unsigned packed) {
   }
 }
 
+// Batched streaming runs (density matrices, config 4): one thread per (element, matrix)
+// evaluates the matrix sources of ALL passes once into a table, so the gate-pass CTAs only
+// copy their few hundred bytes instead of each re-deriving sincos + 4x4 chain products.
+template <typename T>
+__global__ void k_stream_mats(DevProg P, RunArgs A, const StreamMatOp* __restrict__ list,
+                              int n_list, int mat_row, cx<T>* __restrict__ out) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= A.batch * n_list) return;
+  const int64_t bl = t / n_list;
+  const StreamMatOp mo = list[t % n_list];
+  cx<T>* dst = out + (size_t)bl * mat_row + mo.off;
+  const RowsDirect rows{A, bl + A.batch_offset};
+  if (mo.swap2) {
+    cx<T> tmp[16];
+    eval_source_mem<T>(P, A, rows, mo.src, tmp);
+#pragma unroll
+    for (int v = 0; v < 4; ++v)
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int sv = ((v & 1) << 1) | (v >> 1), su = ((u & 1) << 1) | (u >> 1);
+        dst[sv * 4 + su] = tmp[v * 4 + u];
+      }
+  } else {
+    eval_source_mem<T>(P, A, rows, mo.src, dst);
+  }
+}
+
 // HEAVY = the pass holds a dense / permutation op on 3 or 4 bits (rare: CCX, CSWAP,
 // 2-qubit channels); the lean variant keeps the register count of the common passes low.
 // IDX = uint32_t when every amplitude index of the launch fits 32 bits (one element of at
@@ -222,7 +249,7 @@ __device__ __forceinline__ void reg_perm2(RegState<T, N>& S, unsigned packed) {
 template <typename T, int R, bool HEAVY, typename IDX>
 __global__ void __launch_bounds__(STREAM_THREADS, HEAVY ? 1 : (sizeof(T) == 4 ? 4 : STREAM_MIN_CTAS))
     k_stream(DevProg P, RunArgs A, const __grid_constant__ StreamPass pass,
-             cx<T>* __restrict__ gstate) {
+             cx<T>* __restrict__ gstate, const cx<T>* __restrict__ premats) {
   constexpr int D = 1 << R;
   // complex64: amplitudes v and v^1 are moved as one 16-byte access when register bit 0
   // is state bit 0 (the scheduler then also puts state bit 1 at register bit 1, so a
@@ -251,6 +278,11 @@ __global__ void __launch_bounds__(STREAM_THREADS, HEAVY ? 1 : (sizeof(T) == 4 ? 
   for (int64_t bl = blockIdx.y; bl < A.batch; bl += gridDim.y) {
     const int64_t b = bl + A.batch_offset;
     __syncthreads();  // previous element's matrices are no longer read
+    if (premats != nullptr) {
+      // batched run: the matrices of every (element, op) were evaluated by k_stream_mats
+      const cx<T>* row = premats + (size_t)bl * pass.mat_row + pass.mat_base;
+      for (int e = threadIdx.x; e < pass.matw; e += blockDim.x) mb[e] = row[e];
+    } else
     for (int j = threadIdx.x; j < pass.n_ops; j += blockDim.x) {
       const StreamOp op = pass.ops[j];
       if (op.kind == QMLB_OP_PERM) continue;

@@ -6,28 +6,40 @@ namespace qmlb {
 
 template <bool HEAVY, typename IDX>
 static void launch_v(const qmlb_program* p, const RunArgs& R, const StreamPass& pass, dim3 grid,
-                     cx<QMLB_T>* s, size_t smem, cudaStream_t st) {
+                     cx<QMLB_T>* s, const cx<QMLB_T>* premats, size_t smem, cudaStream_t st) {
   static bool attr_set = false;  // > 48 KB of dynamic shared memory needs the opt-in (once)
   if (!attr_set) {
     cudaFuncSetAttribute(k_stream<QMLB_T, QMLB_STREAM_R, HEAVY, IDX>,
                          cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
     attr_set = true;
   }
-  k_stream<QMLB_T, QMLB_STREAM_R, HEAVY, IDX><<<grid, STREAM_THREADS, smem, st>>>(p->dev, R, pass, s);
+  k_stream<QMLB_T, QMLB_STREAM_R, HEAVY, IDX><<<grid, STREAM_THREADS, smem, st>>>(p->dev, R, pass, s, premats);
+}
+
+cudaError_t QMLB_LAUNCH_STREAM_MATS(const qmlb_program* p, const RunArgs& R, void* out,
+                                    cudaStream_t st) {
+  const int64_t total = R.batch * (int64_t)p->stream_matlist.size();
+  if (total == 0) return cudaSuccess;
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  k_stream_mats<QMLB_T><<<(unsigned)((total + 63) / 64), 64, 0, st>>>(
+      p->dev, R, p->stream_matlist_dev, (int)p->stream_matlist.size(), p->stream_mat_row,
+      static_cast<cx<QMLB_T>*>(out));
+  return cudaGetLastError();
 }
 
 cudaError_t QMLB_LAUNCH_STREAM(const qmlb_program* p, const RunArgs& R, const StreamPass& pass,
-                               dim3 grid, void* state, cudaStream_t st) {
+                               dim3 grid, void* state, const void* premats_v, cudaStream_t st) {
   cx<QMLB_T>* s = static_cast<cx<QMLB_T>*>(state);
+  const cx<QMLB_T>* premats = static_cast<const cx<QMLB_T>*>(premats_v);
   g_launches.fetch_add(1, std::memory_order_relaxed);
   const size_t smem = ((size_t)pass.matw + 2 * (size_t(1) << QMLB_STREAM_R) * STREAM_THREADS) *
                       sizeof(cx<QMLB_T>);
   const bool heavy = pass.flags & QMLB_PASS_HEAVY;
   const bool narrow = pass.n_bits <= 32;  // element-relative indices
-  if (heavy && narrow) launch_v<true, uint32_t>(p, R, pass, grid, s, smem, st);
-  else if (heavy) launch_v<true, uint64_t>(p, R, pass, grid, s, smem, st);
-  else if (narrow) launch_v<false, uint32_t>(p, R, pass, grid, s, smem, st);
-  else launch_v<false, uint64_t>(p, R, pass, grid, s, smem, st);
+  if (heavy && narrow) launch_v<true, uint32_t>(p, R, pass, grid, s, premats, smem, st);
+  else if (heavy) launch_v<true, uint64_t>(p, R, pass, grid, s, premats, smem, st);
+  else if (narrow) launch_v<false, uint32_t>(p, R, pass, grid, s, premats, smem, st);
+  else launch_v<false, uint64_t>(p, R, pass, grid, s, premats, smem, st);
   return cudaGetLastError();
 }
 

@@ -21,6 +21,14 @@ struct StreamOp {
   uint64_t data;            // PERM: table packed k bits/entry; DIAG: global bits, 6 bits each
 };
 
+// one matrix of the per-element table filled by k_stream_mats (batched runs)
+struct StreamMatOp {
+  int32_t src;    // matrix source
+  int32_t off;    // offset (complex entries) in the element's row
+  int32_t swap2;  // 4x4 whose two local bits must swap roles (canonical register order)
+  int32_t pad;
+};
+
 struct StreamPass {
   StreamOp ops[STREAM_MAX_OPS];
   uint16_t matoff[STREAM_MAX_OPS];  // per op: offset (complex entries) into the matrix buffer
@@ -28,6 +36,8 @@ struct StreamPass {
   int32_t n_bits;          // total state bits
   int32_t flags;           // QMLB_PASS_INIT | QMLB_PASS_HEAVY
   int32_t matw;            // matrix buffer entries
+  int32_t mat_base;        // offset of this pass in a per-element row of precomputed matrices
+  int32_t mat_row;         // entries per element in that table (sum of matw over passes)
   int32_t gb[STREAM_MAX_R];      // register bit j -> state bit
   int32_t sorted[STREAM_MAX_R];  // the same bits ascending
 };

@@ -192,8 +192,11 @@ def test_compiler_fusion_counts():
     n_chan = sum(isinstance(o, op.KrausChannel) for o in m.script._record(
         m.params, np.array([0.3]), noise_params=m.noise_params, random_key=rng.key(0)))
     assert n_chan > 40
-    # ops: one 4x4 superchain per (layer-block, wire) + one 4-bit permutation per CX
-    assert len(plan.program.ops) < 0.5 * plan.n_ops
+    # ops: one 4x4 superchain per (layer-block, wire) + two 2-bit permutations per CX
+    # (ket side and bra side), none for the channels
+    assert len(plan.program.ops) <= 0.65 * plan.n_ops
+    kinds = list(plan.program.ops["kind"])
+    assert kinds.count(compiler.OP_PERM) == 2 * 18  # 18 CX -> ket-side + bra-side shuffles
 
 
 def test_plan_cache_reuse_and_value_independence():
