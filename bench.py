@@ -215,7 +215,7 @@ def hbm_peak_gbs():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def run_reference(args):
+def run_reference(args, json_out):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -247,10 +247,22 @@ def run_reference(args):
         "e2e": {"value": value, "unit": "evals/s", "h2d_bytes_per_step": 0,
                 "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    json_out.write(json.dumps(line) + "\n")
+    json_out.flush()
+
+
+def _claim_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries (NCCL's version banner, ...) also
+    write to file descriptor 1, so the real stdout is kept aside for the JSON line and fd 1
+    is pointed at stderr for everything else."""
+    sys.stdout.flush()
+    keep = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    return keep
 
 
 def main():
+    json_out = _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -266,7 +278,7 @@ def main():
     args.warmup = max(args.warmup, 3)
 
     if args.impl == "reference":
-        run_reference(args)
+        run_reference(args, json_out)
         return
 
     import torch
@@ -469,9 +481,15 @@ def main():
             line["cpu_baseline"] = {"value": cpu_v, "unit": "evals/s", "cores": cores,
                                     "kind": "port", "sample": sample,
                                     "max_abs_err_vs_gpu": err}
-        print(json.dumps(line), flush=True)
+        json_out.write(json.dumps(line) + "\n")
+        json_out.flush()
     if world > 1:
-        dist.destroy_process_group()
+        # The NCCL communicator is referenced by the captured CUDA graph; tearing the
+        # process group down with it alive can block.  Everything is reported: leave
+        # without the collective shutdown.
+        torch.cuda.synchronize()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 if __name__ == "__main__":
