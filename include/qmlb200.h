@@ -180,6 +180,13 @@ const char* qmlb_last_error(void);
 int qmlb_program_create(const qmlb_program_desc* desc, qmlb_program** out);
 int qmlb_program_destroy(qmlb_program* prog);
 
+/* Host-only planning (no CUDA call, works without a GPU): validates `desc`, plans it and
+ * writes a text description into buf - "strategy S", then for streamed programs one
+ * line per fused gate pass: "pass flags F group b0 b1 .. ops i:kind:bits ..." where i is the
+ * index of the op in desc->ops and bits are register positions (state bits for diagonal
+ * ops).  Used by the CPU test-suite to check the pass scheduler. */
+int qmlb_plan_describe(const qmlb_program_desc* desc, char* buf, size_t buflen);
+
 /* strategy: 0 = register-resident (one thread per circuit), 1 = shared-memory
  * resident (one warp / CTA per circuit), 2 = streamed tile passes over HBM.
  * n_passes: state passes per run (strategy 2), n_device_ops: ops after fusion. */

@@ -31,7 +31,7 @@ EXPORTED_SYMBOLS = (
     "qmlb_version", "qmlb_launch_count", "qmlb_last_error", "qmlb_program_create",
     "qmlb_program_destroy", "qmlb_program_info", "qmlb_workspace_bytes", "qmlb_run",
     "qmlb_sample", "qmlb_purity", "qmlb_overlap_fidelity", "qmlb_fma_peak",
-    "qmlb_evolve", "qmlb_zsums", "qmlb_zsums_workspace_bytes",
+    "qmlb_evolve", "qmlb_zsums", "qmlb_zsums_workspace_bytes", "qmlb_plan_describe",
 )
 QMLB_DESC_FORCE_STREAM = 1
 
@@ -96,6 +96,7 @@ def load_library(path: str = LIB_PATH) -> C.CDLL:
                                 C.c_void_p, C.c_int32, C.c_void_p, C.c_size_t, C.c_void_p]
     lib.qmlb_zsums_workspace_bytes.argtypes = [C.c_int64, C.c_int32]
     lib.qmlb_zsums_workspace_bytes.restype = C.c_size_t
+    lib.qmlb_plan_describe.argtypes = [C.POINTER(_Desc), C.c_char_p, C.c_size_t]
     lib.qmlb_zsums.argtypes = [C.c_void_p, C.c_int, C.c_int64, C.c_int32, C.c_void_p,
                                C.c_void_p, C.c_size_t, C.c_void_p]
     return lib
@@ -103,6 +104,43 @@ def load_library(path: str = LIB_PATH) -> C.CDLL:
 
 def _np_ptr(a: np.ndarray) -> Optional[int]:
     return a.ctypes.data if a.size else None
+
+
+def make_desc(prog: Program, out_type: int, obs_recs, obs_pool, precision: str,
+              flags: int = 0):
+    """``qmlb_program_desc`` over the arrays of a compiled program.  Returns the struct
+    and the list of arrays that must stay alive while it is in use."""
+    dt = QMLB_C128 if precision == "complex128" else QMLB_C64
+    keep = [np.ascontiguousarray(x) for x in (
+        prog.ops, prog.sources, prog.items, prog.angles, prog.terms, prog.consts,
+        obs_recs, obs_pool,
+        prog.pre if prog.pre is not None else np.zeros(0, dtype=compiler.PRE_DTYPE))]
+    d = _Desc(
+        n_qubits=prog.n_qubits, n_bits=prog.n_bits, density=int(prog.density), dtype=dt,
+        out_type=int(out_type), reserved=int(flags),
+        ops=_np_ptr(keep[0]), n_ops=len(keep[0]),
+        sources=_np_ptr(keep[1]), n_sources=len(keep[1]),
+        items=_np_ptr(keep[2]), n_items=len(keep[2]),
+        angles=_np_ptr(keep[3]), n_angles=len(keep[3]),
+        terms=_np_ptr(keep[4]), n_terms=len(keep[4]),
+        consts=_np_ptr(keep[5]), n_consts=len(keep[5]),
+        obs=_np_ptr(keep[6]), n_obs=len(keep[6]),
+        obs_consts=_np_ptr(keep[7]), n_obs_consts=len(keep[7]),
+        pre=_np_ptr(keep[8]), n_pre=len(keep[8]),
+    )
+    return d, keep
+
+
+def plan_describe(lib, prog: Program, out_type: int, obs_recs, obs_pool, precision: str,
+                  flags: int = 0) -> str:
+    """Host-only planning (``qmlb_plan_describe``): no GPU needed."""
+    d, keep = make_desc(prog, out_type, obs_recs, obs_pool, precision, flags)
+    buf = C.create_string_buffer(1 << 22)
+    rc = lib.qmlb_plan_describe(C.byref(d), buf, len(buf))
+    if rc != 0:
+        raise BackendError(f"qmlb_plan_describe: {_ERRORS.get(rc, rc)}: "
+                           f"{lib.qmlb_last_error().decode()}")
+    return buf.value.decode()
 
 
 class ProgramHandle:
@@ -113,23 +151,7 @@ class ProgramHandle:
         self.lib = lib
         self.ptr = C.c_void_p()
         dt = QMLB_C128 if precision == "complex128" else QMLB_C64
-        keep = [np.ascontiguousarray(x) for x in (
-            prog.ops, prog.sources, prog.items, prog.angles, prog.terms, prog.consts,
-            obs_recs, obs_pool,
-            prog.pre if prog.pre is not None else np.zeros(0, dtype=compiler.PRE_DTYPE))]
-        d = _Desc(
-            n_qubits=prog.n_qubits, n_bits=prog.n_bits, density=int(prog.density), dtype=dt,
-            out_type=int(out_type), reserved=int(flags),
-            ops=_np_ptr(keep[0]), n_ops=len(keep[0]),
-            sources=_np_ptr(keep[1]), n_sources=len(keep[1]),
-            items=_np_ptr(keep[2]), n_items=len(keep[2]),
-            angles=_np_ptr(keep[3]), n_angles=len(keep[3]),
-            terms=_np_ptr(keep[4]), n_terms=len(keep[4]),
-            consts=_np_ptr(keep[5]), n_consts=len(keep[5]),
-            obs=_np_ptr(keep[6]), n_obs=len(keep[6]),
-            obs_consts=_np_ptr(keep[7]), n_obs_consts=len(keep[7]),
-            pre=_np_ptr(keep[8]), n_pre=len(keep[8]),
-        )
+        d, keep = make_desc(prog, out_type, obs_recs, obs_pool, precision, flags)
         rc = lib.qmlb_program_create(C.byref(d), C.byref(self.ptr))
         if rc != 0:
             raise BackendError(

@@ -308,6 +308,7 @@ int schedule_stream(qmlb_program* p, int R) {
         o.aux = (int32_t)(uint32_t)(packed >> 32);
       }
       ps.ops.push_back(o);
+      ps.src_index.push_back((int)i);
       done[i] = 1;
     }
     remaining -= picked.size();
@@ -817,15 +818,54 @@ unsigned long long qmlb_launch_count(void) { return g_launches.load(); }
 
 const char* qmlb_last_error(void) { return g_err.c_str(); }
 
+// validate + copy + plan (host only, no CUDA allocation)
+static int build_host_program(const qmlb_program_desc* d, qmlb_program* p);
+
+int qmlb_plan_describe(const qmlb_program_desc* d, char* buf, size_t buflen) {
+  if (!d || !buf || buflen < 2) return fail(QMLB_ERR_INVALID, "null argument");
+  qmlb_program prog;
+  int rc = build_host_program(d, &prog);
+  if (rc != QMLB_OK) return rc;
+  std::string s = "strategy " + std::to_string(prog.strategy) + "\n";
+  if (prog.strategy == 2) {
+    for (const QmlbStreamPassHost& ps : prog.stream_passes) {
+      s += "pass flags " + std::to_string(ps.flags) + " group";
+      for (int j = 0; j < prog.stream_r; ++j) s += " " + std::to_string(ps.gb[j]);
+      s += " ops";
+      for (size_t i = 0; i < ps.ops.size(); ++i) {
+        const qmlb_op& o = ps.ops[i];
+        s += " " + std::to_string(ps.src_index[i]) + ":" + std::to_string(o.kind) + ":";
+        for (int j = 0; j < o.k; ++j) s += (j ? "," : "") + std::to_string(o.bits[j]);
+      }
+      s += "\n";
+    }
+  } else if (prog.strategy == 1) {
+    s += "smem_bytes " + std::to_string(prog.smem) + " teams " + std::to_string(prog.teams) + "\n";
+  }
+  if (s.size() + 1 > buflen) return fail(QMLB_ERR_WORKSPACE, "description buffer too small");
+  std::memcpy(buf, s.c_str(), s.size() + 1);
+  return QMLB_OK;
+}
+
 int qmlb_program_create(const qmlb_program_desc* d, qmlb_program** out) {
   if (!d || !out) return fail(QMLB_ERR_INVALID, "null argument");
   *out = nullptr;
   qmlb_program* p = new qmlb_program();
-  int rc = validate(d, p);
+  int rc = build_host_program(d, p);
+  if (rc == QMLB_OK) rc = upload(p);
+  if (rc == QMLB_OK) rc = set_smem_attr(p);
   if (rc != QMLB_OK) {
+    if (p->blob) cudaFree(p->blob);
     delete p;
     return rc;
   }
+  *out = p;
+  return QMLB_OK;
+}
+
+static int build_host_program(const qmlb_program_desc* d, qmlb_program* p) {
+  int rc = validate(d, p);
+  if (rc != QMLB_OK) return rc;
   p->n_qubits = d->n_qubits;
   p->n_bits = d->n_bits;
   p->density = d->density;
@@ -842,16 +882,7 @@ int qmlb_program_create(const qmlb_program_desc* d, qmlb_program** out) {
   p->obs_consts.assign(d->obs_consts, d->obs_consts + d->n_obs_consts);
   if (d->n_pre > 0) p->pre.assign(d->pre, d->pre + d->n_pre);
   for (int i = 0; i < (int)p->pre.size(); ++i) p->pre_ids[p->pre[i].arg].push_back(i);
-  rc = plan(p);
-  if (rc == QMLB_OK) rc = upload(p);
-  if (rc == QMLB_OK) rc = set_smem_attr(p);
-  if (rc != QMLB_OK) {
-    if (p->blob) cudaFree(p->blob);
-    delete p;
-    return rc;
-  }
-  *out = p;
-  return QMLB_OK;
+  return plan(p);
 }
 
 int qmlb_program_destroy(qmlb_program* p) {

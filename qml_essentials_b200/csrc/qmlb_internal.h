@@ -24,6 +24,7 @@ struct QmlbPassHost {
 struct QmlbStreamPassHost {
   std::vector<qmlb_op> ops;      // register-position bits, packed PERM tables
   std::vector<int32_t> matoff;
+  std::vector<int32_t> src_index;  // index of each op in the program's op list
   int gb[qmlb::STREAM_MAX_R] = {0, 0, 0, 0, 0};
   int sorted[qmlb::STREAM_MAX_R] = {0, 0, 0, 0, 0};
   int flags = 0;

@@ -66,3 +66,111 @@ def test_no_cpu_fallback_without_gpu():
     script._set_executor_for_testing(None)
     with pytest.raises(backend.BackendUnavailable):
         script.Script(lambda: op.H(wires=0), 1).execute("probs")
+
+
+# ---- host-only planning: the streaming pass scheduler, checked without a GPU -------------
+def _plan_of(n, L, ct, precision="complex64", typ="expval", noise=None):
+    import warnings
+
+    import numpy as np
+
+    from qml_essentials_b200.model import Model
+
+    captured = {}
+
+    class Capture:
+        def execute(self, plan, host_args, batch, chunk=None, to_host=True):
+            captured["plan"] = plan
+            raise StopIteration
+
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        m = Model(n, L, ct, precision=precision)
+        m.script.executor = Capture()
+        try:
+            m(params=np.random.default_rng(0).uniform(0, 6, (1, *m._params_shape)),
+              inputs=np.array([[0.3]]), execution_type=typ,
+              noise_params=dict(noise) if noise else None)
+        except StopIteration:
+            pass
+    return captured["plan"]
+
+
+@pytest.mark.parametrize("n,L,ct,precision,noise", [
+    (20, 3, "Hardware_Efficient", "complex64", None),
+    (18, 2, "Circuit_19", "complex128", None),
+    (16, 2, "Strongly_Entangling", "complex64", None),
+    (8, 2, "Strongly_Entangling", "complex128", {"Depolarizing": 0.01, "AmplitudeDamping": 0.02}),
+    (8, 1, "Circuit_6", "complex64", {"BitFlip": 0.1, "MultiQubitDepolarizing": 0.05}),
+])
+def test_stream_scheduler_invariants(lib, n, L, ct, precision, noise):
+    """Every op lands in exactly one pass, inside its group, and never before an earlier
+    op it shares a bit with (qmlb_plan_describe, host only)."""
+    plan = _plan_of(n, L, ct, precision, "expval", noise)
+    prog = plan.program
+    text = backend.plan_describe(lib, prog, plan.out_type, plan.obs_recs, plan.obs_pool,
+                                 precision)
+    lines = text.strip().split("\n")
+    assert lines[0] == "strategy 2"
+    R = 4
+    seen = {}
+    for pi_, line in enumerate(lines[1:]):
+        tok = line.split()
+        assert tok[0] == "pass"
+        gi, oi = tok.index("group"), tok.index("ops")
+        group = [int(x) for x in tok[gi + 1:oi]]
+        assert len(group) == R and len(set(group)) == R
+        assert all(0 <= g < prog.n_bits for g in group)
+        flags = int(tok[2])
+        assert (flags & 1) == (1 if pi_ == 0 else 0)  # only the first pass initialises
+        for ent in tok[oi + 1:]:
+            idx, kind, bits = ent.split(":")
+            idx, kind = int(idx), int(kind)
+            bits = [int(b) for b in bits.split(",")]
+            o = prog.ops[idx]
+            assert idx not in seen and kind == o["kind"]
+            want = [int(b) for b in o["bits"][: o["k"]]]
+            if kind == compiler.OP_DIAG:
+                assert bits == want  # diagonal ops keep state bits
+            else:
+                mapped = [group[b] for b in bits]
+                if kind == compiler.OP_PERM and o["k"] == 2:
+                    assert sorted(mapped) == sorted(want)  # canonical order may swap them
+                else:
+                    assert mapped == want
+            seen[idx] = (pi_, len(seen))
+    assert sorted(seen) == list(range(len(prog.ops)))
+    # dependency order: ops sharing a bit keep their program order
+    last = {}
+    for idx in range(len(prog.ops)):
+        o = prog.ops[idx]
+        for b in o["bits"][: o["k"]]:
+            if int(b) in last:
+                assert seen[last[int(b)]] < seen[idx], (last[int(b)], idx)
+            last[int(b)] = idx
+
+
+def test_plan_strategies_by_size(lib):
+    """n <= 5 -> registers, mid sizes -> shared memory, beyond -> streamed passes; the
+    force flag used by the qubit-sharded path always streams."""
+    for n, want in ((4, 0), (9, 1), (16, 2)):
+        plan = _plan_of(n, 1, "Hardware_Efficient", "complex128")
+        text = backend.plan_describe(lib, plan.program, plan.out_type, plan.obs_recs,
+                                     plan.obs_pool, "complex128")
+        assert text.startswith(f"strategy {want}")
+    plan = _plan_of(9, 1, "Hardware_Efficient", "complex128")
+    text = backend.plan_describe(lib, plan.program, plan.out_type, plan.obs_recs, plan.obs_pool,
+                                 "complex128", flags=backend.QMLB_DESC_FORCE_STREAM)
+    assert text.startswith("strategy 2")
+
+
+def test_plan_rejects_malformed_programs(lib):
+    plan = _plan_of(4, 1, "Hardware_Efficient", "complex128")
+    import copy
+
+    bad = copy.copy(plan.program)
+    bad.ops = plan.program.ops.copy()
+    bad.ops["bits"][0][0] = 99
+    with pytest.raises(backend.BackendError, match="outside the state"):
+        backend.plan_describe(lib, bad, plan.out_type, plan.obs_recs, plan.obs_pool,
+                              "complex128")
