@@ -204,14 +204,106 @@ void make_windows(const qmlb_program* p, QmlbPassHost& ps, int matw) {
 // blocked by an earlier op that had to be left out and the union of group bits
 // stays within R.  Diagonal ops act on global indices and need no group bits.
 // Ops on 3 or 4 bits pin their bits to register positions 0..k-1.
+int schedule_stream_with(qmlb_program* p, int R, bool first_fit);
+
+// Two list schedulers (first-fit in program order; look-ahead group choice) - neither
+// dominates (nearest-neighbour statevector circuits favour look-ahead, the (ket, bra)
+// structure of density programs first-fit), so both run and the shorter schedule wins.
 int schedule_stream(qmlb_program* p, int R) {
+  const int forced = env_int("QMLB_SCHED_GREEDY", -1);
+  if (forced >= 0) return schedule_stream_with(p, R, forced != 0);
+  int rc = schedule_stream_with(p, R, true);
+  if (rc != QMLB_OK) return rc;
+  std::vector<QmlbStreamPassHost> a = std::move(p->stream_passes);
+  p->stream_passes.clear();
+  rc = schedule_stream_with(p, R, false);
+  if (rc != QMLB_OK || a.size() <= p->stream_passes.size()) p->stream_passes = std::move(a);
+  return QMLB_OK;
+}
+
+int schedule_stream_with(qmlb_program* p, int R, bool first_fit) {
   const int N = p->n_bits;
   const int max_entries = 2048;  // matrix buffer entries per pass (<= 32 KB)
   std::vector<char> done(p->ops.size(), 0);
   size_t remaining = p->ops.size();
   bool first_pass = true;
+  const bool pair_rule = p->dtype != QMLB_C128 && N >= R + 2;
+  std::vector<uint64_t> opbits(p->ops.size(), 0);
+  for (size_t i = 0; i < p->ops.size(); ++i)
+    for (int j = 0; j < p->ops[i].k; ++j) opbits[i] |= 1ull << p->ops[i].bits[j];
+  const int look_ahead = env_int("QMLB_SCHED_WINDOW", 600);
+  const int max_seeds = env_int("QMLB_SCHED_SEEDS", 64);
+
+  // ops (within the look-ahead window) that could run in a pass owning exactly group G
+  auto closure_count = [&](uint64_t G) {
+    uint64_t blk = 0;
+    int count = 0, seen = 0;
+    for (size_t i = 0; i < p->ops.size() && seen < look_ahead; ++i) {
+      if (done[i]) continue;
+      ++seen;
+      const uint64_t b = opbits[i];
+      if (b & blk) {
+        blk |= b;
+        continue;
+      }
+      if (p->ops[i].kind == QMLB_OP_DIAG || (b & ~G) == 0) {
+        count += p->ops[i].kind == QMLB_OP_PERM ? 2 : 3;  // arithmetic ops weigh a bit more
+      } else {
+        blk |= b;
+      }
+    }
+    return count;
+  };
+  auto normalise = [&](uint64_t G) {
+    if (pair_rule && (G & 2ull) && !(G & 1ull)) G |= 1ull;
+    return G;
+  };
+  // Group choice: from every ready op, grow the group one bit at a time by the bit that
+  // unlocks the most work; keep the best.  (First-fit in program order - the previous
+  // scheduler - strands neighbouring qubits in different passes.)
+  auto choose_group = [&]() -> uint64_t {
+    uint64_t cand_bits = 0, blk = 0, best = 0;
+    int best_score = -1, seeds = 0, seen = 0;
+    std::vector<size_t> ready;
+    for (size_t i = 0; i < p->ops.size() && seen < look_ahead; ++i) {
+      if (done[i]) continue;
+      ++seen;
+      cand_bits |= opbits[i];
+      if (!(opbits[i] & blk) && p->ops[i].kind != QMLB_OP_DIAG) ready.push_back(i);
+      blk |= opbits[i];
+    }
+    for (size_t i : ready) {
+      if (seeds++ >= max_seeds) break;
+      uint64_t G = normalise(opbits[i]);
+      if (__builtin_popcountll(G) > R) continue;
+      while (__builtin_popcountll(G) < R) {
+        uint64_t pick = 0;
+        int pick_score = -1;
+        for (int b = 0; b < N; ++b) {
+          if (!(cand_bits >> b & 1) || (G >> b & 1)) continue;
+          const uint64_t G2 = normalise(G | (1ull << b));
+          if (__builtin_popcountll(G2) > R) continue;
+          const int sc = closure_count(G2);
+          if (sc > pick_score) {
+            pick_score = sc;
+            pick = G2;
+          }
+        }
+        if (!pick) break;
+        G = pick;
+      }
+      const int sc = closure_count(G);
+      if (sc > best_score) {
+        best_score = sc;
+        best = G;
+      }
+    }
+    return best;
+  };
+
   while (remaining > 0 || first_pass) {
-    uint64_t S = 0, blocked = 0;
+    uint64_t S = first_fit ? 0 : choose_group(), blocked = 0;
+    const bool fixed_group = __builtin_popcountll(S) == R;
     std::vector<int> canon;  // ordered: register position j -> state bit (k >= 3 op)
     std::vector<size_t> picked;
     int entries = 0;
@@ -225,9 +317,10 @@ int schedule_stream(qmlb_program* p, int R) {
       // 16-byte pairs (bit 0 alone is fine: lanes then cover consecutive pairs).  complex128
       // amplitudes are 16 bytes already.
       uint64_t grp = bits;
-      if (o.kind != QMLB_OP_DIAG && p->dtype != QMLB_C128 && (bits & 2ull) && N >= R + 2 &&
+      if (o.kind != QMLB_OP_DIAG && pair_rule && (bits & 2ull) &&
           __builtin_popcountll(bits | 1ull) <= R)
         grp |= 1ull;
+      (void)fixed_group;
       const int e = op_entries(p, o);
       if ((bits & blocked) || entries + e > max_entries ||
           (int)picked.size() >= STREAM_MAX_OPS) {
