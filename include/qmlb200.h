@@ -188,7 +188,8 @@ int qmlb_program_destroy(qmlb_program* prog);
 int qmlb_plan_describe(const qmlb_program_desc* desc, char* buf, size_t buflen);
 
 /* strategy: 0 = register-resident (one thread per circuit), 1 = shared-memory
- * resident (one warp / CTA per circuit), 2 = streamed tile passes over HBM.
+ * resident (one warp / CTA per circuit), 2 = streamed fused gate passes over HBM
+ * (register groups of 4 state bits, one launch per pass).
  * n_passes: state passes per run (strategy 2), n_device_ops: ops after fusion. */
 int qmlb_program_info(const qmlb_program* prog, int32_t* strategy, int32_t* n_passes,
                       int32_t* n_device_ops);
