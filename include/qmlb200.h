@@ -221,6 +221,18 @@ int qmlb_evolve(const qmlb_program* prog, const qmlb_arg* args, int32_t n_args, 
                 int64_t batch_offset, void* state, int32_t init_mode, void* workspace,
                 size_t workspace_bytes, void* stream);
 
+/* The fused form of "exchange, then evolve": the FIRST gate pass of the epoch reads every
+ * amplitude of the post-swap layout directly from the peer GPU that holds it (NVLink
+ * peer loads issued by the gate-pass kernel itself) and writes `dst_state`; the
+ * remaining passes run in place on `dst_state`.  peer_src[s] is the address, valid in
+ * this process, of rank s's pre-swap shard (peer_src[rank] is this rank's own);
+ * n_peers = 2, 4 or 8.  The swap exchanges the top log2(n_peers) local bits with the
+ * rank-index bits.  The caller orders the ranks (every rank must have finished writing
+ * its pre-swap shard, and `dst_state` must not be a buffer peers still read). */
+int qmlb_evolve_peer(const qmlb_program* prog, const qmlb_arg* args, int32_t n_args,
+                     void* dst_state, const void* const* peer_src, int32_t n_peers,
+                     int32_t rank, void* workspace, size_t workspace_bytes, void* stream);
+
 /* One sweep over pure states: out[b][q] = sum of |amp|^2 over indices with bit q set
  * (q < n_bits), out[b][32] = total probability; double, (batch, 33).  <Z> of the qubit
  * on bit q is out[32] - 2 out[q]; a sharded state adds the per-rank tables (and `total`

@@ -32,6 +32,7 @@ EXPORTED_SYMBOLS = (
     "qmlb_program_destroy", "qmlb_program_info", "qmlb_workspace_bytes", "qmlb_run",
     "qmlb_sample", "qmlb_purity", "qmlb_overlap_fidelity", "qmlb_fma_peak",
     "qmlb_evolve", "qmlb_zsums", "qmlb_zsums_workspace_bytes", "qmlb_plan_describe",
+    "qmlb_evolve_peer",
 )
 QMLB_DESC_FORCE_STREAM = 1
 
@@ -96,6 +97,9 @@ def load_library(path: str = LIB_PATH) -> C.CDLL:
                                 C.c_void_p, C.c_int32, C.c_void_p, C.c_size_t, C.c_void_p]
     lib.qmlb_zsums_workspace_bytes.argtypes = [C.c_int64, C.c_int32]
     lib.qmlb_zsums_workspace_bytes.restype = C.c_size_t
+    lib.qmlb_evolve_peer.argtypes = [C.c_void_p, C.POINTER(_Arg), C.c_int32, C.c_void_p,
+                                     C.POINTER(C.c_void_p), C.c_int32, C.c_int32, C.c_void_p,
+                                     C.c_size_t, C.c_void_p]
     lib.qmlb_plan_describe.argtypes = [C.POINTER(_Desc), C.c_char_p, C.c_size_t]
     lib.qmlb_zsums.argtypes = [C.c_void_p, C.c_int, C.c_int64, C.c_int32, C.c_void_p,
                                C.c_void_p, C.c_size_t, C.c_void_p]

@@ -819,7 +819,7 @@ int prepare_tables(const qmlb_program* p, RunArgs& R, void* workspace, size_t ws
 // the streamed gate passes over `state`; init_mode 1: |0..0>, 2: zero vector, 0: continue
 template <typename T>
 int evolve_stream(const qmlb_program* p, const RunArgs& R, void* state, int init_mode,
-                  void* premats, cudaStream_t st) {
+                  void* premats, cudaStream_t st, const StreamPeers* peers = nullptr) {
   if (premats)
     CUDA_TRY((std::is_same<T, double>::value ? launch_stream_mats_f64 : launch_stream_mats_f32)(
         p, R, premats, st));
@@ -845,7 +845,8 @@ int evolve_stream(const qmlb_program* p, const RunArgs& R, void* state, int init
       if (init_mode == 2) pass.flags |= QMLB_PASS_INIT_ZERO;
     }
     CUDA_TRY((std::is_same<T, double>::value ? launch_stream_f64 : launch_stream_f32)(
-        p, R, pass, grid, state, premats, st));
+        p, R, pass, grid, state, premats, peers, st));
+    peers = nullptr;  // only the first pass of the epoch pulls from the peers
   }
   return QMLB_OK;
 }
@@ -1052,6 +1053,41 @@ int qmlb_evolve(const qmlb_program* p, const qmlb_arg* args, int32_t n_args, int
   }
   rc = prepare_tables<float>(p, R, workspace, workspace_bytes, st, &tab);
   return rc != QMLB_OK ? rc : evolve_stream<float>(p, R, state, init_mode, nullptr, st);
+}
+
+int qmlb_evolve_peer(const qmlb_program* p, const qmlb_arg* args, int32_t n_args, void* dst_state,
+                     const void* const* peer_src, int32_t n_peers, int32_t rank,
+                     void* workspace, size_t workspace_bytes, void* stream) {
+  if (!p || !dst_state || !peer_src) return fail(QMLB_ERR_INVALID, "null argument");
+  if (p->strategy != 2)
+    return fail(QMLB_ERR_INVALID, "qmlb_evolve_peer needs a streaming program");
+  if (n_peers < 2 || n_peers > 8 || (n_peers & (n_peers - 1)) || rank < 0 || rank >= n_peers)
+    return fail(QMLB_ERR_INVALID, "peer count must be 2, 4 or 8 and rank inside it");
+  int g = 0;
+  while ((1 << g) < n_peers) ++g;
+  if (p->n_bits < 2 * g || p->n_bits - g < 1)
+    return fail(QMLB_ERR_INVALID, "shard too small for the exchange");
+  if (p->stream_passes.empty() || (p->stream_passes[0].ops.empty()))
+    return fail(QMLB_ERR_INVALID, "epoch without operations");
+  RunArgs R;
+  int rc = fill_run_args(p, args, n_args, 1, 0, R);
+  if (rc != QMLB_OK) return rc;
+  StreamPeers peers{};
+  for (int i = 0; i < n_peers; ++i) {
+    if (!peer_src[i]) return fail(QMLB_ERR_INVALID, "null peer pointer");
+    peers.ptr[i] = peer_src[i];
+  }
+  peers.enabled = 1;
+  peers.cshift = p->n_bits - g;
+  peers.rank = rank;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  size_t tab = 0;
+  if (p->dtype == QMLB_C128) {
+    rc = prepare_tables<double>(p, R, workspace, workspace_bytes, st, &tab);
+    return rc != QMLB_OK ? rc : evolve_stream<double>(p, R, dst_state, 0, nullptr, st, &peers);
+  }
+  rc = prepare_tables<float>(p, R, workspace, workspace_bytes, st, &tab);
+  return rc != QMLB_OK ? rc : evolve_stream<float>(p, R, dst_state, 0, nullptr, st, &peers);
 }
 
 size_t qmlb_zsums_workspace_bytes(int64_t batch, int32_t n_bits) {

@@ -81,9 +81,11 @@ cudaError_t launch_tile_f32(const qmlb_program* p, const RunArgs& R, const PassD
 cudaError_t launch_tile_f64(const qmlb_program* p, const RunArgs& R, const PassDev& pass,
                             unsigned grid, void* state, cudaStream_t st);
 cudaError_t launch_stream_f32(const qmlb_program* p, const RunArgs& R, const StreamPass& pass,
-                              dim3 grid, void* state, const void* premats, cudaStream_t st);
+                              dim3 grid, void* state, const void* premats,
+                              const StreamPeers* peers, cudaStream_t st);
 cudaError_t launch_stream_f64(const qmlb_program* p, const RunArgs& R, const StreamPass& pass,
-                              dim3 grid, void* state, const void* premats, cudaStream_t st);
+                              dim3 grid, void* state, const void* premats,
+                              const StreamPeers* peers, cudaStream_t st);
 cudaError_t launch_stream_mats_f32(const qmlb_program* p, const RunArgs& R, void* out,
                                    cudaStream_t st);
 cudaError_t launch_stream_mats_f64(const qmlb_program* p, const RunArgs& R, void* out,

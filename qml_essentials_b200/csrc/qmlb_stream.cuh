@@ -249,7 +249,8 @@ __global__ void k_stream_mats(DevProg P, RunArgs A, const StreamMatOp* __restric
 template <typename T, int R, bool HEAVY, typename IDX>
 __global__ void __launch_bounds__(STREAM_THREADS, HEAVY ? 1 : (sizeof(T) == 4 ? 4 : STREAM_MIN_CTAS))
     k_stream(DevProg P, RunArgs A, const __grid_constant__ StreamPass pass,
-             cx<T>* __restrict__ gstate, const cx<T>* __restrict__ premats) {
+             cx<T>* __restrict__ gstate, const cx<T>* __restrict__ premats,
+             const StreamPeers peers) {
   constexpr int D = 1 << R;
   // complex64: amplitudes v and v^1 are moved as one 16-byte access when register bit 0
   // is state bit 0 (the scheduler then also puts state bit 1 at register bit 1, so a
@@ -319,6 +320,15 @@ __global__ void __launch_bounds__(STREAM_THREADS, HEAVY ? 1 : (sizeof(T) == 4 ? 
     // with cp.async (LDGSTS, no registers held, thread-private slots so no barrier) while
     // the current item is in the arithmetic; with ~12 resident warps per SM that is what
     // keeps HBM requests in flight during the compute phase.
+    // where amplitude idx is read from: this GPU's state, or (fused exchange) the peer
+    // that holds it before the global<->local swap
+    auto src_of = [&](IDX idx) -> const cx<T>* {
+      if (!peers.enabled) return gs + idx;
+      const IDX chunk = idx >> peers.cshift;
+      const IDX within = idx & (((IDX)1 << peers.cshift) - (IDX)1);
+      return static_cast<const cx<T>*>(peers.ptr[chunk]) +
+             (((IDX)peers.rank << peers.cshift) | within);
+    };
     auto prefetch = [&](IDX w, int stage) {
       if (w < items && !init_pass) {
         const IDX base = base_of(w);
@@ -329,12 +339,12 @@ __global__ void __launch_bounds__(STREAM_THREADS, HEAVY ? 1 : (sizeof(T) == 4 ? 
                             (size_t)stage * (D / 2) * STREAM_THREADS + threadIdx.x;
 #pragma unroll
             for (int v = 0; v < D; v += 2)
-              cp_async16(slot4 + (v >> 1) * STREAM_THREADS, gs + (base | offv(v)));
+              cp_async16(slot4 + (v >> 1) * STREAM_THREADS, src_of(base | offv(v)));
           }
         } else {
 #pragma unroll
           for (int v = 0; v < D; ++v)
-            cp_async_elem<T>(slot + v * STREAM_THREADS, gs + (base | offv(v)));
+            cp_async_elem<T>(slot + v * STREAM_THREADS, src_of(base | offv(v)));
         }
       }
       cp_async_commit();

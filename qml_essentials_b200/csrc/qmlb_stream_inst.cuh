@@ -6,14 +6,15 @@ namespace qmlb {
 
 template <bool HEAVY, typename IDX>
 static void launch_v(const qmlb_program* p, const RunArgs& R, const StreamPass& pass, dim3 grid,
-                     cx<QMLB_T>* s, const cx<QMLB_T>* premats, size_t smem, cudaStream_t st) {
+                     cx<QMLB_T>* s, const cx<QMLB_T>* premats, const StreamPeers& peers,
+                     size_t smem, cudaStream_t st) {
   static bool attr_set = false;  // > 48 KB of dynamic shared memory needs the opt-in (once)
   if (!attr_set) {
     cudaFuncSetAttribute(k_stream<QMLB_T, QMLB_STREAM_R, HEAVY, IDX>,
                          cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
     attr_set = true;
   }
-  k_stream<QMLB_T, QMLB_STREAM_R, HEAVY, IDX><<<grid, STREAM_THREADS, smem, st>>>(p->dev, R, pass, s, premats);
+  k_stream<QMLB_T, QMLB_STREAM_R, HEAVY, IDX><<<grid, STREAM_THREADS, smem, st>>>(p->dev, R, pass, s, premats, peers);
 }
 
 cudaError_t QMLB_LAUNCH_STREAM_MATS(const qmlb_program* p, const RunArgs& R, void* out,
@@ -28,7 +29,10 @@ cudaError_t QMLB_LAUNCH_STREAM_MATS(const qmlb_program* p, const RunArgs& R, voi
 }
 
 cudaError_t QMLB_LAUNCH_STREAM(const qmlb_program* p, const RunArgs& R, const StreamPass& pass,
-                               dim3 grid, void* state, const void* premats_v, cudaStream_t st) {
+                               dim3 grid, void* state, const void* premats_v,
+                               const StreamPeers* peers_in, cudaStream_t st) {
+  StreamPeers peers{};
+  if (peers_in) peers = *peers_in;
   cx<QMLB_T>* s = static_cast<cx<QMLB_T>*>(state);
   const cx<QMLB_T>* premats = static_cast<const cx<QMLB_T>*>(premats_v);
   g_launches.fetch_add(1, std::memory_order_relaxed);
@@ -36,10 +40,10 @@ cudaError_t QMLB_LAUNCH_STREAM(const qmlb_program* p, const RunArgs& R, const St
                       sizeof(cx<QMLB_T>);
   const bool heavy = pass.flags & QMLB_PASS_HEAVY;
   const bool narrow = pass.n_bits <= 32;  // element-relative indices
-  if (heavy && narrow) launch_v<true, uint32_t>(p, R, pass, grid, s, premats, smem, st);
-  else if (heavy) launch_v<true, uint64_t>(p, R, pass, grid, s, premats, smem, st);
-  else if (narrow) launch_v<false, uint32_t>(p, R, pass, grid, s, premats, smem, st);
-  else launch_v<false, uint64_t>(p, R, pass, grid, s, premats, smem, st);
+  if (heavy && narrow) launch_v<true, uint32_t>(p, R, pass, grid, s, premats, peers, smem, st);
+  else if (heavy) launch_v<true, uint64_t>(p, R, pass, grid, s, premats, peers, smem, st);
+  else if (narrow) launch_v<false, uint32_t>(p, R, pass, grid, s, premats, peers, smem, st);
+  else launch_v<false, uint64_t>(p, R, pass, grid, s, premats, peers, smem, st);
   return cudaGetLastError();
 }
 

@@ -21,6 +21,19 @@ struct StreamOp {
   uint64_t data;            // PERM: table packed k bits/entry; DIAG: global bits, 6 bits each
 };
 
+// Fused global<->local qubit swap (qubit-sharded statevector): when enabled, the pass
+// READS amplitude idx of the new local layout straight from the peer GPU that holds it
+// (NVLink P2P loads through cp.async) and writes its own buffer - the exchange costs no
+// HBM round trip of its own and overlaps with the arithmetic.  Chunk s = idx >> cshift
+// lives on rank s at its chunk `rank`.
+struct StreamPeers {
+  const void* ptr[8];
+  int32_t enabled;
+  int32_t cshift;   // log2(amplitudes per chunk) = local bits - log2(ranks)
+  int32_t rank;
+  int32_t pad;
+};
+
 // one matrix of the per-element table filled by k_stream_mats (batched runs)
 struct StreamMatOp {
   int32_t src;    // matrix source

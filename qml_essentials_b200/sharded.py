@@ -123,14 +123,45 @@ def epoch_program(prog: Program, ops: np.ndarray, consts: np.ndarray, nl: int) -
 
 # ---------------------------------------------------------------------------------------
 class CudaShardEngine:
-    """Shard-local work through the C ABI; exchange through torch.distributed (NCCL)."""
+    """Shard-local work through the C ABI.
 
-    def __init__(self, executor=None):
+    Exchange, two forms:
+
+    * fused (default when torch symmetric memory can map the peers' shards): the shard
+      lives in two symmetric buffers; after a device-side barrier the first gate pass of
+      the next epoch reads its amplitudes straight from the peers over NVLink
+      (``qmlb_evolve_peer``) and writes the other buffer - no separate exchange step, no
+      extra HBM round trip, transfer overlapped with the arithmetic;
+    * NCCL ``all_to_all_single`` into a second buffer, then the epoch in place (fallback,
+      and the reference point for the fused form).
+    """
+
+    def __init__(self, executor=None, fused: Optional[bool] = None):
         from . import script
 
         self.ex = executor or script.get_executor()
         self.torch = self.ex.torch
         self.lib = self.ex.lib
+        self.want_fused = fused
+        self.fused_exchange = False
+        self._symm = {}   # (nl, precision) -> (buffers, handles)
+        self._cur = None  # (key, index of the buffer that holds the state)
+
+    def _symmetric_buffers(self, nl: int, precision: str):
+        key = (nl, precision)
+        if key in self._symm:
+            return self._symm[key]
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm
+
+        real = self.torch.float64 if precision == "complex128" else self.torch.float32
+        bufs, hdls = [], []
+        for _ in range(2):
+            t = symm.empty(2 * 2 ** nl, dtype=real, device=self.ex.device)
+            hdls.append(symm.rendezvous(t, dist.group.WORLD))
+            bufs.append(self.torch.view_as_complex(t.view(-1, 2)))
+        self._symm[key] = (bufs, hdls)
+        return self._symm[key]
 
     def make(self, prog: Program, precision: str):
         from .backend import QMLB_DESC_FORCE_STREAM, ProgramHandle
@@ -142,8 +173,42 @@ class CudaShardEngine:
                                  flags=QMLB_DESC_FORCE_STREAM)
 
     def alloc(self, nl: int, precision: str):
+        if self.want_fused is not False and parallel.world()[1] in (2, 4, 8):
+            try:
+                bufs, _ = self._symmetric_buffers(nl, precision)
+                self.fused_exchange = True
+                self._cur = ((nl, precision), 0)
+                return bufs[0]
+            except Exception as exc:  # noqa: BLE001
+                if self.want_fused:
+                    raise
+                import logging
+
+                logging.getLogger(__name__).info(
+                    "symmetric memory unavailable (%s); exchanging through NCCL", exc)
+        self.fused_exchange = False
         dt = self.torch.complex128 if precision == "complex128" else self.torch.complex64
         return self.torch.empty(2 ** nl, dtype=dt, device=self.ex.device)
+
+    def exchange_evolve(self, handle, staged, state):
+        """Fused global<->local swap + first epoch pass (+ the rest of the epoch)."""
+        key, cur = self._cur
+        bufs, hdls = self._symm[key]
+        rank, size = parallel.world()
+        hdls[cur].barrier()  # device side, stream ordered: every rank finished writing `cur`
+        dst = bufs[1 - cur]
+        dev, c_args, n = staged
+        ptrs = (C.c_void_p * size)(*[int(p) for p in hdls[cur].buffer_ptrs])
+        ws = self.torch.empty(1 << 20, dtype=self.torch.uint8, device=self.ex.device)
+        rc = self.lib.qmlb_evolve_peer(
+            handle.ptr, c_args, n, dst.data_ptr(), ptrs, size, rank, ws.data_ptr(), ws.numel(),
+            self.torch.cuda.current_stream(self.ex.device).cuda_stream)
+        if rc != 0:
+            from .backend import BackendError
+
+            raise BackendError(f"qmlb_evolve_peer: {self.lib.qmlb_last_error().decode()}")
+        self._cur = (key, 1 - cur)
+        return dst
 
     def stage_args(self, host_args):
         from .backend import _Arg
@@ -250,7 +315,19 @@ class ShardedExecutor:
         first, n_exchange, n_epochs = True, 0, 0
         t_ex = 0.0
         timed = getattr(eng, "sync", None)
-        for kind, handle in compiled:
+        fused = bool(getattr(eng, "fused_exchange", False))
+        skip = False
+        for idx, (kind, handle) in enumerate(compiled):
+            if skip:
+                skip = False
+                continue
+            if kind == "exchange" and fused and idx + 1 < len(compiled) \
+                    and compiled[idx + 1][0] == "ops":
+                state = eng.exchange_evolve(compiled[idx + 1][1], staged, state)
+                n_exchange += 1
+                n_epochs += 1
+                skip = True
+                continue
             if kind == "exchange":
                 if timed:
                     timed()
@@ -266,7 +343,9 @@ class ShardedExecutor:
             first = False
             n_epochs += 1
         self.stats = {"exchanges": n_exchange, "epochs": n_epochs, "local_bits": nl,
-                      "ranks": size, "exchange_seconds": t_ex, "bytes_sent_per_exchange":
+                      "ranks": size, "exchange_seconds": t_ex,
+                      "exchange": "fused peer loads (qmlb_evolve_peer)" if fused
+                      else "all_to_all_single", "bytes_sent_per_exchange":
                       (size - 1) * (2 ** nl // size) * (16 if plan.precision == "complex128"
                                                         else 8)}
 
