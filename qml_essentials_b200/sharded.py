@@ -172,8 +172,25 @@ class CudaShardEngine:
                                  np.zeros(0, dtype=np.float64), precision,
                                  flags=QMLB_DESC_FORCE_STREAM)
 
+    def _use_fused(self) -> bool:
+        """Measured (profiles/r1_qubit_sharded_fused_vs_nccl_*): with 2 ranks the fused
+        form is 14 % faster end to end (n = 31); with 4 ranks, where 3/4 of the first
+        pass' reads are remote, it is 8 % slower than all_to_all + local pass (n = 32) -
+        the gate-pass kernel reaches only ~360 GB/s of peer reads.  Until that is fixed
+        the fused form is the default for 2 ranks and opt-in (QMLB_SHARD_FUSED=1 or
+        ``fused=True``) beyond."""
+        import os
+
+        size = parallel.world()[1]
+        if self.want_fused is not None:
+            return bool(self.want_fused) and size in (2, 4, 8)
+        env = os.environ.get("QMLB_SHARD_FUSED")
+        if env is not None:
+            return env not in ("0", "") and size in (2, 4, 8)
+        return size == 2
+
     def alloc(self, nl: int, precision: str):
-        if self.want_fused is not False and parallel.world()[1] in (2, 4, 8):
+        if self._use_fused():
             try:
                 bufs, _ = self._symmetric_buffers(nl, precision)
                 self.fused_exchange = True
