@@ -457,7 +457,11 @@ def main():
                 "bound": "fp64_fma" if prec64 else "fp32_fma",
                 "kernel": f"k_reg<{'double' if prec64 else 'float'},4>",
                 "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
-                "frac": achieved_tf / peak_tf, "traffic": None,
+                "frac": achieved_tf / peak_tf,
+                # dram__bytes_read.sum + dram__bytes_write.sum per launch from the ncu --set full
+                # capture of this kernel (profiles/r1_kreg_f64_n4_v2_hoist_full_summary.txt):
+                # parameters + hoisted tables in, the 8.6 MB of results still in L2
+                "traffic": 1676800 if prec64 else None,
                 "kernel_ms": kern_ms,
                 "note": "achieved = algorithmic (unfused, dense) 26624 flop/eval x 270336 "
                         "evals / CUDA-event launch time; peak = qmlb_fma_peak measured on "

@@ -36,6 +36,31 @@ struct RegState<float, N> {
   __device__ __forceinline__ float& im(int k) { return (k & 1) ? i2[k >> 1].y : i2[k >> 1].x; }
 };
 
+// Exchange two state registers IN PLACE.  Written as opaque asm with read-write operands
+// on purpose: a C++ swap is pure renaming for the compiler, and because every op variant
+// sits in its own branch of the dispatch, each variant then ends with a different
+// value->register map and the merge points pay for it by copying the whole state (ncu:
+// 200-300 moves per CX plus 64 per loop iteration, half of all instructions).  With the
+// swap done physically every branch leaves the state where it found it.
+__device__ __forceinline__ void swap_in_place(double& a, double& b) {
+  // three XORs on the bit patterns: real ALU work for ptxas (a mov-based swap is folded
+  // back into renaming by its copy propagation)
+  long long x = __double_as_longlong(a), y = __double_as_longlong(b);
+  asm volatile("xor.b64 %0, %0, %1;" : "+l"(x) : "l"(y));
+  asm volatile("xor.b64 %0, %0, %1;" : "+l"(y) : "l"(x));
+  asm volatile("xor.b64 %0, %0, %1;" : "+l"(x) : "l"(y));
+  a = __longlong_as_double(x);
+  b = __longlong_as_double(y);
+}
+__device__ __forceinline__ void swap_in_place(float& a, float& b) {
+  int x = __float_as_int(a), y = __float_as_int(b);
+  asm volatile("xor.b32 %0, %0, %1;" : "+r"(x) : "r"(y));
+  asm volatile("xor.b32 %0, %0, %1;" : "+r"(y) : "r"(x));
+  asm volatile("xor.b32 %0, %0, %1;" : "+r"(x) : "r"(y));
+  a = __int_as_float(x);
+  b = __int_as_float(y);
+}
+
 template <int N, int BIT>
 __device__ __forceinline__ constexpr int pair_i0(int g) {
   return ((g >> BIT) << (BIT + 1)) | (g & ((1 << BIT) - 1));
@@ -118,17 +143,29 @@ __device__ __forceinline__ void reg_ctrl1(RegState<T, N>& S, const cx<T> (&m)[4]
 }
 
 // CX: swap the target pair where the control bit is set (pure register moves)
-template <typename T, int N, int CB, int TB>
+// INPLACE: exchange the registers physically (k_reg: measured 0.313 -> 0.289 ms on config 2,
+// the merge-point copies disappear); the streaming kernel keeps the renaming form (its
+// passes are short, and there the XOR form measured 17 % slower).
+template <typename T>
+__device__ __forceinline__ void swap_renamed(T& a, T& b) {
+  const T t = a;
+  a = b;
+  b = t;
+}
+
+template <typename T, int N, int CB, int TB, bool INPLACE = false>
 __device__ __forceinline__ void reg_cx(RegState<T, N>& S) {
 #pragma unroll
   for (int g = 0; g < (1 << (N - 1)); ++g) {
     const int i0 = pair_i0<N, TB>(g), i1 = i0 | (1 << TB);
     if (i0 & (1 << CB)) {
-      const T r = S.re(i0), q = S.im(i0);
-      S.re(i0) = S.re(i1);
-      S.im(i0) = S.im(i1);
-      S.re(i1) = r;
-      S.im(i1) = q;
+      if constexpr (INPLACE) {
+        swap_in_place(S.re(i0), S.re(i1));
+        swap_in_place(S.im(i0), S.im(i1));
+      } else {
+        swap_renamed(S.re(i0), S.re(i1));
+        swap_renamed(S.im(i0), S.im(i1));
+      }
     }
   }
 }
@@ -274,11 +311,8 @@ __global__ void __launch_bounds__(128, reg_min_ctas<T, N>()) k_reg(DevProg P, Ru
 #pragma unroll
           for (int g = 0; g < (1 << (N - 1)); ++g) {
             const int i0 = pair_i0<N, BIT>(g), i1 = i0 | (1 << BIT);
-            const T r = S.re(i0), q = S.im(i0);
-            S.re(i0) = S.re(i1);
-            S.im(i0) = S.im(i1);
-            S.re(i1) = r;
-            S.im(i1) = q;
+            swap_in_place(S.re(i0), S.re(i1));
+            swap_in_place(S.im(i0), S.im(i1));
           }
         });
       } else {
@@ -286,7 +320,7 @@ __global__ void __launch_bounds__(128, reg_min_ctas<T, N>()) k_reg(DevProg P, Ru
         const bool c0 = (int)P.consts[op.aux + 1] == 1;
         const int cb = c0 ? op.bits[0] : op.bits[1], tb = c0 ? op.bits[1] : op.bits[0];
         dispatch2<T, N>(cb, tb, [&](auto CB, auto TB) {
-          reg_cx<T, N, decltype(CB)::value, decltype(TB)::value>(S);
+          reg_cx<T, N, decltype(CB)::value, decltype(TB)::value, true>(S);
         });
       }
       continue;

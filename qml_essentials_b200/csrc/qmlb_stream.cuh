@@ -425,11 +425,8 @@ __global__ void __launch_bounds__(STREAM_THREADS, HEAVY ? 1 : (sizeof(T) == 4 ? 
 #pragma unroll
                 for (int g = 0; g < (1 << (R - 1)); ++g) {
                   const int i0 = pair_i0<R, BIT>(g), i1 = i0 | (1 << BIT);
-                  const T r = S.re(i0), q = S.im(i0);
-                  S.re(i0) = S.re(i1);
-                  S.im(i0) = S.im(i1);
-                  S.re(i1) = r;
-                  S.im(i1) = q;
+                  swap_renamed(S.re(i0), S.re(i1));
+                  swap_renamed(S.im(i0), S.im(i1));
                 }
               });
             } else if (op.k == 2) {

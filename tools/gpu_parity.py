@@ -8,10 +8,7 @@ import time
 sys.path.insert(0, os.path.join(os.path.dirname(__file__), "..", "tests"))
 sys.path.insert(0, os.path.join(os.path.dirname(__file__), ".."))
 if len(sys.argv) > 1:
-    os.environ["QMLB_FORCE_STRATEGY"] = sys.argv[1]
-    if sys.argv[1] == "2":
-        os.environ.setdefault("QMLB_TILE_BITS", "6")
-        os.environ.setdefault("QMLB_TILE_LOW_BITS", "2")
+    os.environ["QMLB_FORCE_STRATEGY"] = sys.argv[1]  # 0 registers, 1 shared memory, 2 streamed
 import parity_cases as pc  # noqa: E402
 
 out = {}
