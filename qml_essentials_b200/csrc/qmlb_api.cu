@@ -227,7 +227,7 @@ int schedule_stream_with(qmlb_program* p, int R, bool first_fit) {
   std::vector<char> done(p->ops.size(), 0);
   size_t remaining = p->ops.size();
   bool first_pass = true;
-  const bool pair_rule = p->dtype != QMLB_C128 && N >= R + 2;
+  const bool pair_rule = p->dtype != QMLB_C128 && N >= R + 2 && env_int("QMLB_PAIR_RULE", 1);
   std::vector<uint64_t> opbits(p->ops.size(), 0);
   for (size_t i = 0; i < p->ops.size(); ++i)
     for (int j = 0; j < p->ops[i].k; ++j) opbits[i] |= 1ull << p->ops[i].bits[j];
