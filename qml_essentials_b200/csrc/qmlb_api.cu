@@ -227,7 +227,7 @@ int schedule_stream_with(qmlb_program* p, int R, bool first_fit) {
   std::vector<char> done(p->ops.size(), 0);
   size_t remaining = p->ops.size();
   bool first_pass = true;
-  const bool pair_rule = p->dtype != QMLB_C128 && N >= R + 2 && env_int("QMLB_PAIR_RULE", 1);
+  const bool pair_rule = p->dtype != QMLB_C128 && N >= R + 2 && env_int("QMLB_PAIR_RULE", 0);
   std::vector<uint64_t> opbits(p->ops.size(), 0);
   for (size_t i = 0; i < p->ops.size(); ++i)
     for (int j = 0; j < p->ops[i].k; ++j) opbits[i] |= 1ull << p->ops[i].bits[j];
@@ -312,10 +312,11 @@ int schedule_stream_with(qmlb_program* p, int R, bool first_fit) {
       const qmlb_op& o = p->ops[i];
       uint64_t bits = 0;
       for (int j = 0; j < o.k; ++j) bits |= 1ull << o.bits[j];
-      // complex64: a group that holds state bit 1 but not bit 0 would touch only every
-      // other 8 bytes of each line; bringing bit 0 along makes the thread move whole
-      // 16-byte pairs (bit 0 alone is fine: lanes then cover consecutive pairs).  complex128
-      // amplitudes are 16 bytes already.
+      // complex64, optional (QMLB_PAIR_RULE=1): a group that holds state bit 1 but not bit 0
+      // touches every other 8 bytes of each line; bringing bit 0 along makes the thread move
+      // whole 16-byte pairs.  Measured (profiles/r1_final_probe*.jsonl): the extra group bit
+      // costs more passes than the wider accesses save (config 4 complex64: 90 vs 60
+      // passes, 38 k vs 49 k evals/s), so the rule is off by default.
       uint64_t grp = bits;
       if (o.kind != QMLB_OP_DIAG && pair_rule && (bits & 2ull) &&
           __builtin_popcountll(bits | 1ull) <= R)
