@@ -275,6 +275,11 @@ __global__ void __launch_bounds__(STREAM_THREADS, HEAVY ? 1 : (sizeof(T) == 4 ? 
     return o;
   };
   const bool paired = CAN_PAIR && pass.gb[0] == 0;
+  // element offsets of the 2^R group members: uniform for the whole launch, computed once;
+  // an amplitude address is then (state + base) + eoff[v] - one wide multiply-add
+  IDX eoff[D];
+#pragma unroll
+  for (int v = 0; v < D; ++v) eoff[v] = offv(v);
 
   for (int64_t bl = blockIdx.y; bl < A.batch; bl += gridDim.y) {
     const int64_t b = bl + A.batch_offset;
@@ -333,18 +338,34 @@ __global__ void __launch_bounds__(STREAM_THREADS, HEAVY ? 1 : (sizeof(T) == 4 ? 
       if (w < items && !init_pass) {
         const IDX base = base_of(w);
         cx<T>* slot = stg + (size_t)stage * D * STREAM_THREADS + threadIdx.x;
-        if (paired) {
-          if constexpr (CAN_PAIR) {
-            float4* slot4 = reinterpret_cast<float4*>(stg) +
-                            (size_t)stage * (D / 2) * STREAM_THREADS + threadIdx.x;
+        if (peers.enabled) {  // fused exchange: general addressing through the peer table
+          if (paired) {
+            if constexpr (CAN_PAIR) {
+              float4* slot4 = reinterpret_cast<float4*>(stg) +
+                              (size_t)stage * (D / 2) * STREAM_THREADS + threadIdx.x;
 #pragma unroll
-            for (int v = 0; v < D; v += 2)
-              cp_async16(slot4 + (v >> 1) * STREAM_THREADS, src_of(base | offv(v)));
+              for (int v = 0; v < D; v += 2)
+                cp_async16(slot4 + (v >> 1) * STREAM_THREADS, src_of(base | eoff[v]));
+            }
+          } else {
+#pragma unroll
+            for (int v = 0; v < D; ++v)
+              cp_async_elem<T>(slot + v * STREAM_THREADS, src_of(base | eoff[v]));
           }
         } else {
+          const cx<T>* pb = gs + base;
+          if (paired) {
+            if constexpr (CAN_PAIR) {
+              float4* slot4 = reinterpret_cast<float4*>(stg) +
+                              (size_t)stage * (D / 2) * STREAM_THREADS + threadIdx.x;
 #pragma unroll
-          for (int v = 0; v < D; ++v)
-            cp_async_elem<T>(slot + v * STREAM_THREADS, src_of(base | offv(v)));
+              for (int v = 0; v < D; v += 2)
+                cp_async16(slot4 + (v >> 1) * STREAM_THREADS, pb + eoff[v]);
+            }
+          } else {
+#pragma unroll
+            for (int v = 0; v < D; ++v) cp_async_elem<T>(slot + v * STREAM_THREADS, pb + eoff[v]);
+          }
         }
       }
       cp_async_commit();
@@ -446,7 +467,7 @@ __global__ void __launch_bounds__(STREAM_THREADS, HEAVY ? 1 : (sizeof(T) == 4 ? 
             // diagonal on GLOBAL bits (any position): d[v] from shared memory
 #pragma unroll
             for (int v = 0; v < D; ++v) {
-              const uint64_t gi = (uint64_t)(base | offv(v));
+              const uint64_t gi = (uint64_t)(base | eoff[v]);
               int loc = 0;
               for (int j = 0; j < op.k; ++j)
                 loc |= (int)((gi >> ((op.data >> (6 * j)) & 63)) & 1ull) << (op.k - 1 - j);
@@ -460,16 +481,17 @@ __global__ void __launch_bounds__(STREAM_THREADS, HEAVY ? 1 : (sizeof(T) == 4 ? 
         }
       }
 
+      cx<T>* pw = gs + base;
       if (paired) {
         if constexpr (CAN_PAIR) {
 #pragma unroll
           for (int v = 0; v < D; v += 2)
-            *reinterpret_cast<float4*>(gs + (base | offv(v))) =
+            *reinterpret_cast<float4*>(pw + eoff[v]) =
                 make_float4(S.r2[v >> 1].x, S.i2[v >> 1].x, S.r2[v >> 1].y, S.i2[v >> 1].y);
         }
       } else {
 #pragma unroll
-        for (int v = 0; v < D; ++v) gs[base | offv(v)] = mk<T>(S.re(v), S.im(v));
+        for (int v = 0; v < D; ++v) pw[eoff[v]] = mk<T>(S.re(v), S.im(v));
       }
     }
   }
