@@ -161,6 +161,64 @@ class Entanglement:
         return min(max(float(measure.mean()), 0.0), 1.0)
 
     @classmethod
+    def concentratable_entanglement(cls, model: Model, n_samples: int, random_key=None,
+                                    scale: bool = False, **kwargs: Any) -> float:
+        """Concentratable entanglement (arXiv:2104.06923) by a swap test on a 3n-qubit
+        circuit: ancillas on wires 0..n-1, two copies of the model state on the other two
+        registers, H - CSWAP - H, ``1 - P(ancillas = 0..0)`` (entanglement.py:471-577).
+        The 3n-qubit circuit goes through the same ``Script`` -> CUDA path as every other
+        circuit (CSWAP = a 3-bit permutation)."""
+        n = model.n_qubits
+        if scale:
+            n_samples = int(2 ** n * n_samples)
+
+        def _swap_test_circuit(params, inputs, pulse_params=None, random_key=None, **kw):
+            from .tape import copy_to_tape
+
+            def vari():
+                model._variational(params, inputs, pulse_params=pulse_params,
+                                   random_key=random_key, **kw)
+
+            copy_to_tape(vari, offset=n)
+            copy_to_tape(vari, offset=2 * n)
+            for i in range(n):
+                op.H(wires=i)
+            for i in range(n):
+                op.CSWAP(wires=[i, i + n, i + 2 * n])
+            for i in range(n):
+                op.H(wires=i)
+
+        swap = js.Script(f=_swap_test_circuit, n_qubits=3 * n)
+        if n_samples is not None and n_samples > 0:
+            model.initialize_params(random_key, repeat=n_samples)
+            params = model.params
+        else:
+            params = model.params
+            if params.ndim <= 2:
+                params = params.reshape(1, *params.shape)
+        total = params.shape[0]
+        lo, hi = parallel.shard_bounds(total)
+        if parallel.world()[1] > 1 and total > 1:
+            params = params[lo:hi]
+        inputs = model._inputs_validation(kwargs.pop("inputs", None))
+        key = random_key if random_key is not None else model.random_key
+
+        if params.shape[0] > 1:
+            keys = rng.split(key, params.shape[0])
+            probs = swap.execute(type="probs", args=(params, inputs, model.pulse_params, keys),
+                                 kwargs=kwargs, in_axes=(0, None, None, 0))
+        elif params.shape[0] == 1:
+            probs = swap.execute(type="probs", args=(params[0], inputs, model.pulse_params, key),
+                                 kwargs=kwargs)[None]
+        else:
+            probs = np.zeros((0, 8 ** n))
+        anc = js.marginalize_probs(probs, 3 * n, tuple(range(n)))
+        ent = 1 - np.asarray(anc)[..., 0]
+        stats = parallel.allreduce_sum(
+            np.array([ent.sum(), float(ent.shape[0])], dtype=np.float64))
+        return float(stats[0] / stats[1])
+
+    @classmethod
     def relative_entropy(cls, *a, **k):
         raise NotImplementedError("host scipy.linalg.logm analysis: outside the backend scope")
 

@@ -275,3 +275,32 @@ def test_batch_sharding_two_ranks_equals_single_process():
         if k == "shard":
             continue
         assert np.allclose(np.asarray(one[k]), np.asarray(two[k]), atol=1e-10), k
+
+
+def test_concentratable_entanglement_matches_subset_purity_formula():
+    """CE = 1 - 2^-n sum over qubit subsets of Tr(rho_subset^2) (arXiv:2104.06923, eq. 1),
+    evaluated from the model's own state; the product path measures it with the 3n-qubit
+    swap-test circuit (entanglement.py:471-577)."""
+    import itertools
+
+    from qml_essentials_b200 import jaqsi as js
+    from qml_essentials_b200 import rng
+
+    n = 2
+    m = _model(n_qubits=n, n_layers=1, circuit_type="Strongly_Entangling")
+    ce = Entanglement.concentratable_entanglement(m, n_samples=6, random_key=rng.key(3))
+    rho = np.asarray(m(params=m.params, inputs=None, execution_type="density"))
+    want = []
+    for r in rho:
+        tot = 0.0
+        for k in range(n + 1):
+            for sub in itertools.combinations(range(n), k):
+                if not sub:
+                    tot += 1.0
+                    continue
+                red = js.partial_trace(r[None], n, list(sub))[0]
+                tot += float(np.real(np.trace(red @ red)))
+        want.append(1 - tot / 2 ** n)
+    assert abs(ce - np.mean(want)) < 1e-10
+    m0 = _model(n_qubits=2, n_layers=1, circuit_type="No_Entangling")
+    assert abs(Entanglement.concentratable_entanglement(m0, n_samples=3)) < 1e-12
