@@ -457,29 +457,39 @@ int upload(qmlb_program* p) {
          o_terms = place(off, p->terms), o_consts = place(off, p->consts),
          o_obs = place(off, p->obs), o_oc = place(off, p->obs_consts),
          o_pre = place(off, p->pre);
-  // register kernel: which ops read their matrix from one / two hoisted-factor tables
-  std::vector<RegFast> fast;
+  // register kernel: compact op stream (staged in shared memory by every CTA) with, per
+  // op, the one / two hoisted-factor tables its matrix is read from
+  std::vector<RegOp> fast;
   if (p->strategy == 0) {
-    fast.assign(p->ops.size(), RegFast{});
+    fast.assign(p->ops.size(), RegOp{});
     for (size_t i = 0; i < p->ops.size(); ++i) {
       const qmlb_op& o = p->ops[i];
-      if (o.kind != QMLB_OP_MAT && o.kind != QMLB_OP_CTRL1) continue;
-      const qmlb_source& s = p->sources[o.src];
-      RegFast f{};
-      if (s.kind == QMLB_SRC_PRE) {
-        f.n = 1;
-        f.slot0 = s.a1;
-        f.local0 = s.a0;
-      } else if (s.kind == QMLB_SRC_CHAIN && s.a1 == 2 &&
-                 p->sources[p->items[s.a0]].kind == QMLB_SRC_PRE &&
-                 p->sources[p->items[s.a0 + 1]].kind == QMLB_SRC_PRE) {
-        const qmlb_source& a = p->sources[p->items[s.a0]];
-        const qmlb_source& b = p->sources[p->items[s.a0 + 1]];
-        f.n = 2;
-        f.slot0 = a.a1;
-        f.local0 = a.a0;
-        f.slot1 = b.a1;
-        f.local1 = b.a0;
+      RegOp f{};
+      f.kind = (uint8_t)o.kind;
+      f.k = (uint8_t)o.k;
+      f.b0 = (uint8_t)o.bits[0];
+      f.b1 = (uint8_t)(o.k > 1 ? o.bits[1] : 0);
+      f.src = o.src;
+      if (o.kind == QMLB_OP_PERM && o.k == 2) {  // CX: (control, target)
+        if (reg_cx_orientation(p->consts.data() + o.aux) == 1) std::swap(f.b0, f.b1);
+      }
+      if (o.kind == QMLB_OP_MAT || o.kind == QMLB_OP_CTRL1) {
+        const qmlb_source& s = p->sources[o.src];
+        if (s.kind == QMLB_SRC_PRE) {
+          f.n = 1;
+          f.slot0 = s.a1;
+          f.local0 = s.a0;
+        } else if (s.kind == QMLB_SRC_CHAIN && s.a1 == 2 &&
+                   p->sources[p->items[s.a0]].kind == QMLB_SRC_PRE &&
+                   p->sources[p->items[s.a0 + 1]].kind == QMLB_SRC_PRE) {
+          const qmlb_source& x = p->sources[p->items[s.a0]];
+          const qmlb_source& y = p->sources[p->items[s.a0 + 1]];
+          f.n = 2;
+          f.slot0 = x.a1;
+          f.local0 = x.a0;
+          f.slot1 = y.a1;
+          f.local1 = y.a0;
+        }
       }
       fast[i] = f;
     }
@@ -511,7 +521,7 @@ int upload(qmlb_program* p) {
   put(o_obs, p->obs.data(), p->obs.size() * sizeof(qmlb_obs));
   put(o_oc, p->obs_consts.data(), p->obs_consts.size() * sizeof(double));
   put(o_pre, p->pre.data(), p->pre.size() * sizeof(qmlb_pre));
-  put(o_fast, fast.data(), fast.size() * sizeof(RegFast));
+  put(o_fast, fast.data(), fast.size() * sizeof(RegOp));
   put(o_matlist, p->stream_matlist.data(), p->stream_matlist.size() * sizeof(StreamMatOp));
   for (int a = 0; a < QMLB_MAX_ARGS; ++a)
     put(o_ids[a], p->pre_ids[a].data(), p->pre_ids[a].size() * sizeof(int32_t));
@@ -534,7 +544,7 @@ int upload(qmlb_program* p) {
   d.obs_consts = reinterpret_cast<const double*>(base + o_oc);
   d.pre = reinterpret_cast<const qmlb_pre*>(base + o_pre);
   d.n_pre = (int)p->pre.size();
-  d.fast = fast.empty() ? nullptr : reinterpret_cast<const RegFast*>(base + o_fast);
+  d.rops = fast.empty() ? nullptr : reinterpret_cast<const RegOp*>(base + o_fast);
   p->stream_matlist_dev = reinterpret_cast<const StreamMatOp*>(base + o_matlist);
   for (int a = 0; a < QMLB_MAX_ARGS; ++a)
     p->pre_ids_dev[a] = reinterpret_cast<const int32_t*>(base + o_ids[a]);

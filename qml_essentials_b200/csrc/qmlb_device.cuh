@@ -51,6 +51,18 @@ struct RegFast {
   int32_t n, slot0, local0, slot1, local1, pad0, pad1, pad2;
 };
 
+// Compact op of the register kernel (32 bytes), staged in shared memory by every CTA so
+// that decoding an op costs shared-memory latency instead of two dependent global loads
+// (op record, then its table descriptor) in front of every gate.  CX: b0 = control,
+// b1 = target (resolved on the host).
+struct RegOp {
+  uint8_t kind, k, b0, b1;
+  int32_t src;
+  int32_t n, slot0, local0, slot1, local1;  // RegFast
+  int32_t pad;
+};
+constexpr int REG_SMEM_OPS = 1024;
+
 // Device copy of a program (all pointers are device pointers into one blob).
 struct DevProg {
   const qmlb_op* ops;
@@ -62,7 +74,7 @@ struct DevProg {
   const qmlb_obs* obs;
   const double* obs_consts;
   const qmlb_pre* pre;
-  const RegFast* fast;  // strategy 0 only, else nullptr
+  const RegOp* rops;  // strategy 0 only, else nullptr
   int32_t n_ops, n_obs, n_bits, n_qubits, density, out_type, n_pre, pad;
 };
 

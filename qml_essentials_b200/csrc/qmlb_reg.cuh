@@ -250,6 +250,17 @@ template <typename T, int N>
 __global__ void __launch_bounds__(128, reg_min_ctas<T, N>()) k_reg(DevProg P, RunArgs R, int mode, int n_args,
                                              void* __restrict__ out) {
   constexpr int D = 1 << N;
+  // op stream -> shared memory (all threads take part before anyone leaves)
+  extern __shared__ __align__(16) unsigned char reg_smem[];
+  RegOp* s_ops = reinterpret_cast<RegOp*>(reg_smem);
+  const bool staged = P.n_ops <= REG_SMEM_OPS;
+  if (staged) {
+    const int4* src4 = reinterpret_cast<const int4*>(P.rops);
+    int4* dst4 = reinterpret_cast<int4*>(s_ops);
+    for (int i = threadIdx.x; i < P.n_ops * 2; i += blockDim.x) dst4[i] = src4[i];
+    __syncthreads();
+  }
+  const RegOp* ops = staged ? s_ops : P.rops;
   const int64_t bl = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (bl >= R.batch) return;
   const int64_t b = bl + R.batch_offset;
@@ -277,8 +288,8 @@ __global__ void __launch_bounds__(128, reg_min_ctas<T, N>()) k_reg(DevProg P, Ru
   int nfn = 0;
   auto fetch = [&](int o) {
     nfn = 0;
-    if (o >= P.n_ops || P.fast == nullptr) return;
-    const RegFast d = P.fast[o];
+    if (o >= P.n_ops) return;
+    const RegOp d = ops[o];
     if (d.n < 1 || !R.pre_on[d.slot0] || (d.n == 2 && !R.pre_on[d.slot1])) return;
     nfn = d.n;
     const cx<T>* t0 = static_cast<const cx<T>*>(R.pre_tab[d.slot0]) +
@@ -295,7 +306,7 @@ __global__ void __launch_bounds__(128, reg_min_ctas<T, N>()) k_reg(DevProg P, Ru
   fetch(0);
 
   for (int o = 0; o < P.n_ops; ++o) {
-    const qmlb_op op = P.ops[o];
+    const RegOp op = ops[o];
     cx<T> m[4];
     const bool have_m = nfn > 0;
     if (have_m) {
@@ -306,7 +317,7 @@ __global__ void __launch_bounds__(128, reg_min_ctas<T, N>()) k_reg(DevProg P, Ru
     fetch(o + 1);
     if (op.kind == QMLB_OP_PERM) {
       if (op.k == 1) {  // the only non-identity 1-bit permutation is X
-        dispatch1<T, N>(op.bits[0], [&](auto B) {
+        dispatch1<T, N>(op.b0, [&](auto B) {
           constexpr int BIT = decltype(B)::value;
 #pragma unroll
           for (int g = 0; g < (1 << (N - 1)); ++g) {
@@ -316,10 +327,8 @@ __global__ void __launch_bounds__(128, reg_min_ctas<T, N>()) k_reg(DevProg P, Ru
           }
         });
       } else {
-        // CX; perm[1] == 1 <=> control is bits[0]
-        const bool c0 = (int)P.consts[op.aux + 1] == 1;
-        const int cb = c0 ? op.bits[0] : op.bits[1], tb = c0 ? op.bits[1] : op.bits[0];
-        dispatch2<T, N>(cb, tb, [&](auto CB, auto TB) {
+        // CX: b0 = control, b1 = target (orientation resolved at upload)
+        dispatch2<T, N>(op.b0, op.b1, [&](auto CB, auto TB) {
           reg_cx<T, N, decltype(CB)::value, decltype(TB)::value, true>(S);
         });
       }
@@ -368,11 +377,11 @@ __global__ void __launch_bounds__(128, reg_min_ctas<T, N>()) k_reg(DevProg P, Ru
       eval_2x2<T>(P, R, rows, op.src, m);
     }
     if (op.kind == QMLB_OP_CTRL1) {
-      dispatch2<T, N>(op.bits[0], op.bits[1], [&](auto CB, auto TB) {
+      dispatch2<T, N>(op.b0, op.b1, [&](auto CB, auto TB) {
         reg_ctrl1<T, N, decltype(CB)::value, decltype(TB)::value>(S, m);
       });
     } else {
-      dispatch1<T, N>(op.bits[0], [&](auto B) {
+      dispatch1<T, N>(op.b0, [&](auto B) {
         reg_mat1<T, N, decltype(B)::value>(S, m);
       });
     }

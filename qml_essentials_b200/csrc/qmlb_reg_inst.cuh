@@ -1,4 +1,6 @@
 // Instantiates the register kernel for one precision (QMLB_T / QMLB_SUFFIX).
+#include <algorithm>
+
 #include "qmlb_internal.h"
 #include "qmlb_reg.cuh"
 
@@ -9,7 +11,8 @@ static void launch_n(const qmlb_program* p, const RunArgs& R, void* dst, cudaStr
   const int threads = 128;
   const unsigned grid = (unsigned)((R.batch + threads - 1) / threads);
   g_launches.fetch_add(1, std::memory_order_relaxed);
-  k_reg<QMLB_T, N><<<grid, threads, 0, st>>>(p->dev, R, p->reg_mode, p->max_arg + 1, dst);
+  const size_t smem = (size_t)std::min<int>(p->dev.n_ops, REG_SMEM_OPS) * sizeof(RegOp);
+  k_reg<QMLB_T, N><<<grid, threads, smem, st>>>(p->dev, R, p->reg_mode, p->max_arg + 1, dst);
 }
 
 cudaError_t QMLB_LAUNCH_REG(const qmlb_program* p, const RunArgs& R, void* dst,
