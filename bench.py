@@ -459,9 +459,9 @@ def main():
                 "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
                 "frac": achieved_tf / peak_tf,
                 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the ncu --set full
-                # capture of this kernel (profiles/r1_kreg_f64_n4_v2_hoist_full_summary.txt):
+                # capture of this kernel (profiles/r1_final_kreg_v5_smem_ops_full_summary.txt):
                 # parameters + hoisted tables in, the 8.6 MB of results still in L2
-                "traffic": 1676800 if prec64 else None,
+                "traffic": 1666304 if prec64 else None,
                 "kernel_ms": kern_ms,
                 "note": "achieved = algorithmic (unfused, dense) 26624 flop/eval x 270336 "
                         "evals / CUDA-event launch time; peak = qmlb_fma_peak measured on "
