@@ -80,12 +80,31 @@ cudaError_t launch_tile_f32(const qmlb_program* p, const RunArgs& R, const PassD
                             unsigned grid, void* state, cudaStream_t st);
 cudaError_t launch_tile_f64(const qmlb_program* p, const RunArgs& R, const PassDev& pass,
                             unsigned grid, void* state, cudaStream_t st);
-cudaError_t launch_stream_f32(const qmlb_program* p, const RunArgs& R, const StreamPass& pass,
-                              dim3 grid, void* state, const void* premats,
-                              const StreamPeers* peers, cudaStream_t st);
-cudaError_t launch_stream_f64(const qmlb_program* p, const RunArgs& R, const StreamPass& pass,
-                              dim3 grid, void* state, const void* premats,
-                              const StreamPeers* peers, cudaStream_t st);
+#define QMLB_DECL_STREAM(name)                                                              \
+  cudaError_t name(const qmlb_program* p, const RunArgs& R, const StreamPass& pass, dim3 grid, \
+                   void* state, const void* premats, const StreamPeers* peers, cudaStream_t st)
+QMLB_DECL_STREAM(launch_stream_f32_lean);
+QMLB_DECL_STREAM(launch_stream_f32_heavy);
+QMLB_DECL_STREAM(launch_stream_f64_lean);
+QMLB_DECL_STREAM(launch_stream_f64_heavy);
+#undef QMLB_DECL_STREAM
+
+inline cudaError_t launch_stream_f32(const qmlb_program* p, const RunArgs& R,
+                                     const StreamPass& pass, dim3 grid, void* state,
+                                     const void* premats, const StreamPeers* peers,
+                                     cudaStream_t st) {
+  return (pass.flags & QMLB_PASS_HEAVY)
+             ? launch_stream_f32_heavy(p, R, pass, grid, state, premats, peers, st)
+             : launch_stream_f32_lean(p, R, pass, grid, state, premats, peers, st);
+}
+inline cudaError_t launch_stream_f64(const qmlb_program* p, const RunArgs& R,
+                                     const StreamPass& pass, dim3 grid, void* state,
+                                     const void* premats, const StreamPeers* peers,
+                                     cudaStream_t st) {
+  return (pass.flags & QMLB_PASS_HEAVY)
+             ? launch_stream_f64_heavy(p, R, pass, grid, state, premats, peers, st)
+             : launch_stream_f64_lean(p, R, pass, grid, state, premats, peers, st);
+}
 cudaError_t launch_stream_mats_f32(const qmlb_program* p, const RunArgs& R, void* out,
                                    cudaStream_t st);
 cudaError_t launch_stream_mats_f64(const qmlb_program* p, const RunArgs& R, void* out,

@@ -1,6 +1,6 @@
 #define QMLB_T double
 #define QMLB_STREAM_R 4
-#define QMLB_LAUNCH_STREAM launch_stream_f64
-#define QMLB_STREAM_SET_SMEM stream_set_smem_f64
+#define QMLB_STREAM_HEAVY 1
+#define QMLB_LAUNCH_STREAM launch_stream_f64_heavy
 #define QMLB_LAUNCH_STREAM_MATS launch_stream_mats_f64
 #include "qmlb_stream_inst.cuh"

@@ -1,22 +1,26 @@
-// Instantiates the streaming kernel for one precision.
+// Instantiates the streaming kernel for one precision and one weight class (lean passes /
+// passes with a 3-4 bit dense or permutation op) - one translation unit each so the build
+// parallelises.
 #include "qmlb_internal.h"
 #include "qmlb_stream.cuh"
 
 namespace qmlb {
 
-template <bool HEAVY, typename IDX>
+template <typename IDX>
 static void launch_v(const qmlb_program* p, const RunArgs& R, const StreamPass& pass, dim3 grid,
                      cx<QMLB_T>* s, const cx<QMLB_T>* premats, const StreamPeers& peers,
                      size_t smem, cudaStream_t st) {
   static bool attr_set = false;  // > 48 KB of dynamic shared memory needs the opt-in (once)
   if (!attr_set) {
-    cudaFuncSetAttribute(k_stream<QMLB_T, QMLB_STREAM_R, HEAVY, IDX>,
+    cudaFuncSetAttribute(k_stream<QMLB_T, QMLB_STREAM_R, QMLB_STREAM_HEAVY, IDX>,
                          cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
     attr_set = true;
   }
-  k_stream<QMLB_T, QMLB_STREAM_R, HEAVY, IDX><<<grid, STREAM_THREADS, smem, st>>>(p->dev, R, pass, s, premats, peers);
+  k_stream<QMLB_T, QMLB_STREAM_R, QMLB_STREAM_HEAVY, IDX>
+      <<<grid, STREAM_THREADS, smem, st>>>(p->dev, R, pass, s, premats, peers);
 }
 
+#if !QMLB_STREAM_HEAVY
 cudaError_t QMLB_LAUNCH_STREAM_MATS(const qmlb_program* p, const RunArgs& R, void* out,
                                     cudaStream_t st) {
   const int64_t total = R.batch * (int64_t)p->stream_matlist.size();
@@ -27,6 +31,7 @@ cudaError_t QMLB_LAUNCH_STREAM_MATS(const qmlb_program* p, const RunArgs& R, voi
       static_cast<cx<QMLB_T>*>(out));
   return cudaGetLastError();
 }
+#endif
 
 cudaError_t QMLB_LAUNCH_STREAM(const qmlb_program* p, const RunArgs& R, const StreamPass& pass,
                                dim3 grid, void* state, const void* premats_v,
@@ -38,12 +43,10 @@ cudaError_t QMLB_LAUNCH_STREAM(const qmlb_program* p, const RunArgs& R, const St
   g_launches.fetch_add(1, std::memory_order_relaxed);
   const size_t smem = ((size_t)pass.matw + 2 * (size_t(1) << QMLB_STREAM_R) * STREAM_THREADS) *
                       sizeof(cx<QMLB_T>);
-  const bool heavy = pass.flags & QMLB_PASS_HEAVY;
-  const bool narrow = pass.n_bits <= 32;  // element-relative indices
-  if (heavy && narrow) launch_v<true, uint32_t>(p, R, pass, grid, s, premats, peers, smem, st);
-  else if (heavy) launch_v<true, uint64_t>(p, R, pass, grid, s, premats, peers, smem, st);
-  else if (narrow) launch_v<false, uint32_t>(p, R, pass, grid, s, premats, peers, smem, st);
-  else launch_v<false, uint64_t>(p, R, pass, grid, s, premats, peers, smem, st);
+  if (pass.n_bits <= 32)  // element-relative indices fit 32 bits
+    launch_v<uint32_t>(p, R, pass, grid, s, premats, peers, smem, st);
+  else
+    launch_v<uint64_t>(p, R, pass, grid, s, premats, peers, smem, st);
   return cudaGetLastError();
 }
 
