@@ -247,3 +247,64 @@ def case_shots(precision="complex128", n=3, batch=4, shots=2000, seed=5):
     ev_ref = est @ signs.T
     return {"count_mismatch": mism, "expval_err": float(np.abs(ev - ev_ref).max()),
             "sums": float(np.abs(est.sum(axis=1) - 1).max())}
+
+
+def case_edge_cases(precision="complex128"):
+    """Edge cases of the path (empty / permutation-only circuits, one qubit, ragged last CTA,
+    single-element batches, one shot, deterministic probabilities): max |result - expected|
+    with exact expectations or the oracle."""
+    errs = {}
+    z = lambda n: [op.PauliZ(q, record=False) for q in range(n)]  # noqa: E731
+
+    # empty circuit (only a barrier): |000>
+    s = Script(lambda: op.Barrier(wires=[0, 1, 2]), n_qubits=3, precision=precision)
+    p = s.execute("probs")
+    errs["empty_probs"] = float(np.abs(p - np.eye(8)[0]).max())
+    errs["empty_expval"] = float(np.abs(s.execute("expval", obs=z(3)) - 1).max())
+    errs["empty_density"] = float(np.abs(s.execute("density") - np.outer(np.eye(8)[0],
+                                                                         np.eye(8)[0])).max())
+
+    # permutation / diagonal ops only: X, CX, CCX, SWAP, Z, CZ  ->  a basis state with a sign
+    def perm_only():
+        op.PauliX(wires=0); op.CX(wires=[0, 2]); op.CCX(wires=[0, 2, 1])
+        op.SWAP(wires=[1, 3]); op.PauliZ(wires=0); op.CZ(wires=[0, 3])
+
+    s = Script(perm_only, n_qubits=4, precision=precision)
+    st = s.execute("state")
+    want = np.zeros(16, dtype=complex)
+    want[0b1011] = 1.0  # X0 -> 1000, CX02 -> 1010, CCX(0,2;1) -> 1110, SWAP13 -> 1011, Z0 * CZ03
+    errs["perm_only_state"] = float(np.abs(st - want).max())
+
+    # one qubit, batch of one element along an axis, and a ragged batch (130 = 128 + 2)
+    for B in (1, 130):
+        th = np.linspace(-2.0, 2.0, B).reshape(B, 1)
+        s = Script(lambda t: op.RX(t[0], wires=0), n_qubits=1, precision=precision)
+        ev = s.execute("expval", obs=z(1), args=(th,), in_axes=(0,))
+        errs[f"rx_cos_batch{B}"] = float(np.abs(ev[:, 0] - np.cos(th[:, 0])).max())
+        assert ev.shape == (B, 1)
+
+    # one-qubit noisy density: RX(pi) then BitFlip(0.5) -> maximally mixed diagonal
+    def noisy():
+        op.RX(np.pi, wires=0); op.BitFlip(0.5, wires=0)
+
+    rho = Script(noisy, n_qubits=1, precision=precision).execute("density")
+    errs["bitflip_half"] = float(np.abs(rho - np.eye(2) / 2).max())
+
+    # shots on a deterministic distribution (|10>): every shot lands on index 2, one shot too
+    def det():
+        op.PauliX(wires=0)
+
+    s = Script(det, n_qubits=2, precision=precision)
+    for shots in (1, 7):
+        est = s.execute("probs", shots=shots)
+        errs[f"det_shots{shots}"] = float(np.abs(est - np.eye(4)[2]).max())
+
+    # repeated / subset observables
+    def bell():
+        op.H(wires=0); op.CX(wires=[0, 1])
+
+    s = Script(bell, n_qubits=3, precision=precision)
+    ev = s.execute("expval", obs=[op.PauliZ(2, record=False), op.PauliZ(0, record=False),
+                                  op.PauliZ(2, record=False)])
+    errs["subset_obs"] = float(np.abs(ev - np.array([1.0, 0.0, 1.0])).max())
+    return errs

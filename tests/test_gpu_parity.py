@@ -66,6 +66,13 @@ def test_shots_counts_bit_exact(precision):
     assert r["expval_err"] < 1e-12 and r["sums"] < 1e-12
 
 
+@pytest.mark.parametrize("precision", ["complex128", "complex64"])
+def test_edge_cases(precision):
+    """Empty and permutation-only circuits, one qubit, ragged last CTA, one shot."""
+    errs = pc.case_edge_cases(precision)
+    assert max(errs.values()) < pc.TOL[precision], errs
+
+
 @pytest.mark.parametrize("n", [1, 2, 3, 5, 6, 7, 9, 10, 12])
 def test_statevector_sizes_across_kernel_regimes(n):
     """n <= 5 register kernel, 6..7 warp teams, 8..13 CTA teams (complex128)."""

@@ -46,6 +46,12 @@ def test_encoding_strategies(strategy):
     assert pc.case_model(2, 2, "Circuit_19", 5, 2, strategy=strategy) < 1e-10
 
 
+def test_edge_cases_through_host_path():
+    for prec in ("complex128", "complex64"):
+        errs = pc.case_edge_cases(prec)
+        assert max(errs.values()) < pc.TOL[prec], errs
+
+
 def test_shots_bookkeeping_matches_oracle_bit_for_bit():
     r = pc.case_shots()
     assert r["count_mismatch"] == 0 and r["expval_err"] < 1e-12 and r["sums"] < 1e-12
