@@ -55,6 +55,22 @@ def threefry2x32(k0, k1, x0, x1):
     return x0, x1
 
 
+def _threefry_scalar(k0: int, k1: int, x0: int, x1: int):
+    """The same block function on Python ints - one scalar key is split on every
+    ``Model.__call__`` and NumPy's per-call overhead on 2-element arrays dominated it."""
+    M = 0xFFFFFFFF
+    ks = (k0, k1, k0 ^ k1 ^ 0x1BD11BDA)
+    x0 = (x0 + ks[0]) & M
+    x1 = (x1 + ks[1]) & M
+    for i in range(5):
+        for r in _ROT[i % 2]:
+            x0 = (x0 + x1) & M
+            x1 = (((x1 << r) | (x1 >> (32 - r))) & M) ^ x0
+        x0 = (x0 + ks[(i + 1) % 3]) & M
+        x1 = (x1 + ks[(i + 2) % 3] + i + 1) & M
+    return x0, x1
+
+
 class PRNGKey:
     """An array of threefry keys: ``data`` is uint32 with shape ``(*batch, 2)``."""
 
@@ -114,6 +130,10 @@ def split(k, num: int = 2):
     ``(num, *k.shape)``; for a :class:`SymKey` a tuple of derived SymKeys."""
     if isinstance(k, SymKey):
         return tuple(SymKey(k.arg, k.path + ((num, i),)) for i in range(num))
+    if k.data.ndim == 1 and num <= 8:  # scalar key, few children: pure-int fast path
+        k0, k1 = int(k.data[0]), int(k.data[1])
+        return PRNGKey(np.array([_threefry_scalar(k0, k1, 0, i) for i in range(num)],
+                                dtype=_U32))
     d = _split_data(k.data, num)  # (*batch, num, 2)
     return PRNGKey(np.moveaxis(d, -2, 0))
 

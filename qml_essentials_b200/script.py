@@ -252,8 +252,12 @@ class Script:
                 sig.append((axk, "key"))
             else:
                 sig.append((axk, _make_hashable(a)))
+        # observables with a class-level constant matrix (PauliZ, ...) are identified by
+        # name and wires; only free-form ones (Hermitian, parity) hash their matrix
         obs_sig = tuple(
-            (o.name, tuple(o.wires), _make_hashable(np.asarray(o.matrix))) for o in obs
+            (o.name, tuple(o.wires)) if getattr(o.__class__, "_matrix", None) is not None
+            else (o.name, tuple(o.wires), _make_hashable(np.asarray(o.matrix)))
+            for o in obs
         )
         return (
             type,
