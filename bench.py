@@ -420,6 +420,9 @@ def main():
     clocks = sampler.stop() if rank == 0 else None
     gp_ms = gp.get("ms_per_circuit", 0.0) if gp else 0.0
 
+    # measured while every rank is still alive (the ranks leave right after the last collective)
+    peak_tf = ex.fma_peak_tflops(args.precision) if rank == 0 else None
+
     t = torch.tensor([dev_ms, e2e_s * 1e3, gp_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -430,7 +433,6 @@ def main():
         value = total_evals / (dev_ms * 1e-3)
         e2e_value = total_evals / (e2e_ms * 1e-3)
         prec64 = args.precision == "complex128"
-        peak_tf = ex.fma_peak_tflops(args.precision)
         achieved_tf = ALGO_FLOP_PER_EVAL * B / (kern_ms * 1e-3) / 1e12
         line = {
             "metric": "circuit evals/sec (batched)", "value": value, "unit": "evals/s",
