@@ -304,3 +304,19 @@ def test_concentratable_entanglement_matches_subset_purity_formula():
     assert abs(ce - np.mean(want)) < 1e-10
     m0 = _model(n_qubits=2, n_layers=1, circuit_type="No_Entangling")
     assert abs(Entanglement.concentratable_entanglement(m0, n_samples=3)) < 1e-12
+
+
+def test_two_feature_spectrum_reconstructs_model_output():
+    """n_input_feat = 2 (encoding ['RX', 'RY']): N-D FFT grid, per-axis frequencies, and the
+    series evaluated at off-grid points equals the model (coefficients.py:109-150,172-236)."""
+    m = _model(n_qubits=2, n_layers=1, circuit_type="Circuit_19", encoding=["RX", "RY"])
+    assert m.n_input_feat == 2
+    coeffs, freqs = Coefficients.get_spectrum(m, shift=True)
+    assert coeffs.ndim == 2 and len(freqs) == 2
+    assert coeffs.shape == (len(freqs[0]), len(freqs[1]))
+    pts = np.array([[0.3, 1.7], [2.9, 0.2], [4.1, 5.5]])
+    want = np.asarray(m(inputs=pts, force_mean=True)).reshape(-1)
+    got = Coefficients.evaluate_Fourier_series(coeffs, list(freqs), pts)
+    assert np.allclose(got, want, atol=1e-10)
+    fcc = FCC.get_fcc(model=m, n_samples=12)
+    assert 0 <= fcc <= 1
