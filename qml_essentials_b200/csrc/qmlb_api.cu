@@ -178,6 +178,12 @@ int op_entries(const qmlb_program* p, const qmlb_op& o) {
   return source_entries(s.kind, s.k, s.flags);
 }
 
+bool all_zstring(const qmlb_program* p) {
+  for (const auto& o : p->obs)
+    if (o.kind != QMLB_OBS_ZSTRING) return false;
+  return true;
+}
+
 // split a pass' ops into windows whose matrices fit `matw` entries
 void make_windows(const qmlb_program* p, QmlbPassHost& ps, int matw) {
   ps.matoff.assign(ps.ops.size(), 0);
@@ -496,6 +502,7 @@ int upload(qmlb_program* p) {
   }
   const size_t o_fast = place(off, fast);
   const size_t o_matlist = place(off, p->stream_matlist);
+  const size_t o_fsteps = place(off, p->frame_steps);
   size_t o_ids[QMLB_MAX_ARGS];
   for (int a = 0; a < QMLB_MAX_ARGS; ++a) o_ids[a] = place(off, p->pre_ids[a]);
   struct PO {
@@ -523,6 +530,7 @@ int upload(qmlb_program* p) {
   put(o_pre, p->pre.data(), p->pre.size() * sizeof(qmlb_pre));
   put(o_fast, fast.data(), fast.size() * sizeof(RegOp));
   put(o_matlist, p->stream_matlist.data(), p->stream_matlist.size() * sizeof(StreamMatOp));
+  put(o_fsteps, p->frame_steps.data(), p->frame_steps.size() * sizeof(FrameStep));
   for (int a = 0; a < QMLB_MAX_ARGS; ++a)
     put(o_ids[a], p->pre_ids[a].data(), p->pre_ids[a].size() * sizeof(int32_t));
   for (size_t i = 0; i < p->passes.size(); ++i) {
@@ -546,6 +554,7 @@ int upload(qmlb_program* p) {
   d.n_pre = (int)p->pre.size();
   d.rops = fast.empty() ? nullptr : reinterpret_cast<const RegOp*>(base + o_fast);
   p->stream_matlist_dev = reinterpret_cast<const StreamMatOp*>(base + o_matlist);
+  p->frame_steps_dev = reinterpret_cast<const FrameStep*>(base + o_fsteps);
   for (int a = 0; a < QMLB_MAX_ARGS; ++a)
     p->pre_ids_dev[a] = reinterpret_cast<const int32_t*>(base + o_ids[a]);
   d.n_ops = (int)p->ops.size();
@@ -572,12 +581,6 @@ int upload(qmlb_program* p) {
     }
   }
   return QMLB_OK;
-}
-
-bool all_zstring(const qmlb_program* p) {
-  for (const auto& o : p->obs)
-    if (o.kind != QMLB_OBS_ZSTRING) return false;
-  return true;
 }
 
 int plan(qmlb_program* p) {
@@ -611,6 +614,26 @@ int plan(qmlb_program* p) {
       p->reg_mode = 0;
     }
     return QMLB_OK;
+  }
+
+  // ---- strategy 3: on-chip frame engine (state in shared memory / cluster DSMEM) -----
+  if ((force < 0 || force == 3) && !p->force_stream && env_int("QMLB_FRAME", 1)) {
+    if (plan_frame(p) == QMLB_OK) {
+      p->strategy = 3;
+      p->direct_out = true;
+      if (p->out_type == QMLB_OUT_STATE || (p->out_type == QMLB_OUT_DENSITY && p->density)) {
+        p->frame_out_mode = 0;
+      } else if (p->out_type == QMLB_OUT_PROBS) {
+        p->frame_out_mode = 1;
+      } else if (p->out_type == QMLB_OUT_EXPVAL && all_zstring(p)) {
+        p->frame_out_mode = 2;
+      } else {
+        p->frame_out_mode = 0;  // state to the workspace, measured by the kernels below
+        p->direct_out = false;
+      }
+      return QMLB_OK;
+    }
+    if (force == 3) return fail(QMLB_ERR_UNSUPPORTED, "program outside the frame engine's envelope");
   }
 
   // ---- strategy 1: whole state in shared memory ---------------------------------
@@ -787,7 +810,7 @@ size_t pre_layout(const qmlb_program* p, const qmlb_arg* a, int64_t batch, bool 
 
 // batched streaming runs keep a table of every (element, op) matrix
 size_t premats_bytes(const qmlb_program* p, int64_t batch) {
-  if (p->strategy != 2 || batch <= 1) return 0;
+  if (!(p->strategy == 3 || (p->strategy == 2 && batch > 1))) return 0;
   return ((size_t)batch * p->stream_mat_row * cs_of(p->dtype) + 255) & ~size_t(255);
 }
 
@@ -891,6 +914,15 @@ int run_typed(const qmlb_program* p, RunArgs& R, void* out, void* workspace, siz
                 (state_layout(p, R.batch, &part_off) - premats_bytes(p, R.batch));
     int rc = evolve_stream<T>(p, R, state, 1, premats, st);
     if (rc != QMLB_OK) return rc;
+  } else if (p->strategy == 3) {
+    // [tables | state + partials | evaluated matrices]: one launch evaluates every matrix
+    // of every element, one launch runs the whole tape on chip
+    unsigned char* premats = static_cast<unsigned char*>(workspace) + tab_bytes +
+                             (state_layout(p, R.batch, &part_off) - premats_bytes(p, R.batch));
+    const bool f64 = std::is_same<T, double>::value;
+    CUDA_TRY((f64 ? launch_stream_mats_f64 : launch_stream_mats_f32)(p, R, premats, st));
+    CUDA_TRY((f64 ? launch_frame_f64 : launch_frame_f32)(
+        p, R, premats, p->direct_out ? out : static_cast<void*>(ws_state), p->frame_out_mode, st));
   } else {
     for (const QmlbPassHost& ps : p->passes) {
       const int kt = (int)ps.tile_bits.size();
@@ -944,6 +976,8 @@ int qmlb_plan_describe(const qmlb_program_desc* d, char* buf, size_t buflen) {
       }
       s += "\n";
     }
+  } else if (prog.strategy == 3) {
+    s += describe_frame(&prog);
   } else if (prog.strategy == 1) {
     s += "smem_bytes " + std::to_string(prog.smem) + " teams " + std::to_string(prog.teams) + "\n";
   }
@@ -1002,9 +1036,10 @@ int qmlb_program_info(const qmlb_program* p, int32_t* strategy, int32_t* n_passe
   if (!p) return fail(QMLB_ERR_INVALID, "null program");
   if (strategy) *strategy = p->strategy;
   if (n_passes)
-    *n_passes = p->strategy == 0 ? 1
-                                 : (p->strategy == 2 ? (int32_t)p->stream_passes.size()
-                                                     : (int32_t)p->passes.size());
+    *n_passes = p->strategy == 0   ? 1
+                : p->strategy == 2 ? (int32_t)p->stream_passes.size()
+                : p->strategy == 3 ? (int32_t)p->frame_steps.size()
+                                   : (int32_t)p->passes.size();
   if (n_device_ops) *n_device_ops = (int32_t)p->ops.size();
   return QMLB_OK;
 }

@@ -1,0 +1,547 @@
+// Host planner of the on-chip frame engine (strategy 3): cuts a device program into
+// SUBPASS / RELAYOUT steps (qmlb_frame_types.h).  Pure host code - no CUDA call - so the
+// CPU test-suite can check every schedule through qmlb_plan_describe.
+#include <algorithm>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "qmlb_internal.h"
+
+namespace qmlb {
+
+namespace {
+
+inline int popc64(uint64_t x) { return __builtin_popcountll(x); }
+inline int top_bit(uint64_t x) { return 63 - __builtin_clzll(x); }
+
+// physical = A * logical; col[j] = A e_j (mask of logical bit j), row[j] = row j of A^-1
+// (parity row: the logical value of bit j at physical index p is parity(p & row[j])).
+// Invariant: every outer physical position g >= T holds exactly one un-mixed logical bit
+// (row g of A is a unit vector), so "logical bit j is local" <=> col[j] has no outer bit.
+struct Frame {
+  int N = 0, T = 0;
+  uint64_t col[FRAME_MAX_BITS] = {}, row[FRAME_MAX_BITS] = {};
+  bool outer(int j) const { return (col[j] >> T) != 0; }
+  void set_permutation(const std::vector<int>& pos) {  // logical j -> position pos[j]
+    for (int j = 0; j < N; ++j) col[j] = row[j] = 1ull << pos[j];
+  }
+};
+
+struct OpInfo {
+  uint64_t bits = 0;   // every logical bit the op touches
+  uint64_t need = 0;   // bits that must be local (and, for gates, in the register group)
+  bool fold = false;   // GF(2)-linear permutation: folded into the frame
+  int entries = 0;     // base matrix entries (premat row)
+  std::vector<int> pimg, pinv_img;  // fold: images of the unit vectors under perm / perm^-1
+};
+
+int base_entries(const qmlb_program* p, const qmlb_op& o) {
+  if (o.kind == QMLB_OP_PERM) return 0;
+  const qmlb_source& s = p->sources[o.src];
+  return source_entries(s.kind, s.k, s.flags);
+}
+
+// local bit b of an op (b = 0 least significant) is logical bit bits[k-1-b]
+inline int op_logical(const qmlb_op& o, int b) { return o.bits[o.k - 1 - b]; }
+
+bool analyse(const qmlb_program* p, std::vector<OpInfo>& info) {
+  info.assign(p->ops.size(), OpInfo{});
+  for (size_t i = 0; i < p->ops.size(); ++i) {
+    const qmlb_op& o = p->ops[i];
+    OpInfo& f = info[i];
+    for (int j = 0; j < o.k; ++j) f.bits |= 1ull << o.bits[j];
+    f.entries = base_entries(p, o);
+    switch (o.kind) {
+      case QMLB_OP_MAT:
+        if (o.k > 4) return false;
+        f.need = f.bits;
+        break;
+      case QMLB_OP_CTRL1:
+        f.need = 1ull << o.bits[1];
+        break;
+      case QMLB_OP_DIAG:
+        break;
+      case QMLB_OP_PERM: {
+        const int D = 1 << o.k;
+        std::vector<int> perm(D), pinv(D);
+        for (int v = 0; v < D; ++v) perm[v] = (int)p->consts[o.aux + v];
+        for (int v = 0; v < D; ++v) {
+          if (perm[v] < 0 || perm[v] >= D) return false;
+          pinv[perm[v]] = v;
+        }
+        if (perm[0] != 0) return false;
+        for (int v = 1; v < D; ++v) {  // linear: perm[v] = XOR of the images of its bits
+          int acc = 0;
+          for (int b = 0; b < o.k; ++b)
+            if (v >> b & 1) acc ^= perm[1 << b];
+          if (acc != perm[v]) return false;
+        }
+        f.fold = true;
+        f.pimg.resize(o.k);
+        f.pinv_img.resize(o.k);
+        for (int b = 0; b < o.k; ++b) {
+          f.pimg[b] = perm[1 << b];
+          f.pinv_img[b] = pinv[1 << b];
+        }
+        // a bit whose value after the permutation depends on another bit ("target") must be
+        // local: row b of L (bit b of every image) has to be the unit vector for outer bits
+        for (int b = 0; b < o.k; ++b) {
+          bool unit = true;
+          for (int c = 0; c < o.k; ++c)
+            if (((f.pimg[c] >> b) & 1) != (c == b ? 1 : 0)) unit = false;
+          if (!unit) f.need |= 1ull << op_logical(o, b);
+        }
+        break;
+      }
+      default:
+        return false;
+    }
+  }
+  return true;
+}
+
+// A' = A * L for the linear permutation of op o
+void fold_into(Frame& F, const qmlb_op& o, const OpInfo& f) {
+  uint64_t ncol[QMLB_MAX_OP_BITS], nrow[QMLB_MAX_OP_BITS];
+  for (int b = 0; b < o.k; ++b) {
+    uint64_t c = 0, r = 0;
+    for (int c2 = 0; c2 < o.k; ++c2) {
+      if ((f.pimg[b] >> c2) & 1) c ^= F.col[op_logical(o, c2)];
+      // row'[b] = sum_c2 (L^-1)[b][c2] row[c2], (L^-1)[b][c2] = bit b of pinv[e_c2]
+      if ((f.pinv_img[c2] >> b) & 1) r ^= F.row[op_logical(o, c2)];
+    }
+    ncol[b] = c;
+    nrow[b] = r;
+  }
+  for (int b = 0; b < o.k; ++b) {
+    F.col[op_logical(o, b)] = ncol[b];
+    F.row[op_logical(o, b)] = nrow[b];
+  }
+}
+
+struct Builder {
+  qmlb_program* p;
+  std::vector<OpInfo> info;
+  std::vector<char> done;
+  std::vector<int> premat_off;  // per program op
+  Frame F;
+  int N, T, G;
+  int mat_cap;
+  std::vector<FrameStep> steps;
+  std::vector<std::vector<int>> step_ops;  // program-op indices per step (describe)
+
+  // first not-done op that needs logical bit j local
+  std::vector<int> next_need() const {
+    std::vector<int> nn(N, 1 << 30);
+    for (size_t i = 0; i < p->ops.size(); ++i) {
+      if (done[i]) continue;
+      for (int j = 0; j < N; ++j)
+        if ((info[i].need >> j & 1) && nn[j] == (1 << 30)) nn[j] = (int)i;
+    }
+    return nn;
+  }
+
+  // permutation frame: the G bits needed last go outer, the rest fill the tile from the top
+  // (soonest-needed bits highest: register groups then sit above the lane bits)
+  std::vector<int> choose_positions() const {
+    std::vector<int> nn = next_need();
+    std::vector<int> order(N);
+    for (int j = 0; j < N; ++j) order[j] = j;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return nn[a] > nn[b]; });
+    std::vector<int> pos(N);
+    for (int r = 0; r < G; ++r) pos[order[r]] = T + r;      // latest needed -> outer
+    for (int r = G; r < N; ++r) pos[order[r]] = r - G;      // then ascending urgency upwards
+    return pos;
+  }
+
+  void emit_relayout(const std::vector<int>& pos) {
+    FrameStep s;
+    std::memset(&s, 0, sizeof(s));
+    s.kind = QMLB_FSTEP_RELAYOUT;
+    for (int j = 0; j < N; ++j) s.qcol[pos[j]] = F.col[j];
+    steps.push_back(s);
+    step_ops.emplace_back();
+    F.set_permutation(pos);
+  }
+
+  int run();
+  bool build_step();
+};
+
+// One SUBPASS (plus the folds that follow it).  Returns false when nothing could be done.
+bool Builder::build_step() {
+  uint64_t S = 0, blocked = 0;
+  std::vector<int> picked;       // gate ops of the step, program order
+  std::vector<int> folds;        // permutations folded after the step
+  std::vector<int> pinned;       // k >= 3: register position j -> logical bit
+  std::vector<int> par_bits;     // logical bits with a parity row beyond the register bits
+  int slots = 0, entries = 0;
+  for (size_t i = 0; i < p->ops.size(); ++i) {
+    if (done[i]) continue;
+    const qmlb_op& o = p->ops[i];
+    const OpInfo& f = info[i];
+    if (f.bits & blocked) {
+      blocked |= f.bits;
+      continue;
+    }
+    bool outer_need = false;
+    for (int j = 0; j < N; ++j)
+      if ((f.need >> j & 1) && F.outer(j)) outer_need = true;
+    if (outer_need) {
+      blocked |= f.bits;
+      continue;
+    }
+    if (f.fold) {
+      folds.push_back((int)i);
+      blocked |= f.bits;  // later ops on these bits see the new frame: next step
+      continue;
+    }
+    // gate: register group, parity rows, slots, matrix area
+    const uint64_t U = S | f.need;
+    bool ok = popc64(U) <= FRAME_R;
+    std::vector<int> pin_try = pinned;
+    if (ok && o.kind == QMLB_OP_MAT && o.k >= 3) {
+      std::vector<int> want(o.k);
+      for (int b = 0; b < o.k; ++b) want[b] = op_logical(o, b);
+      if (pin_try.empty())
+        pin_try = want;
+      else
+        ok = want.size() <= pin_try.size() && std::equal(want.begin(), want.end(), pin_try.begin());
+    }
+    std::vector<int> par_try = par_bits;
+    if (ok && (o.kind == QMLB_OP_CTRL1 || o.kind == QMLB_OP_DIAG)) {
+      const int first = o.kind == QMLB_OP_CTRL1 ? 0 : 0;
+      const int last = o.kind == QMLB_OP_CTRL1 ? 1 : o.k;
+      for (int a = first; a < last; ++a)
+        if (std::find(par_try.begin(), par_try.end(), o.bits[a]) == par_try.end())
+          par_try.push_back(o.bits[a]);
+      ok = FRAME_R + (int)par_try.size() <= FRAME_MAX_PAR;
+    }
+    const int need_slots = o.kind == QMLB_OP_DIAG ? 2 : 1;
+    int var = 1;
+    if (o.kind == QMLB_OP_MAT && o.k <= 2) var = 1 << o.k;
+    if (o.kind == QMLB_OP_CTRL1) var = 2;
+    const int e = f.entries * var;
+    if (ok) ok = slots + need_slots <= FRAME_MAX_OPS && entries + e <= mat_cap;
+    if (!ok) {
+      blocked |= f.bits;
+      continue;
+    }
+    S = U;
+    pinned = pin_try;
+    par_bits = par_try;
+    slots += need_slots;
+    entries += e;
+    picked.push_back((int)i);
+  }
+  if (picked.empty() && folds.empty()) return false;
+
+  if (!picked.empty()) {
+    // register positions: pinned bits first, then the other group bits, then pads (local
+    // bits outside the group, highest mask first so the lanes keep the low addresses)
+    std::vector<int> gb(pinned);
+    auto in_gb = [&](int j) { return std::find(gb.begin(), gb.end(), j) != gb.end(); };
+    for (int j = 0; j < N; ++j)
+      if ((S >> j & 1) && !in_gb(j)) gb.push_back(j);
+    {
+      std::vector<int> cand;
+      for (int j = 0; j < N; ++j)
+        if (!in_gb(j) && !F.outer(j)) cand.push_back(j);
+      std::stable_sort(cand.begin(), cand.end(), [&](int a, int b) {
+        return top_bit(F.col[a]) > top_bit(F.col[b]);
+      });
+      for (int j : cand) {
+        if ((int)gb.size() >= FRAME_R) break;
+        gb.push_back(j);
+      }
+    }
+    if ((int)gb.size() < FRAME_R) return false;  // tile smaller than a register group
+    std::vector<int> regpos(N, -1);
+    for (int j = 0; j < FRAME_R; ++j) regpos[gb[j]] = j;
+
+    FrameStep s;
+    std::memset(&s, 0, sizeof(s));
+    s.kind = QMLB_FSTEP_SUBPASS;
+    const uint64_t tile_mask = (1ull << T) - 1ull;
+    // pivots: echelon form of the masks (leading bit = highest set bit)
+    uint64_t ech[FRAME_R];
+    int piv[FRAME_R];
+    for (int j = 0; j < FRAME_R; ++j) {
+      uint64_t v = F.col[gb[j]];
+      bool changed = true;
+      while (changed) {
+        changed = false;
+        for (int i = 0; i < j; ++i)
+          if (v >> piv[i] & 1) {
+            v ^= ech[i];
+            changed = true;
+          }
+      }
+      ech[j] = v;
+      piv[j] = top_bit(v);
+      // keep earlier vectors reduced against the new pivot
+      for (int i = 0; i < j; ++i)
+        if (ech[i] >> piv[j] & 1) ech[i] ^= v;
+    }
+    std::vector<int> sp(piv, piv + FRAME_R);
+    std::sort(sp.begin(), sp.end());
+    uint64_t pivmask = 0;
+    for (int j = 0; j < FRAME_R; ++j) {
+      s.pivots[j] = (uint32_t)sp[j];
+      pivmask |= 1ull << sp[j];
+    }
+    for (int v = 0; v < FRAME_D; ++v) {
+      uint64_t e = 0;
+      for (int j = 0; j < FRAME_R; ++j)
+        if (v >> j & 1) e ^= F.col[gb[j]];
+      s.eoff[v] = (uint32_t)e;
+    }
+    auto make_par = [&](int logical) {
+      FramePar q{};
+      q.rloc = (uint32_t)(F.row[logical] & tile_mask);
+      q.rout = (uint32_t)(F.row[logical] >> T);
+      for (int v = 0; v < FRAME_D; ++v)
+        if (popc64((uint64_t)s.eoff[v] & F.row[logical]) & 1) q.smask |= (uint16_t)(1u << v);
+      return q;
+    };
+    for (int j = 0; j < FRAME_R; ++j) s.par[j] = make_par(gb[j]);
+    for (size_t t = 0; t < par_bits.size(); ++t) s.par[FRAME_R + t] = make_par(par_bits[t]);
+    s.n_par = FRAME_R + (int)par_bits.size();
+    auto par_index = [&](int logical) {
+      for (size_t t = 0; t < par_bits.size(); ++t)
+        if (par_bits[t] == logical) return FRAME_R + (int)t;
+      return -1;
+    };
+    // does register bit j ever see a flipped local value?
+    auto has_c = [&](int j) {
+      return (s.par[j].rloc & ~(uint32_t)pivmask) != 0 || s.par[j].rout != 0;
+    };
+
+    int slot = 0, used = 0;
+    std::vector<int> ops_of_step;
+    for (int i : picked) {
+      const qmlb_op& o = p->ops[i];
+      FrameOp fo;
+      std::memset(&fo, 0, sizeof(fo));
+      fo.k = (uint8_t)o.k;
+      fo.premat_off = premat_off[i];
+      fo.smem_off = used;
+      fo.nvar = 1;
+      if (o.kind == QMLB_OP_MAT && o.k == 1) {
+        fo.code = QMLB_FOP_MAT1;
+        fo.j0 = (uint8_t)regpos[o.bits[0]];
+        if (has_c(fo.j0)) fo.nvar = 2;
+      } else if (o.kind == QMLB_OP_MAT && o.k == 2) {
+        fo.code = QMLB_FOP_MAT2;
+        const int p0 = regpos[o.bits[0]], p1 = regpos[o.bits[1]];
+        fo.j0 = (uint8_t)std::max(p0, p1);
+        fo.j1 = (uint8_t)std::min(p0, p1);
+        fo.flags = p0 < p1 ? 1 : 0;
+        if (has_c(fo.j0) || has_c(fo.j1)) fo.nvar = 4;
+      } else if (o.kind == QMLB_OP_MAT) {
+        fo.code = QMLB_FOP_MATK;
+      } else if (o.kind == QMLB_OP_CTRL1) {
+        fo.code = QMLB_FOP_CTRL1;
+        fo.j0 = (uint8_t)regpos[o.bits[1]];
+        fo.j1 = (uint8_t)par_index(o.bits[0]);
+        if (has_c(fo.j0)) fo.nvar = 2;
+      } else {
+        fo.code = QMLB_FOP_DIAG;
+      }
+      used += info[i].entries * fo.nvar;
+      s.ops[slot++] = fo;
+      if (o.kind == QMLB_OP_DIAG) {
+        FrameOp aux;
+        std::memset(&aux, 0, sizeof(aux));
+        uint8_t* idx = reinterpret_cast<uint8_t*>(&aux);
+        for (int a = 0; a < o.k; ++a) idx[a] = (uint8_t)par_index(o.bits[a]);
+        s.ops[slot++] = aux;
+      }
+      ops_of_step.push_back(i);
+      done[i] = 1;
+    }
+    s.n_ops = slot;
+    s.mat_entries = used;
+    steps.push_back(s);
+    step_ops.push_back(ops_of_step);
+  }
+  for (int i : folds) {
+    fold_into(F, p->ops[i], info[i]);
+    done[i] = 1;
+  }
+  return true;
+}
+
+int Builder::run() {
+  done.assign(p->ops.size(), 0);
+  F.N = N;
+  F.T = T;
+  F.set_permutation(choose_positions());
+  size_t remaining = p->ops.size();
+  auto count_left = [&]() {
+    size_t n = 0;
+    for (char d : done) n += d ? 0 : 1;
+    return n;
+  };
+  int guard = 0;
+  while (remaining > 0) {
+    if (!build_step()) {
+      if (G == 0) return QMLB_ERR_UNSUPPORTED;  // cannot happen: nothing is ever outer
+      std::vector<int> pos = choose_positions();
+      bool same = true;
+      for (int j = 0; j < N; ++j)
+        if (F.col[j] != (1ull << pos[j])) same = false;
+      if (same || ++guard > 4096) return QMLB_ERR_UNSUPPORTED;
+      emit_relayout(pos);
+    }
+    remaining = count_left();
+  }
+  // back to index order (logical bit j at position j) for the output
+  bool ident = true;
+  for (int j = 0; j < N; ++j)
+    if (F.col[j] != (1ull << j)) ident = false;
+  if (!ident) {
+    std::vector<int> pos(N);
+    for (int j = 0; j < N; ++j) pos[j] = j;
+    emit_relayout(pos);
+  }
+  return QMLB_OK;
+}
+
+}  // namespace
+
+// Fills p->frame_* ; returns QMLB_ERR_UNSUPPORTED (without touching the error string) when
+// the program is outside the engine's envelope so that plan() can fall back.
+int plan_frame(qmlb_program* p) {
+  const int N = p->n_bits;
+  const size_t cs = p->dtype == QMLB_C128 ? 16 : 8;
+  const int maxT = p->dtype == QMLB_C128 ? 13 : 14;
+  if (N < 6 || N > maxT + 3) return QMLB_ERR_UNSUPPORTED;
+  Builder B;
+  B.p = p;
+  if (!analyse(p, B.info)) return QMLB_ERR_UNSUPPORTED;
+  B.N = N;
+  B.G = std::max(0, N - maxT);
+  B.T = N - B.G;
+
+  // geometry
+  int threads, team_bits, teams;
+  if (B.T - FRAME_R >= 8) {
+    threads = B.T >= 13 ? 512 : 256;
+    team_bits = B.T >= 13 ? 9 : 8;
+    teams = 1;
+  } else {
+    threads = 256;
+    team_bits = B.T - FRAME_R;
+    teams = threads >> team_bits;
+  }
+  int biggest = 1;
+  for (size_t i = 0; i < p->ops.size(); ++i) {
+    const qmlb_op& o = p->ops[i];
+    int var = 1;
+    if (o.kind == QMLB_OP_MAT && o.k <= 2) var = 1 << o.k;
+    if (o.kind == QMLB_OP_CTRL1) var = 2;
+    biggest = std::max(biggest, B.info[i].entries * var);
+  }
+  const size_t budget = 200 * 1024;
+  const size_t tile_bytes = (size_t(1) << B.T) * cs;
+  int cap = teams == 1 ? 1024 : 96;
+  cap = std::max(cap, biggest);
+  while (teams > 1 && (size_t)teams * (tile_bytes + (size_t)cap * cs) + 4096 > budget) teams >>= 1;
+  if ((size_t)teams * (tile_bytes + (size_t)cap * cs) + 4096 > budget) {
+    cap = (int)((budget - 4096 - tile_bytes) / cs);
+    if (cap < biggest) return QMLB_ERR_UNSUPPORTED;
+  }
+  if (teams > 1) threads = teams << team_bits;
+  if (threads < 32) return QMLB_ERR_UNSUPPORTED;
+  B.mat_cap = cap;
+
+  // evaluated matrices of one element: every gate op, program order
+  B.premat_off.assign(p->ops.size(), 0);
+  p->stream_matlist.clear();
+  int row = 0;
+  for (size_t i = 0; i < p->ops.size(); ++i) {
+    if (p->ops[i].kind == QMLB_OP_PERM) continue;
+    B.premat_off[i] = row;
+    StreamMatOp mo{};
+    mo.src = p->ops[i].src;
+    mo.off = row;
+    mo.swap2 = 0;
+    p->stream_matlist.push_back(mo);
+    row += B.info[i].entries;
+  }
+  p->stream_mat_row = row;
+
+  const int rc = B.run();
+  if (rc != QMLB_OK) return rc;
+  p->frame_steps = std::move(B.steps);
+  p->frame_step_ops = std::move(B.step_ops);
+  FrameProg& fp = p->frame;
+  std::memset(&fp, 0, sizeof(fp));
+  fp.n_steps = (int)p->frame_steps.size();
+  fp.n_bits = N;
+  fp.tile_bits = B.T;
+  fp.outer_bits = B.G;
+  fp.team_bits = team_bits;
+  fp.teams = teams;
+  fp.mat_cap = cap;
+  fp.premat_row = row;
+  fp.density = p->density;
+  fp.n_qubits = p->n_qubits;
+  fp.n_obs = (int)p->obs.size();
+  p->frame_threads = threads;
+  p->frame_heavy = false;
+  for (const qmlb_op& o : p->ops)
+    if (o.kind == QMLB_OP_MAT && o.k >= 3) p->frame_heavy = true;
+  // [tiles | matrices | 2 step records | relayout tables | reduction scratch]
+  p->frame_smem = (size_t)teams * (tile_bytes + (size_t)cap * cs) + 2 * sizeof(FrameStep) +
+                  (256 + 64) * sizeof(uint32_t) + 64 * sizeof(double);
+  return QMLB_OK;
+}
+
+std::string describe_frame(const qmlb_program* p) {
+  std::string s;
+  const FrameProg& fp = p->frame;
+  s += "frame tile_bits " + std::to_string(fp.tile_bits) + " outer_bits " +
+       std::to_string(fp.outer_bits) + " team_bits " + std::to_string(fp.team_bits) +
+       " teams " + std::to_string(fp.teams) + " threads " + std::to_string(p->frame_threads) +
+       " mat_cap " + std::to_string(fp.mat_cap) + " premat_row " + std::to_string(fp.premat_row) +
+       " smem " + std::to_string(p->frame_smem) + "\n";
+  for (size_t i = 0; i < p->frame_steps.size(); ++i) {
+    const FrameStep& st = p->frame_steps[i];
+    if (st.kind == QMLB_FSTEP_RELAYOUT) {
+      s += "relayout";
+      for (int b = 0; b < fp.n_bits; ++b) s += " " + std::to_string((unsigned long long)st.qcol[b]);
+      s += "\n";
+      continue;
+    }
+    s += "subpass pivots";
+    for (int j = 0; j < FRAME_R; ++j) s += " " + std::to_string(st.pivots[j]);
+    s += " eoff";
+    for (int v = 0; v < FRAME_D; ++v) s += " " + std::to_string(st.eoff[v]);
+    s += " par";
+    for (int j = 0; j < st.n_par; ++j)
+      s += " " + std::to_string(st.par[j].rloc) + ":" + std::to_string(st.par[j].rout) + ":" +
+           std::to_string(st.par[j].smask);
+    s += " ops";
+    size_t t = 0;
+    for (int o = 0; o < st.n_ops; ++o) {
+      const FrameOp& fo = st.ops[o];
+      s += " " + std::to_string(p->frame_step_ops[i][t++]) + ":" + std::to_string(fo.code) + ":" +
+           std::to_string(fo.k) + ":" + std::to_string(fo.j0) + ":" + std::to_string(fo.j1) + ":" +
+           std::to_string(fo.nvar) + ":" + std::to_string(fo.flags) + ":" +
+           std::to_string(fo.premat_off) + ":" + std::to_string(fo.smem_off);
+      if (fo.code == QMLB_FOP_DIAG) {
+        const uint8_t* idx = reinterpret_cast<const uint8_t*>(&st.ops[o + 1]);
+        s += ":";
+        for (int a = 0; a < fo.k; ++a) s += (a ? "," : "") + std::to_string(idx[a]);
+        ++o;
+      }
+    }
+    s += "\n";
+  }
+  return s;
+}
+
+}  // namespace qmlb

@@ -1,0 +1,86 @@
+// Step program of the on-chip "frame" engine (strategy 3), shared by the host planner
+// (qmlb_frame_plan.cu) and the kernel (qmlb_frame.cuh).
+//
+// The whole state of one circuit evaluation - a statevector of up to 2^17 amplitudes or the
+// 4^n entries of a density matrix (BASELINE config 4: n = 8, 1 MiB in complex128) - stays
+// in shared memory for the entire tape: in ONE CTA when it fits 128 KiB, else distributed
+// over the shared memories of a thread-block cluster of 2^G CTAs (DSMEM).  The planner cuts
+// the device program into STEPS:
+//
+//   SUBPASS   every thread takes one item = 2^4 amplitudes (a register group of four
+//             logical bits), applies every op of the step that acts inside the group with
+//             compile-time register indices, and writes them back in place;
+//   RELAYOUT  the physical layout changes (global<->local bit exchange across the cluster
+//             through distributed shared memory, or the final return to index order).
+//
+// CX / SWAP and every other GF(2)-linear permutation cost NOTHING at run time: the planner
+// folds them into the FRAME, the invertible bit matrix A with physical = A * logical.  A
+// gate on logical bit j then pairs the physical addresses p and p ^ col_j(A) (its MASK) and
+// the logical value of bit j at address p is parity(p & row_j(A^-1)).  A register group is
+// therefore described by its masks (eoff = all XOR combinations), the pivot positions of
+// the span of the masks (items enumerate the indices that are zero there) and the parity
+// rows; when a parity row reaches outside the group the item sees the gate with its local
+// value XOR c, which is looked up as one of 2^k pre-permuted matrix VARIANTS.
+#pragma once
+#include <stdint.h>
+
+namespace qmlb {
+
+constexpr int FRAME_R = 4;          // register-group bits
+constexpr int FRAME_D = 1 << FRAME_R;
+constexpr int FRAME_MAX_OPS = 24;   // op slots per step (a DIAG op takes two)
+constexpr int FRAME_MAX_PAR = 16;   // parity rows per step (0..3 = the register bits)
+constexpr int FRAME_MAX_BITS = 40;
+
+#define QMLB_FSTEP_SUBPASS 0
+#define QMLB_FSTEP_RELAYOUT 1
+
+#define QMLB_FOP_MAT1 0   // 2x2 on register bit j0
+#define QMLB_FOP_MAT2 1   // 4x4 on register bits j0 > j1 (local value = bit j0 << 1 | bit j1)
+#define QMLB_FOP_MATK 2   // dense 2^k x 2^k on register bits k-1..0 (k = 3, 4)
+#define QMLB_FOP_CTRL1 3  // 2x2 on register bit j0 where parity row j1 reads 1
+#define QMLB_FOP_DIAG 4   // diagonal over k parity rows (their indices sit in the next slot)
+
+struct FrameOp {           // 16 bytes
+  uint8_t code, k, j0, j1;
+  uint16_t nvar;           // matrix variants in shared memory: 1 or 2^k
+  uint16_t flags;          // bit 0: MAT2 whose two logical bits sit in reversed register order
+  int32_t premat_off;      // offset of the op's matrix in the element's row of evaluated matrices
+  int32_t smem_off;        // offset (complex entries) in the step's matrix area
+};
+
+// logical bit value at physical index (outer, local) of slot v of an item:
+//   parity(local_base & rloc) ^ parity(outer & rout) ^ bit v of smask
+struct FramePar {
+  uint32_t rloc, rout;
+  uint16_t smask, pad;
+};
+
+struct FrameStep {  // 1024 bytes, loaded into shared memory by the CTA that runs it
+  int32_t kind, n_ops, mat_entries, n_par;
+  uint32_t pivots[FRAME_R];           // ascending: items have zeros at these tile positions
+  uint32_t eoff[FRAME_D];             // slot v lives at tile index base ^ eoff[v]
+  FramePar par[FRAME_MAX_PAR];
+  FrameOp ops[FRAME_MAX_OPS];
+  // RELAYOUT: the amplitude that ends at physical index d comes from physical index
+  // XOR of qcol[b] over the set bits b of d (bits >= tile_bits select the CTA of the cluster)
+  uint64_t qcol[FRAME_MAX_BITS];
+  int32_t pad[8];
+};
+static_assert(sizeof(FrameStep) == 1024, "FrameStep is loaded as 256 words");
+
+struct FrameProg {
+  const FrameStep* steps;
+  int32_t n_steps;
+  int32_t n_bits;      // logical state bits (n or 2n)
+  int32_t tile_bits;   // T: bits held by one CTA
+  int32_t outer_bits;  // G: log2(cluster size)
+  int32_t team_bits;   // log2(threads working on one tile)
+  int32_t teams;       // tiles per CTA (1 when the CTA or cluster holds one state)
+  int32_t mat_cap;     // matrix entries per team in shared memory
+  int32_t premat_row;  // evaluated-matrix entries per element
+  int32_t out_mode;    // 0: complex state in index order, 1: probabilities, 2: Z-string expvals
+  int32_t density, n_qubits, n_obs;
+};
+
+}  // namespace qmlb

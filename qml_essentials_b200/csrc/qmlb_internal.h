@@ -8,6 +8,7 @@
 #include <vector>
 
 #include "qmlb_device.cuh"
+#include "qmlb_frame_types.h"
 #include "qmlb_stream_types.h"
 #include "qmlb_tile_types.h"
 
@@ -62,6 +63,16 @@ struct qmlb_program {
   int stream_mat_row = 0;                                // entries per element
   int sm_count = 148;
 
+  // strategy 3: on-chip frame engine (qmlb_frame_types.h)
+  std::vector<qmlb::FrameStep> frame_steps;
+  std::vector<std::vector<int>> frame_step_ops;  // program-op indices per step
+  const qmlb::FrameStep* frame_steps_dev = nullptr;
+  qmlb::FrameProg frame{};
+  int frame_threads = 0;
+  int frame_out_mode = 0;
+  bool frame_heavy = false;  // a dense op on 3-4 bits
+  size_t frame_smem = 0;
+
   void* blob = nullptr;
   qmlb::DevProg dev{};
 };
@@ -109,6 +120,12 @@ cudaError_t launch_stream_mats_f32(const qmlb_program* p, const RunArgs& R, void
                                    cudaStream_t st);
 cudaError_t launch_stream_mats_f64(const qmlb_program* p, const RunArgs& R, void* out,
                                    cudaStream_t st);
+cudaError_t launch_frame_f32(const qmlb_program* p, const RunArgs& R, const void* premats,
+                             void* out, int out_mode, cudaStream_t st);
+cudaError_t launch_frame_f64(const qmlb_program* p, const RunArgs& R, const void* premats,
+                             void* out, int out_mode, cudaStream_t st);
+int plan_frame(qmlb_program* p);                 // QMLB_OK or QMLB_ERR_UNSUPPORTED (fall back)
+std::string describe_frame(const qmlb_program* p);
 cudaError_t tile_set_smem_f32(size_t bytes);
 cudaError_t tile_set_smem_f64(size_t bytes);
 

@@ -1,6 +1,8 @@
 // Instantiates the streaming kernel for one precision and one weight class (lean passes /
 // passes with a 3-4 bit dense or permutation op) - one translation unit each so the build
 // parallelises.
+#include <cstdlib>
+
 #include "qmlb_internal.h"
 #include "qmlb_stream.cuh"
 
@@ -43,7 +45,13 @@ cudaError_t QMLB_LAUNCH_STREAM(const qmlb_program* p, const RunArgs& R, const St
   g_launches.fetch_add(1, std::memory_order_relaxed);
   const size_t smem = ((size_t)pass.matw + 2 * (size_t(1) << QMLB_STREAM_R) * STREAM_THREADS) *
                       sizeof(cx<QMLB_T>);
-  if (pass.n_bits <= 32)  // element-relative indices fit 32 bits
+  // element-relative indices fit 32 bits (QMLB_FORCE_IDX64=1: run the 64-bit index
+  // instantiation anyway - test hook for the path states beyond 2^32 amplitudes take)
+  static const bool force64 = [] {
+    const char* v = std::getenv("QMLB_FORCE_IDX64");
+    return v && std::atoi(v) != 0;
+  }();
+  if (pass.n_bits <= 32 && !force64)
     launch_v<uint32_t>(p, R, pass, grid, s, premats, peers, smem, st);
   else
     launch_v<uint64_t>(p, R, pass, grid, s, premats, peers, smem, st);

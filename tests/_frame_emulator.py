@@ -1,0 +1,209 @@
+"""Test-only NumPy emulation of the on-chip frame engine's STEP PROGRAM
+(``qml_essentials_b200/csrc/qmlb_frame_types.h``).
+
+The host planner (``qmlb_frame_plan.cu``) is pure host code and its output is dumped by
+``qmlb_plan_describe``; this module parses that dump and executes the steps exactly as the
+kernel ``k_frame`` does - items = indices with zeros at the pivots, slots at
+``base ^ eoff[v]``, XOR-variant matrices selected by the parity rows, relayouts as GF(2)
+linear gathers over (rank, tile index) - with the matrices of the oracle's program
+interpreter.  It lets the CPU suite prove the frame bookkeeping (folded CX, masks, parity
+rows, cluster exchanges) without a GPU; the CUDA kernel itself is covered by the ``-m gpu``
+parity tests.  Never reachable from the product."""
+
+import numpy as np
+
+from oracle import program_interp as pi
+
+FOP_MAT1, FOP_MAT2, FOP_MATK, FOP_CTRL1, FOP_DIAG = 0, 1, 2, 3, 4
+R, D = 4, 16
+
+
+def parse(text):
+    lines = text.strip().split("\n")
+    assert lines[0] == "strategy 3", lines[0]
+    head = lines[1].split()
+    geo = {head[i]: int(head[i + 1]) for i in range(1, len(head), 2)}
+    steps = []
+    for line in lines[2:]:
+        tok = line.split()
+        if tok[0] == "relayout":
+            steps.append(("relayout", [int(x) for x in tok[1:]]))
+            continue
+        assert tok[0] == "subpass"
+        ip, ie, ipar, io = (tok.index(k) for k in ("pivots", "eoff", "par", "ops"))
+        piv = [int(x) for x in tok[ip + 1:ie]]
+        eoff = [int(x) for x in tok[ie + 1:ipar]]
+        par = [tuple(int(y) for y in x.split(":")) for x in tok[ipar + 1:io]]
+        ops = []
+        for ent in tok[io + 1:]:
+            f = ent.split(":")
+            rec = dict(zip(("index", "code", "k", "j0", "j1", "nvar", "flags", "premat_off",
+                            "smem_off"), (int(x) for x in f[:9])))
+            rec["idx"] = [int(x) for x in f[9].split(",")] if len(f) > 9 else []
+            ops.append(rec)
+        steps.append(("subpass", piv, eoff, par, ops))
+    return geo, steps
+
+
+def _deposit(w, piv):
+    for b in piv:  # ascending
+        low = w & ((1 << b) - 1)
+        w = ((w >> b) << (b + 1)) | low
+    return w
+
+
+def _parity(x):
+    """Bit parity of every entry of an integer array."""
+    x = np.asarray(x, dtype=np.int64).copy()
+    for sh in (32, 16, 8, 4, 2, 1):
+        x ^= x >> sh
+    return x & 1
+
+
+def emulate(prog, text, args, batch):
+    """States (batch, 2^n_bits) in index order after the step program (vectorised over
+    the items of a step; the arithmetic per item is what ``k_frame`` does)."""
+    geo, steps = parse(text)
+    T, G, N = geo["tile_bits"], geo["outer_bits"], prog.n_bits
+    assert T + G == N
+    interp = pi.Interp(prog, args, batch)
+    mats = {}
+
+    def matrix(index):
+        if index not in mats:
+            m = interp.source(prog.ops[index]["src"])
+            mats[index] = np.ascontiguousarray(np.broadcast_to(m, (batch,) + m.shape[1:]))
+        return mats[index]
+
+    st = np.zeros((batch, 1 << N), dtype=np.complex128)
+    st[:, 0] = 1.0
+    tile_mask = (1 << T) - 1
+    items = np.arange(1 << (T - R), dtype=np.int64)
+    for step in steps:
+        if step[0] == "relayout":
+            qcol = step[1]
+            src = np.zeros(1 << N, dtype=np.int64)
+            d = np.arange(1 << N)
+            for b in range(N):
+                src ^= np.where((d >> b) & 1, qcol[b], 0)
+            assert np.array_equal(np.sort(src), d), "relayout is not a permutation"
+            st = st[:, src]
+            continue
+        _, piv, eoff, par, ops = step
+        assert sorted(piv) == piv and len(set(piv)) == R
+        base = _deposit(items.copy(), piv)
+        assert base.max() <= tile_mask
+        new = st.copy()
+        touched = np.zeros(1 << N, dtype=np.int32)
+        for rank in range(1 << G):
+            slots = (rank << T) | (base[:, None] ^ np.asarray(eoff, dtype=np.int64)[None, :])
+            np.add.at(touched, slots.ravel(), 1)
+            S = new[:, slots]  # (batch, items, 16)
+
+            def par_at(pi_):
+                rloc, rout, _ = par[pi_]
+                return _parity(base & rloc) ^ (bin(rank & rout).count("1") & 1)
+
+            cj = [par_at(j) for j in range(R)]
+            for o in ops:
+                M = matrix(o["index"])
+                code, k = o["code"], o["k"]
+                if code == FOP_MAT1:
+                    j = o["j0"]
+                    c = cj[j] if o["nvar"] > 1 else np.zeros_like(base)
+                    assert o["nvar"] > 1 or not cj[j].any()
+                    out = S.copy()
+                    for v in range(D):
+                        lv = ((v >> j) & 1) ^ c
+                        acc = 0
+                        for u in range(2):
+                            acc = acc + M[:, lv, u ^ c] * S[:, :, (v & ~(1 << j)) | (u << j)]
+                        out[:, :, v] = acc
+                    S = out
+                elif code == FOP_MAT2:
+                    ja, jb = o["j0"], o["j1"]
+                    assert ja > jb
+                    c = ((cj[ja] << 1) | cj[jb]) if o["nvar"] > 1 else np.zeros_like(base)
+                    assert o["nvar"] > 1 or not (cj[ja].any() or cj[jb].any())
+
+                    def sw(x):
+                        return ((x & 1) << 1) | (x >> 1) if o["flags"] & 1 else x
+
+                    out = S.copy()
+                    for v in range(D):
+                        lv = ((((v >> ja) & 1) << 1) | ((v >> jb) & 1)) ^ c
+                        acc = 0
+                        for u in range(4):
+                            slot = (v & ~((1 << ja) | (1 << jb))) | ((u >> 1) << ja) | ((u & 1) << jb)
+                            acc = acc + M[:, sw(lv), sw(u ^ c)] * S[:, :, slot]
+                        out[:, :, v] = acc
+                    S = out
+                elif code == FOP_MATK:
+                    c = sum(cj[j] << j for j in range(k))
+                    out = S.copy()
+                    dd = 1 << k
+                    for v in range(D):
+                        blk, lv = v >> k, v & (dd - 1)
+                        acc = 0
+                        for u in range(dd):
+                            acc = acc + M[:, lv ^ c, u ^ c] * S[:, :, (blk << k) | u]
+                        out[:, :, v] = acc
+                    S = out
+                elif code == FOP_CTRL1:
+                    j = o["j0"]
+                    c = cj[j] if o["nvar"] > 1 else np.zeros_like(base)
+                    ctl = par_at(o["j1"])
+                    sm = par[o["j1"]][2]
+                    out = S.copy()
+                    for v in range(D):
+                        assert ((sm >> v) & 1) == ((sm >> (v ^ (1 << j))) & 1)
+                        on = (((sm >> v) & 1) ^ ctl).astype(bool)
+                        lv = ((v >> j) & 1) ^ c
+                        acc = 0
+                        for u in range(2):
+                            acc = acc + M[:, lv, u ^ c] * S[:, :, (v & ~(1 << j)) | (u << j)]
+                        out[:, :, v] = np.where(on[None, :], acc, S[:, :, v])
+                    S = out
+                elif code == FOP_DIAG:
+                    out = S.copy()
+                    for v in range(D):
+                        loc = np.zeros_like(base)
+                        for a, pidx in enumerate(o["idx"]):
+                            bit = par_at(pidx) ^ ((par[pidx][2] >> v) & 1)
+                            loc |= bit << (k - 1 - a)
+                        out[:, :, v] = M[:, loc] * S[:, :, v]
+                    S = out
+                else:
+                    raise ValueError(code)
+            new[:, slots] = S
+        assert (touched == 1).all(), "items do not tile the state"
+        st = new
+    return st
+
+
+class FrameEmuExecutor:
+    """Executor for ``script._set_executor_for_testing``: programs the planner assigns to
+    the frame engine run through :func:`emulate`, everything else through the plain
+    program interpreter."""
+
+    name = "frame-emulator"
+
+    def __init__(self, lib):
+        self.lib = lib
+        self.frame_runs = 0
+        self.steps = []
+
+    def execute(self, plan, host_args, batch, chunk=None, to_host=True):
+        from qml_essentials_b200 import backend
+
+        args = [(a[0], a[1], a[2]) if a is not None else (None, 1, 1) for a in host_args]
+        text = backend.plan_describe(self.lib, plan.program, plan.out_type, plan.obs_recs,
+                                     plan.obs_pool, plan.precision)
+        if text.startswith("strategy 3"):
+            st = emulate(plan.program, text, args, batch)
+            self.frame_runs += 1
+            self.steps.append(text)
+        else:
+            st = pi.Interp(plan.program, args, batch).run()
+        names = {0: "state", 1: "probs", 2: "expval", 3: "density"}
+        return pi.measure(plan.program, st, names[plan.out_type], plan.obs_recs, plan.obs_pool)

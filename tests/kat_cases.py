@@ -130,3 +130,93 @@ def run_all(run, atol=1e-10):
     r = run(lambda: two(15 / 16), 2, "expval", z1)
     assert np.allclose(r, 0, atol=0.1)
     assert np.allclose(r, -1 / 16, atol=max(atol, 1e-6))
+
+
+def run_pennylane_conventions(run, atol=1e-10):
+    """The circuits of the reference's PennyLane-equality tests (tests/test_jaqsi.py:494-661)
+    against the CLOSED FORMS that follow from PennyLane's documented gate / channel
+    definitions (the reference asserts equality with ``default.qubit`` / ``default.mixed``;
+    PennyLane is absent here, its definitions are standard).  Independent of the oracle's
+    matrix code: amplitudes are written out by hand."""
+    c2 = lambda t: np.cos(t / 2) ** 2
+    s2 = lambda t: np.sin(t / 2) ** 2
+
+    def ctrl(gate, theta, both):
+        def f():
+            op.H(wires=0)
+            if both:
+                op.H(wires=1)
+            if theta is None:
+                gate(wires=[0, 1])
+            else:
+                gate(theta, wires=[0, 1])
+        return f
+
+    # :496-536 controlled gates on H|0> (x) |0>  (CZ: H on both)
+    want = {
+        "CY": (op.CY, None, False, [0.5, 0, 0, 0.5]),
+        "CZ": (op.CZ, None, True, [0.25] * 4),
+        "CRX": (op.CRX, 1.3, False, [0.5, 0, 0.5 * c2(1.3), 0.5 * s2(1.3)]),
+        "CRY": (op.CRY, 0.9, False, [0.5, 0, 0.5 * c2(0.9), 0.5 * s2(0.9)]),
+        "CRZ": (op.CRZ, 2.1, False, [0.5, 0, 0.5, 0]),
+    }
+    for name, (g, th, both, probs) in want.items():
+        assert np.allclose(run(ctrl(g, th, both), 2, "probs", []), probs, atol=atol), name
+    # CRZ phases (state, not only probabilities): diag(1, 1, e^{-i t/2}, e^{+i t/2})
+    st = run(ctrl(op.CRZ, 2.1, False), 2, "state", [])
+    assert np.allclose(st, [2 ** -0.5, 0, 2 ** -0.5 * np.exp(-1.05j), 0], atol=atol)
+    # :539-555 Rot(phi, theta, omega) = RZ(omega) RY(theta) RZ(phi)
+    r = run(lambda: op.Rot(0.4, 1.2, 2.5, wires=0), 1, "probs", [])
+    assert np.allclose(r, [c2(1.2), s2(1.2)], atol=atol)
+    st = run(lambda: op.Rot(0.4, 1.2, 2.5, wires=0), 1, "state", [])
+    assert np.allclose(st, [np.exp(-0.5j * (0.4 + 2.5)) * np.cos(0.6),
+                            np.exp(-0.5j * (0.4 - 2.5)) * np.sin(0.6)], atol=atol)
+
+    # :589-639 one channel after RX(theta)|0> = cos(t/2)|0> - i sin(t/2)|1>
+    def rho0(t):
+        c, s = np.cos(t / 2), np.sin(t / 2)
+        return np.array([[c * c, 1j * c * s], [-1j * c * s, s * s]])
+
+    X = np.array([[0, 1], [1, 0]], dtype=complex)
+    Y = np.array([[0, -1j], [1j, 0]])
+    Z = np.diag([1.0 + 0j, -1.0])
+
+    def after(ch, p, t):
+        def f(theta):
+            op.RX(theta, wires=0)
+            ch(p, wires=0)
+        return run(f, 1, "density", [], args=(np.array(t),))
+
+    r0 = rho0(0.8)
+    assert np.allclose(after(op.BitFlip, 0.15, 0.8), 0.85 * r0 + 0.15 * X @ r0 @ X, atol=atol)
+    r0 = rho0(1.1)
+    assert np.allclose(after(op.PhaseFlip, 0.2, 1.1), 0.8 * r0 + 0.2 * Z @ r0 @ Z, atol=atol)
+    r0 = rho0(0.6)
+    dep = 0.88 * r0 + 0.04 * (X @ r0 @ X + Y @ r0 @ Y + Z @ r0 @ Z)
+    assert np.allclose(dep, (1 - 0.16) * r0 + 0.16 * np.eye(2) / 2, atol=1e-14)
+    assert np.allclose(after(op.DepolarizingChannel, 0.12, 0.6), dep, atol=atol)
+    r0, g = rho0(1.3), 0.25
+    ad = np.array([[r0[0, 0] + g * r0[1, 1], np.sqrt(1 - g) * r0[0, 1]],
+                   [np.sqrt(1 - g) * r0[1, 0], (1 - g) * r0[1, 1]]])
+    assert np.allclose(after(op.AmplitudeDamping, g, 1.3), ad, atol=atol)
+    r0, g = rho0(0.9), 0.3
+    pdm = np.array([[r0[0, 0], np.sqrt(1 - g) * r0[0, 1]], [np.sqrt(1 - g) * r0[1, 0], r0[1, 1]]])
+    assert np.allclose(after(op.PhaseDamping, g, 0.9), pdm, atol=atol)
+
+    # :642-661 thermal relaxation, T2 <= T1 (PennyLane's six-operator form, pe = 0)
+    pe, t1, t2, tg = 0.0, 1e-4, 5e-5, 1e-6
+    e1, e2 = np.exp(-tg / t1), np.exp(-tg / t2)
+    p_reset = 1 - e1
+    pz = (1 - p_reset) * (1 - e2 / e1) / 2
+    pr0 = (1 - pe) * p_reset
+    pid = 1 - pz - pr0
+    r0 = rho0(1.0)
+    tr = np.array([[(pid + pz) * r0[0, 0] + pr0 * (r0[0, 0] + r0[1, 1]), (pid - pz) * r0[0, 1]],
+                   [(pid - pz) * r0[1, 0], (pid + pz) * r0[1, 1]]])
+
+    def thermal(theta):
+        op.RX(theta, wires=0)
+        op.ThermalRelaxationError(pe, t1, t2, tg, wires=0)
+
+    got = run(thermal, 1, "density", [], args=(np.array(1.0),))
+    assert np.allclose(got, tr, atol=atol)

@@ -1,0 +1,85 @@
+"""Host planner of the on-chip frame engine (strategy 3), checked WITHOUT a GPU: the step
+program dumped by ``qmlb_plan_describe`` is executed by a NumPy emulation of ``k_frame``
+(tests/_frame_emulator.py) and compared with the plain program interpreter - which the
+rest of the CPU suite pins to the reference-faithful oracle."""
+
+import warnings
+
+import numpy as np
+import pytest
+
+import _frame_emulator as fe
+from _interp_executor import InterpExecutor
+from qml_essentials_b200 import backend
+from qml_essentials_b200.model import Model
+
+
+@pytest.fixture(scope="module")
+def lib():
+    return backend.load_library()
+
+
+def _both(lib, n, L, ct, typ, noise=None, precision="complex128", B_I=2, B_P=2, **kw):
+    ex = fe.FrameEmuExecutor(lib)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        m = Model(n, L, ct, precision=precision, **kw)
+        rng = np.random.default_rng(1)
+        params = rng.uniform(0, 2 * np.pi, (B_P, *m._params_shape))
+        inputs = rng.uniform(-1, 1, (B_I, 1))
+        call = lambda: np.asarray(m(params=params, inputs=inputs, execution_type=typ,
+                                    noise_params=dict(noise) if noise else None))
+        m.script.executor = ex
+        got = call()
+        m.script.executor = InterpExecutor()
+        want = call()
+    return ex, float(np.abs(got - want).max())
+
+
+NOISE = {"Depolarizing": 0.01, "AmplitudeDamping": 0.02}
+
+
+@pytest.mark.parametrize("n,L,ct,typ,noise", [
+    (6, 3, "Circuit_15", "density", None),            # BASELINE config 3 circuit
+    (6, 2, "Circuit_19", "expval", None),             # controlled rotations: parity-row controls
+    (7, 2, "Hardware_Efficient", "probs", None),
+    (9, 1, "Strongly_Entangling", "state", None),
+    (3, 2, "Strongly_Entangling", "density", NOISE),  # 4x4 superoperators on (ket, bra)
+    (4, 2, "Strongly_Entangling", "expval", NOISE),
+    (4, 1, "Circuit_6", "probs", {"BitFlip": 0.1, "MultiQubitDepolarizing": 0.05}),  # 16x16
+    (6, 1, "Circuit_9", "expval", None),              # H + CZ: diagonal ops on parity rows
+])
+def test_single_cta_schedules(lib, n, L, ct, typ, noise):
+    ex, err = _both(lib, n, L, ct, typ, noise)
+    assert ex.frame_runs == 1, "planner did not choose the frame engine"
+    assert err < 1e-12
+
+
+@pytest.mark.parametrize("n,L,ct,typ,noise,precision", [
+    (8, 1, "Strongly_Entangling", "expval", NOISE, "complex128"),  # config 4: cluster of 8
+    (7, 1, "Strongly_Entangling", "probs", {"Depolarizing": 0.01}, "complex128"),
+    (14, 1, "Hardware_Efficient", "expval", None, "complex128"),
+    (15, 1, "Circuit_19", "probs", None, "complex64"),
+])
+def test_cluster_schedules(lib, n, L, ct, typ, noise, precision):
+    """States beyond one CTA's shared memory: outer (cluster-rank) bits, relayouts through
+    distributed shared memory, CX folded with an outer control."""
+    ex, err = _both(lib, n, L, ct, typ, noise, precision, B_I=1, B_P=1)
+    assert ex.frame_runs == 1
+    geo, steps = fe.parse(ex.steps[0])
+    assert geo["outer_bits"] >= 1
+    assert any(s[0] == "relayout" for s in steps)
+    assert err < (1e-12 if precision == "complex128" else 1e-9)
+
+
+def test_config4_schedule_shape(lib):
+    """BASELINE config 4 (8 qubits, 4 layers, depolarizing + amplitude damping): 472 tape
+    ops -> at most 100 sub-passes and 12 cluster exchanges; every CX is folded (no
+    permutation op reaches the kernel)."""
+    ex, err = _both(lib, 8, 4, "Strongly_Entangling", "expval", NOISE, B_I=1, B_P=1)
+    geo, steps = fe.parse(ex.steps[0])
+    assert (geo["tile_bits"], geo["outer_bits"], geo["threads"]) == (13, 3, 512)
+    n_sub = sum(1 for s in steps if s[0] == "subpass")
+    n_rel = sum(1 for s in steps if s[0] == "relayout")
+    assert n_sub <= 100 and n_rel <= 12
+    assert err < 1e-12

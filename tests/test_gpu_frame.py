@@ -1,0 +1,97 @@
+"""On-chip frame engine (strategy 3) on a B200 through the C ABI: parity with the oracle
+(1e-10 complex128 / 1e-5 complex64) for single-CTA states, several states per CTA and
+cluster-resident states (DSMEM relayouts), and agreement with the streamed strategy."""
+
+import os
+import warnings
+
+import numpy as np
+import pytest
+
+import parity_cases as pc
+from qml_essentials_b200.model import Model
+from qml_essentials_b200.script import get_executor
+
+pytestmark = pytest.mark.gpu
+NOISE = {"Depolarizing": 0.01, "AmplitudeDamping": 0.02}
+
+
+@pytest.mark.parametrize("precision", ["complex128", "complex64"])
+@pytest.mark.parametrize("n,L,ct,B_I,B_P,typ,noise", [
+    (6, 3, "Circuit_15", 0, 37, "density", None),
+    (6, 3, "Circuit_15", 0, 300, "state", None),
+    (6, 2, "Circuit_19", 5, 3, "expval", None),
+    (7, 2, "Hardware_Efficient", 3, 5, "probs", None),
+    (9, 2, "Strongly_Entangling", 2, 3, "expval", None),
+    (11, 1, "Circuit_19", 2, 2, "expval", None),
+    (12, 1, "Hardware_Efficient", 1, 2, "state", None),
+    (13, 1, "Strongly_Entangling", 2, 1, "probs", None),
+    (3, 2, "Strongly_Entangling", 4, 2, "density", NOISE),
+    (4, 2, "Strongly_Entangling", 3, 2, "expval", NOISE),
+    (5, 1, "Hardware_Efficient", 2, 2, "probs", NOISE),
+    (6, 1, "Circuit_19", 2, 1, "expval", {"BitFlip": 0.05, "PhaseDamping": 0.1}),
+    (4, 1, "Circuit_6", 2, 1, "probs", {"BitFlip": 0.1, "MultiQubitDepolarizing": 0.05}),
+])
+def test_frame_single_cta_parity(precision, n, L, ct, B_I, B_P, typ, noise):
+    err = pc.case_model(n, L, ct, B_I, B_P, typ, noise, precision=precision)
+    assert err < pc.TOL[precision]
+
+
+@pytest.mark.parametrize("precision", ["complex128", "complex64"])
+@pytest.mark.parametrize("n,L,ct,B_I,B_P,typ,noise", [
+    (14, 1, "Hardware_Efficient", 1, 2, "expval", None),
+    (15, 1, "Circuit_19", 2, 1, "probs", None),
+    (7, 1, "Strongly_Entangling", 2, 1, "probs", {"Depolarizing": 0.02}),
+    (7, 1, "Strongly_Entangling", 1, 2, "density", NOISE),
+    (8, 1, "Strongly_Entangling", 3, 1, "expval", NOISE),
+])
+def test_frame_cluster_parity(precision, n, L, ct, B_I, B_P, typ, noise):
+    err = pc.case_model(n, L, ct, B_I, B_P, typ, noise, precision=precision)
+    assert err < pc.TOL[precision]
+
+
+@pytest.mark.parametrize("typ", ["expval", "probs", "density"])
+def test_config4_full_size_vs_oracle(typ):
+    """BASELINE config 4 itself - Model(8, 4, 'Strongly_Entangling'), depolarizing +
+    amplitude damping - on 2 inputs against the oracle at 1e-10."""
+    err = pc.case_model(8, 4, "Strongly_Entangling", 2, 1, typ, NOISE, precision="complex128")
+    assert err < 1e-10
+
+
+def test_frame_equals_streamed_strategy(monkeypatch):
+    """The same circuits through the HBM-streaming kernels (QMLB_FRAME=0) and the frame
+    engine: independent schedules, same numbers."""
+    rng = np.random.default_rng(3)
+
+    def run(n, L, ct, typ, noise, B):
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            m = Model(n, L, ct)
+            params = rng.uniform(0, 2 * np.pi, (B, *m._params_shape))
+            inputs = np.linspace(-1, 1, 3).reshape(3, 1)
+            return np.asarray(m(params=params, inputs=inputs, execution_type=typ,
+                                noise_params=dict(noise) if noise else None)), params
+
+    for n, L, ct, typ, noise in ((8, 2, "Strongly_Entangling", "expval", NOISE),
+                                 (14, 2, "Hardware_Efficient", "expval", None),
+                                 (10, 2, "Circuit_15", "probs", None)):
+        state = rng.bit_generator.state
+        a, _ = run(n, L, ct, typ, noise, 2)
+        rng.bit_generator.state = state
+        monkeypatch.setenv("QMLB_FRAME", "0")
+        b, _ = run(n, L, ct, typ, noise, 2)
+        monkeypatch.delenv("QMLB_FRAME")
+        assert np.abs(a - b).max() < 1e-10, (n, ct)
+
+
+def test_frame_engine_is_selected():
+    """Config 3 / config 4 programs are planned as strategy 3 on the device."""
+    ex = get_executor()
+    from qml_essentials_b200 import backend
+    import test_cabi
+
+    for n, L, ct, noise in ((6, 3, "Circuit_15", None), (8, 4, "Strongly_Entangling", NOISE)):
+        plan = test_cabi._plan_of(n, L, ct, "complex128", "expval", noise)
+        h = backend.ProgramHandle(ex.lib, plan.program, plan.out_type, plan.obs_recs,
+                                  plan.obs_pool, "complex128")
+        assert h.strategy == 3

@@ -40,6 +40,15 @@ def test_reference_kats_on_gpu():
         c, n_qubits=n, precision="complex64").execute(t, obs=o, args=args), atol=1e-5)
 
 
+def test_pennylane_convention_closed_forms_on_gpu():
+    """Closed forms of the circuits the reference compares with PennyLane
+    (tests/test_jaqsi.py:494-661): controlled gates, Rot, every 1-qubit channel."""
+    kat_cases.run_pennylane_conventions(lambda c, n, t, o, args=(): Script(
+        c, n_qubits=n).execute(t, obs=o, args=args), atol=1e-10)
+    kat_cases.run_pennylane_conventions(lambda c, n, t, o, args=(): Script(
+        c, n_qubits=n, precision="complex64").execute(t, obs=o, args=args), atol=1e-5)
+
+
 @pytest.mark.parametrize("precision", ["complex128", "complex64"])
 def test_every_gate_and_channel(precision):
     tol = pc.TOL[precision]

@@ -26,6 +26,10 @@ def test_reference_kats_through_product_host_path():
     kat_cases.run_all(_run)
 
 
+def test_pennylane_convention_closed_forms_through_product_host_path():
+    kat_cases.run_pennylane_conventions(_run, atol=1e-12)
+
+
 def test_parity_every_gate_and_channel():
     assert max(pc.case_every_gate().values()) < 1e-10
     assert max(pc.case_every_channel().values()) < 1e-10

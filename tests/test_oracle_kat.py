@@ -40,6 +40,12 @@ def test_oracle_passes_reference_kats():
     kat_cases.run_all(_oracle_run)
 
 
+def test_oracle_passes_pennylane_convention_closed_forms():
+    """reference tests/test_jaqsi.py:494-661 compare with PennyLane; its documented gate and
+    channel definitions give closed forms the oracle must reproduce (extra pin)."""
+    kat_cases.run_pennylane_conventions(_oracle_run, atol=1e-12)
+
+
 def test_golden_topologies_oracle_and_product():
     from qml_essentials_b200.topologies import Topology
 
