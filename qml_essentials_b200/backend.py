@@ -279,6 +279,30 @@ class CudaExecutor:
             return DeviceCall(self, self.handle_for(plan), self.to_device(host_args), batch,
                               batch_offset)
 
+    def peak_bytes(self, plan, host_args, batch: int) -> int:
+        """Exact device bytes of one launch over ``batch`` elements: the library's own
+        workspace figure (hoisted-factor tables, evaluated matrices, state, reduction
+        partials - ``qmlb_workspace_bytes``) plus the output and the uploaded arguments.
+        ``Script`` chunks on this instead of the arithmetic model of ``memory.py`` so that the
+        chunk size follows what the chosen kernel strategy really allocates."""
+        h = self.handle_for(plan)
+        c_args = (_Arg * max(len(host_args), 1))()
+        arg_bytes = 0
+        for i, a in enumerate(host_args):
+            if a is None:
+                c_args[i] = _Arg(None, 0, 1, 1)
+            else:
+                arr, div, mod = a
+                c_args[i] = _Arg(None, int(np.asarray(arr).shape[1]), int(div), int(mod))
+                arg_bytes += int(np.asarray(arr).size) * 8
+        ws = int(self.lib.qmlb_workspace_bytes(h.ptr, c_args, len(host_args), int(batch)))
+        elem = 16 if plan.precision == "complex128" else 8
+        dim = 2 ** plan.n_qubits
+        out = {compiler.OUT_STATE: dim * elem, compiler.OUT_PROBS: dim * elem // 2,
+               compiler.OUT_EXPVAL: max(h.n_obs, 1) * elem // 2,
+               compiler.OUT_DENSITY: dim * dim * elem}[h.out_type] * int(batch)
+        return ws + out + arg_bytes
+
     # -- Script-facing entry points -----------------------------------------------
     def execute(self, plan, host_args, batch: int, chunk: Optional[int] = None,
                 to_host: bool = True):

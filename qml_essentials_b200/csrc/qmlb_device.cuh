@@ -42,8 +42,16 @@ __device__ __forceinline__ cx<T> cadd(cx<T> a, cx<T> b) {
   return mk<T>(a.x + b.x, a.y + b.y);
 }
 
-__device__ __forceinline__ void sincos_t(double a, double* s, double* c) { sincos(a, s, c); }
-__device__ __forceinline__ void sincos_t(float a, float* s, float* c) { sincosf(a, s, c); }
+// sin / cos of an angle that is always formed in double (c0 + sum coeff * arg).  complex64:
+// the angle is reduced to [-pi, pi] in double BEFORE it is rounded to float - encodings
+// scale inputs by 2^q / 3^q (ansaetze.py:933-961), and a float32 angle of several hundred
+// radians carries an error of 1e-5 by itself.
+__device__ __forceinline__ void sincos_angle(double a, double* s, double* c) { sincos(a, s, c); }
+__device__ __forceinline__ void sincos_angle(double a, float* s, float* c) {
+  const double two_pi = 6.283185307179586476925286766559;
+  a = fma(-two_pi, rint(a * (1.0 / two_pi)), a);
+  sincosf((float)a, s, c);
+}
 
 // Register kernel: per op, the hoisted factors its 2x2 matrix is made of when the source
 // is one SRC_PRE or a chain of two (matrix = factor1 * factor0), else n = 0.
@@ -126,7 +134,7 @@ __device__ __forceinline__ void eval_elem2(const DevProg& P, const RunArgs& R,
                                            cx<T> m[4]) {
   if (s.kind == QMLB_SRC_TRIG) {
     T sn, cs;
-    sincos_t((T)(eval_angle(P, R, rows, s.angle) * s.kappa), &sn, &cs);
+    sincos_angle(eval_angle(P, R, rows, s.angle) * s.kappa, &sn, &cs);
     const int axis = (s.flags >> QMLB_FLAG_ROT_SHIFT) & 3;
     if (axis == 1) {  // RX
       m[0] = mk<T>(cs, 0); m[1] = mk<T>(0, -sn); m[2] = mk<T>(0, -sn); m[3] = mk<T>(cs, 0);
@@ -245,7 +253,7 @@ __device__ void eval_source_mem(const DevProg& P, const RunArgs& R, const Rows& 
         break;
       }
       T sn, cs;
-      sincos_t((T)(eval_angle(P, R, rows, s.angle) * s.kappa), &sn, &cs);
+      sincos_angle(eval_angle(P, R, rows, s.angle) * s.kappa, &sn, &cs);
       for (int i = 0; i < d * d; ++i) {
         cx<T> c0 = ld_const<T>(P.consts, s.a0 + i);
         cx<T> a = ld_const<T>(P.consts, s.a1 + i);
@@ -266,7 +274,7 @@ __device__ void eval_source_mem(const DevProg& P, const RunArgs& R, const Rows& 
       double th = eval_angle(P, R, rows, s.angle);
       for (int i = 0; i < d; ++i) {
         T sn, cs;
-        sincos_t((T)(-P.consts[s.a0 + i] * th), &sn, &cs);
+        sincos_angle(-P.consts[s.a0 + i] * th, &sn, &cs);
         out[i] = mk<T>(cs, sn);
       }
       break;

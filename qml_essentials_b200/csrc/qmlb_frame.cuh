@@ -56,20 +56,110 @@ __device__ __forceinline__ void frame_matk(RegState<T, FRAME_R>& S, const cx<T>*
   }
 }
 
+// ---- register-group updates -----------------------------------------------------------
+// SHAPE: QMLB_FSHAPE_FULL / _REAL (imaginary parts known to be zero) / _XREAL (4x4: only
+// v == u and v == u ^ 3, real).
+
+template <typename T, int BIT, int SHAPE>
+__device__ __forceinline__ void frame_mat1(RegState<T, FRAME_R>& S, const cx<T>* __restrict__ m) {
+  if constexpr (SHAPE == QMLB_FSHAPE_FULL) {
+    cx<T> mm[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) mm[i] = m[i];
+    reg_mat1<T, FRAME_R, BIT>(S, mm);
+  } else {
+    T r[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) r[i] = m[i].x;
+#pragma unroll
+    for (int g = 0; g < (1 << (FRAME_R - 1)); ++g) {
+      const int i0 = pair_i0<FRAME_R, BIT>(g), i1 = i0 | (1 << BIT);
+      const T ar = S.re(i0), ai = S.im(i0), br = S.re(i1), bi = S.im(i1);
+      S.re(i0) = r[0] * ar + r[1] * br;
+      S.im(i0) = r[0] * ai + r[1] * bi;
+      S.re(i1) = r[2] * ar + r[3] * br;
+      S.im(i1) = r[2] * ai + r[3] * bi;
+    }
+  }
+}
+
+template <typename T, int JA, int JB, int SHAPE>
+__device__ __forceinline__ void frame_mat2(RegState<T, FRAME_R>& S, const cx<T>* __restrict__ m) {
+  static_assert(JA > JB, "canonical order");
+  if constexpr (SHAPE == QMLB_FSHAPE_XREAL) {
+    // new[v] = d[v] * old[v] + e[v] * old[v ^ 3]
+    T d[4], e[4];
+#pragma unroll
+    for (int v = 0; v < 4; ++v) {
+      d[v] = m[v * 5].x;
+      e[v] = m[v * 4 + (v ^ 3)].x;
+    }
+#pragma unroll
+    for (int g = 0; g < (1 << (FRAME_R - 2)); ++g) {
+      const int t = ((g >> JB) << (JB + 1)) | (g & ((1 << JB) - 1));
+      const int i00 = ((t >> JA) << (JA + 1)) | (t & ((1 << JA) - 1));
+      const int idx[4] = {i00, i00 | (1 << JB), i00 | (1 << JA), i00 | (1 << JA) | (1 << JB)};
+      T ar[4], ai[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        ar[u] = S.re(idx[u]);
+        ai[u] = S.im(idx[u]);
+      }
+#pragma unroll
+      for (int v = 0; v < 4; ++v) {
+        S.re(idx[v]) = fma(d[v], ar[v], e[v] * ar[v ^ 3]);
+        S.im(idx[v]) = fma(d[v], ai[v], e[v] * ai[v ^ 3]);
+      }
+    }
+  } else {
+#pragma unroll
+    for (int g = 0; g < (1 << (FRAME_R - 2)); ++g) {
+      const int t = ((g >> JB) << (JB + 1)) | (g & ((1 << JB) - 1));
+      const int i00 = ((t >> JA) << (JA + 1)) | (t & ((1 << JA) - 1));
+      const int idx[4] = {i00, i00 | (1 << JB), i00 | (1 << JA), i00 | (1 << JA) | (1 << JB)};
+      T ar[4], ai[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        ar[u] = S.re(idx[u]);
+        ai[u] = S.im(idx[u]);
+      }
+#pragma unroll
+      for (int v = 0; v < 4; ++v) {
+        T xr = (T)0, xi = (T)0;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const cx<T> c = m[v * 4 + u];
+          xr = fma(c.x, ar[u], xr);
+          xi = fma(c.x, ai[u], xi);
+          if constexpr (SHAPE == QMLB_FSHAPE_FULL) {
+            xr = fma(-c.y, ai[u], xr);
+            xi = fma(c.y, ar[u], xi);
+          }
+        }
+        S.re(idx[v]) = xr;
+        S.im(idx[v]) = xi;
+      }
+    }
+  }
+}
+
 // 2x2 on register bit TB of the pairs whose control value is 1.  The control value of
 // slot i is ctl_base ^ bit i of smask (it never depends on the target bit itself).
 template <typename T, int TB>
-__device__ __forceinline__ void frame_ctrl1(RegState<T, FRAME_R>& S, const cx<T> (&m)[4],
+__device__ __forceinline__ void frame_ctrl1(RegState<T, FRAME_R>& S, const cx<T>* __restrict__ m,
                                             unsigned smask, int ctl_base) {
+  cx<T> mm[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) mm[i] = m[i];
 #pragma unroll
   for (int g = 0; g < (1 << (FRAME_R - 1)); ++g) {
     const int i0 = pair_i0<FRAME_R, TB>(g), i1 = i0 | (1 << TB);
     const bool on = (((smask >> i0) & 1u) ^ (unsigned)ctl_base) != 0u;
     const T ar = S.re(i0), ai = S.im(i0), br = S.re(i1), bi = S.im(i1);
-    const T xr = m[0].x * ar - m[0].y * ai + m[1].x * br - m[1].y * bi;
-    const T xi = m[0].x * ai + m[0].y * ar + m[1].x * bi + m[1].y * br;
-    const T yr = m[2].x * ar - m[2].y * ai + m[3].x * br - m[3].y * bi;
-    const T yi = m[2].x * ai + m[2].y * ar + m[3].x * bi + m[3].y * br;
+    const T xr = mm[0].x * ar - mm[0].y * ai + mm[1].x * br - mm[1].y * bi;
+    const T xi = mm[0].x * ai + mm[0].y * ar + mm[1].x * bi + mm[1].y * br;
+    const T yr = mm[2].x * ar - mm[2].y * ai + mm[3].x * br - mm[3].y * bi;
+    const T yi = mm[2].x * ai + mm[2].y * ar + mm[3].x * bi + mm[3].y * br;
     S.re(i0) = on ? xr : ar;
     S.im(i0) = on ? xi : ai;
     S.re(i1) = on ? yr : br;
@@ -77,10 +167,143 @@ __device__ __forceinline__ void frame_ctrl1(RegState<T, FRAME_R>& S, const cx<T>
   }
 }
 
+
+// ---- items of a SUBPASS ------------------------------------------------------------------
+// The parity rows of the register bits tell which logical value slot 0 of an item holds
+// (c_j = parity(base & rloc_j) ^ parity(rank & rout_j)).  eoff is linear in the slot number,
+// so starting the item at base ^ eoff[c] instead makes slot v hold logical value v exactly:
+// every matrix is then read with plain compile-time entry offsets.
+__device__ __forceinline__ uint32_t frame_item_base(const FrameStep& st, uint32_t it,
+                                                    const uint32_t (&piv)[FRAME_R], unsigned rank) {
+  uint32_t base = frame_deposit(it, piv);
+  int c = 0;
+#pragma unroll
+  for (int j = 0; j < FRAME_R; ++j)
+    c |= ((__popc(base & st.par[j].rloc) ^ __popc(rank & st.par[j].rout)) & 1) << j;
+  return base ^ st.eoff[c];
+}
+
+template <typename T>
+__device__ __forceinline__ void frame_load(RegState<T, FRAME_R>& S, const cx<T>* tile,
+                                           uint32_t base, const FrameStep& st) {
+#pragma unroll
+  for (int v = 0; v < FRAME_D; ++v) {
+    const cx<T> a = tile[base ^ st.eoff[v]];
+    S.re(v) = a.x;
+    S.im(v) = a.y;
+  }
+}
+
+template <typename T>
+__device__ __forceinline__ void frame_store(RegState<T, FRAME_R>& S, cx<T>* tile, uint32_t base,
+                                            const FrameStep& st) {
+#pragma unroll
+  for (int v = 0; v < FRAME_D; ++v) tile[base ^ st.eoff[v]] = mk<T>(S.re(v), S.im(v));
+}
+
+// fast path: at most one 4x4 on register pair (1,0) (shape SA) and one on (3,2) (shape SB);
+// -1 = absent.  Straight-line code: no op decoding, no dispatch inside the item loop.
+template <typename T, int SA, int SB>
+__device__ __noinline__ void frame_items_d2(cx<T>* tile, const cx<T>* mats, const FrameStep& st,
+                                            unsigned rank, uint32_t tlane, uint32_t tsize,
+                                            uint32_t n_items) {
+  uint32_t piv[FRAME_R];
+#pragma unroll
+  for (int j = 0; j < FRAME_R; ++j) piv[j] = st.pivots[j];
+  const cx<T>* ma = mats + st.foff[0];
+  const cx<T>* mb = mats + st.foff[1];
+  for (uint32_t it = tlane; it < n_items; it += tsize) {
+    const uint32_t base = frame_item_base(st, it, piv, rank);
+    RegState<T, FRAME_R> S;
+    frame_load<T>(S, tile, base, st);
+    if constexpr (SA >= 0) frame_mat2<T, 1, 0, SA>(S, ma);
+    if constexpr (SB >= 0) frame_mat2<T, 3, 2, SB>(S, mb);
+    frame_store<T>(S, tile, base, st);
+  }
+}
+
+// fast path: only 2x2 ops, at most one per register bit (MASK)
+template <typename T, int MASK, bool REAL>
+__device__ __noinline__ void frame_items_m1(cx<T>* tile, const cx<T>* mats, const FrameStep& st,
+                                            unsigned rank, uint32_t tlane, uint32_t tsize,
+                                            uint32_t n_items) {
+  constexpr int SH = REAL ? QMLB_FSHAPE_REAL : QMLB_FSHAPE_FULL;
+  uint32_t piv[FRAME_R];
+#pragma unroll
+  for (int j = 0; j < FRAME_R; ++j) piv[j] = st.pivots[j];
+  for (uint32_t it = tlane; it < n_items; it += tsize) {
+    const uint32_t base = frame_item_base(st, it, piv, rank);
+    RegState<T, FRAME_R> S;
+    frame_load<T>(S, tile, base, st);
+    if constexpr (MASK & 1) frame_mat1<T, 0, SH>(S, mats + st.foff[0]);
+    if constexpr (MASK & 2) frame_mat1<T, 1, SH>(S, mats + st.foff[1]);
+    if constexpr (MASK & 4) frame_mat1<T, 2, SH>(S, mats + st.foff[2]);
+    if constexpr (MASK & 8) frame_mat1<T, 3, SH>(S, mats + st.foff[3]);
+    frame_store<T>(S, tile, base, st);
+  }
+}
+
+template <typename T, int I = 0>
+__device__ __forceinline__ void frame_dispatch_d2(int code, cx<T>* tile, const cx<T>* mats,
+                                                  const FrameStep& st, unsigned rank,
+                                                  uint32_t tlane, uint32_t tsize, uint32_t n) {
+  if constexpr (I < 16) {
+    if (code == I) {
+      if constexpr (I > 0) frame_items_d2<T, (I >> 2) - 1, (I & 3) - 1>(tile, mats, st, rank, tlane, tsize, n);
+    } else {
+      frame_dispatch_d2<T, I + 1>(code, tile, mats, st, rank, tlane, tsize, n);
+    }
+  }
+}
+
+template <typename T, int I = 1>
+__device__ __forceinline__ void frame_dispatch_m1(int code, cx<T>* tile, const cx<T>* mats,
+                                                  const FrameStep& st, unsigned rank,
+                                                  uint32_t tlane, uint32_t tsize, uint32_t n) {
+  if constexpr (I < 32) {
+    if (code == I) {
+      if constexpr ((I & 15) != 0)
+        frame_items_m1<T, (I & 15), (I >> 4) != 0>(tile, mats, st, rank, tlane, tsize, n);
+    } else {
+      frame_dispatch_m1<T, I + 1>(code, tile, mats, st, rank, tlane, tsize, n);
+    }
+  }
+}
+
+// RELAYOUT gather: destination d of this thread <- source (rank, index) through the GF(2)
+// map; PER amplitudes per thread held in registers across the cluster barrier
+template <typename T, int PER, typename Cluster>
+__device__ __forceinline__ void frame_relayout(cx<T>* tile, Cluster& cluster, bool clustered,
+                                               unsigned rank, int Tb, int team_bits, int tlane,
+                                               uint32_t cmine, const uint32_t* tab_lo,
+                                               const uint32_t* tab_hi) {
+  using V = typename std::conditional<sizeof(T) == 8, double2, float2>::type;  // one access
+  const uint32_t tile_mask = (1u << Tb) - 1u;
+  V* tv = reinterpret_cast<V*>(tile);
+  V hold[PER];
+#pragma unroll
+  for (int k = 0; k < PER; ++k) {
+    const uint32_t d = (uint32_t)tlane + ((uint32_t)k << team_bits);
+    const uint32_t src = cmine ^ tab_lo[d & 255u] ^ tab_hi[d >> 8];
+    const uint32_t r = src >> Tb, loc = src & tile_mask;
+    const V* from = tv;
+    if (clustered && r != rank) from = cluster.map_shared_rank(tv, r);
+    hold[k] = from[loc];
+  }
+  if (clustered)
+    cluster.sync();
+  else
+    __syncthreads();
+#pragma unroll
+  for (int k = 0; k < PER; ++k) tv[(uint32_t)tlane + ((uint32_t)k << team_bits)] = hold[k];
+}
+
 // HEAVY = the program holds a dense op on 3 or 4 bits (rare: 2-qubit channels, CCX as a
 // matrix); the lean variant keeps the register pressure of the common steps low.
-template <typename T, int THREADS, bool HEAVY>
-__global__ void __launch_bounds__(THREADS, THREADS == 512 ? 1 : 2)
+// WIDE = one CTA per SM even at 256 threads (255 registers per thread: two items per thread
+// without spills when the tile fills the CTA's shared memory anyway).
+template <typename T, int THREADS, bool HEAVY, bool WIDE = false>
+__global__ void __launch_bounds__(THREADS, (THREADS == 512 || WIDE) ? 1 : 2)
     k_frame(DevProg P, RunArgs A, const FrameProg F, const cx<T>* __restrict__ premats,
             void* __restrict__ out) {
   extern __shared__ __align__(16) unsigned char fsm[];
@@ -125,6 +348,8 @@ __global__ void __launch_bounds__(THREADS, THREADS == 512 ? 1 : 2)
     // |0..0>: the frame is linear, so logical index 0 sits at physical index 0
     for (uint32_t i = tlane; i < tile_n; i += tsize)
       tile[i] = mk<T>((i == 0 && rank == 0) ? (T)1 : (T)0, (T)0);
+    if (F.mat_resident)  // every matrix of this element, once
+      for (int i = tlane; i < F.premat_row; i += tsize) mats[i] = prow[i];
     for (int i = threadIdx.x; i < 256; i += THREADS)
       reinterpret_cast<uint32_t*>(&sstep[0])[i] =
           reinterpret_cast<const uint32_t*>(&F.steps[0])[i];
@@ -155,138 +380,110 @@ __global__ void __launch_bounds__(THREADS, THREADS == 512 ? 1 : 2)
         uint32_t cmine = 0;
         for (int g = 0; g < F.outer_bits; ++g)
           if (rank >> g & 1) cmine ^= (uint32_t)st.qcol[Tb + g];
-        sync_all();  // tables visible; every CTA of the cluster has finished its previous step
-        constexpr int PER = sizeof(T) == 8 ? 16 : 32;
+        const bool across = clustered && st.mat_entries == 0;  // else a tile-local shuffle
+        if (across)
+          cluster.sync();  // tables visible; every CTA of the cluster finished its previous step
+        else
+          __syncthreads();
         const int per = (int)(tile_n >> F.team_bits);
-        cx<T> hold[PER];
-#pragma unroll
-        for (int k = 0; k < PER; ++k) {
-          if (k < per) {
-            const uint32_t d = (uint32_t)tlane + ((uint32_t)k << F.team_bits);
-            const uint32_t src = cmine ^ tab_lo[d & 255u] ^ tab_hi[d >> 8];
-            const uint32_t r = src >> Tb, loc = src & (tile_n - 1u);
-            const cx<T>* from = tile;
-            if (clustered && r != rank) from = cluster.map_shared_rank(tile, r);
-            hold[k] = from[loc];
-          }
-        }
-        sync_all();
-#pragma unroll
-        for (int k = 0; k < PER; ++k)
-          if (k < per) tile[(uint32_t)tlane + ((uint32_t)k << F.team_bits)] = hold[k];
-        sync_all();
+        if (per == 16)
+          frame_relayout<T, 16>(tile, cluster, across, rank, Tb, F.team_bits, tlane, cmine,
+                                tab_lo, tab_hi);
+        else
+          frame_relayout<T, 32>(tile, cluster, across, rank, Tb, F.team_bits, tlane, cmine,
+                                tab_lo, tab_hi);
+        __syncthreads();  // the next reader of this tile is this CTA (or a later relayout)
         continue;
       }
 
-      // ---- SUBPASS: matrices (with their XOR variants) into shared memory -----------------
-      if (valid) {
-        for (int o = 0; o < st.n_ops; ++o) {
-          const FrameOp fo = st.ops[o];
-          cx<T>* dst = mats + fo.smem_off;
-          const cx<T>* srcm = prow + fo.premat_off;
-          if (fo.code == QMLB_FOP_DIAG) {
-            for (int e = tlane; e < (1 << fo.k); e += tsize) dst[e] = srcm[e];
-            ++o;  // parity-row indices
-          } else if (fo.code == QMLB_FOP_MATK) {
-            for (int e = tlane; e < (1 << (2 * fo.k)); e += tsize) dst[e] = srcm[e];
-          } else {
-            const int k = (fo.code == QMLB_FOP_MAT2) ? 2 : 1, dd = 1 << k, ee = dd * dd;
-            for (int e = tlane; e < ee * fo.nvar; e += tsize) {
-              const int c = e / ee, idx = e % ee;
-              int v = (idx >> k) ^ c, u = (idx & (dd - 1)) ^ c;
-              if (fo.flags & 1) {  // logical (bits[0], bits[1]) sit at register bits (j1, j0)
-                v = ((v & 1) << 1) | (v >> 1);
-                u = ((u & 1) << 1) | (u >> 1);
-              }
-              dst[e] = srcm[v * dd + u];
-            }
+      // ---- SUBPASS ------------------------------------------------------------------------
+      if (!F.mat_resident) {  // stage the matrices of this step
+        if (valid)
+          for (int o = 0; o < st.n_ops; ++o) {
+            const FrameOp fo = st.ops[o];
+            const int n = fo.code == QMLB_FOP_DIAG ? (1 << fo.k) : (1 << (2 * fo.k));
+            for (int e = tlane; e < n; e += tsize) mats[fo.smem_off + e] = prow[fo.premat_off + e];
+            if (fo.code == QMLB_FOP_DIAG) ++o;
           }
-        }
+        __syncthreads();
       }
-      __syncthreads();
 
-      if (valid) {
+      if (valid && !HEAVY && st.fast >= 64) {
+        frame_dispatch_m1<T>(st.fast - 64, tile, mats, st, rank, tlane, tsize, n_items);
+      } else if (valid && !HEAVY && st.fast >= 16) {
+        frame_dispatch_d2<T>(st.fast - 16, tile, mats, st, rank, tlane, tsize, n_items);
+      } else if (valid) {
         uint32_t piv[FRAME_R];
 #pragma unroll
         for (int j = 0; j < FRAME_R; ++j) piv[j] = st.pivots[j];
         for (uint32_t it = tlane; it < n_items; it += tsize) {
-          const uint32_t base = frame_deposit(it, piv);
+          const uint32_t base = frame_item_base(st, it, piv, rank);
           RegState<T, FRAME_R> S;
-#pragma unroll
-          for (int v = 0; v < FRAME_D; ++v) {
-            const cx<T> a = tile[base ^ st.eoff[v]];
-            S.re(v) = a.x;
-            S.im(v) = a.y;
-          }
-          int cj[FRAME_R];
-#pragma unroll
-          for (int j = 0; j < FRAME_R; ++j)
-            cj[j] = (__popc(base & st.par[j].rloc) ^ __popc(rank & st.par[j].rout)) & 1;
+          frame_load<T>(S, tile, base, st);
           auto parity_at = [&](int pi) -> int {
             return (__popc(base & st.par[pi].rloc) ^ __popc(rank & st.par[pi].rout)) & 1;
           };
-
 #pragma unroll 1
           for (int o = 0; o < st.n_ops; ++o) {
             const FrameOp fo = st.ops[o];
             const cx<T>* m = mats + fo.smem_off;
             switch (fo.code) {
-              case QMLB_FOP_MAT1: {
-                cx<T> mm[4];
+              case QMLB_FOP_MAT1:
                 dispatch1<T, FRAME_R>(fo.j0, [&](auto B) {
                   constexpr int BIT = decltype(B)::value;
-                  const cx<T>* mv = m + (fo.nvar > 1 ? 4 * cj[BIT] : 0);
-#pragma unroll
-                  for (int i = 0; i < 4; ++i) mm[i] = mv[i];
-                  reg_mat1<T, FRAME_R, BIT>(S, mm);
+                  if (fo.shape != QMLB_FSHAPE_FULL)
+                    frame_mat1<T, BIT, QMLB_FSHAPE_REAL>(S, m);
+                  else
+                    frame_mat1<T, BIT, QMLB_FSHAPE_FULL>(S, m);
                 });
                 break;
-              }
-              case QMLB_FOP_MAT2:
-                dispatch2<T, FRAME_R>(fo.j0, fo.j1, [&](auto JA, auto JB) {
+              case QMLB_FOP_MAT2: {
+                auto on_pair = [&](auto JA, auto JB) {
                   constexpr int A_ = decltype(JA)::value, B_ = decltype(JB)::value;
                   if constexpr (A_ > B_) {
-                    const int c = fo.nvar > 1 ? ((cj[A_] << 1) | cj[B_]) : 0;
-                    reg_mat2<T, FRAME_R, A_, B_>(S, m + 16 * c);
+                    if (fo.shape == QMLB_FSHAPE_XREAL)
+                      frame_mat2<T, A_, B_, QMLB_FSHAPE_XREAL>(S, m);
+                    else if (fo.shape == QMLB_FSHAPE_REAL)
+                      frame_mat2<T, A_, B_, QMLB_FSHAPE_REAL>(S, m);
+                    else
+                      frame_mat2<T, A_, B_, QMLB_FSHAPE_FULL>(S, m);
                   }
-                });
-                break;
-              case QMLB_FOP_MATK: if constexpr (HEAVY) {
-                int c = 0;
-#pragma unroll
-                for (int j = 0; j < FRAME_R; ++j)
-                  if (j < fo.k) c |= cj[j] << j;
-                if (fo.k == 3)
-                  frame_matk<T, 3>(S, m, c);
+                };
+                // the planner seats 2-bit ops on the register pairs (3,2) / (1,0)
+                if (fo.j0 == 3 && fo.j1 == 2)
+                  on_pair(std::integral_constant<int, 3>{}, std::integral_constant<int, 2>{});
+                else if (fo.j0 == 1 && fo.j1 == 0)
+                  on_pair(std::integral_constant<int, 1>{}, std::integral_constant<int, 0>{});
                 else
-                  frame_matk<T, 4>(S, m, c);
-              } break;
+                  dispatch2<T, FRAME_R>(fo.j0, fo.j1, on_pair);
+                break;
+              }
+              case QMLB_FOP_MATK:
+                if constexpr (HEAVY) {
+                  if (fo.k == 3)
+                    frame_matk<T, 3>(S, m, 0);
+                  else
+                    frame_matk<T, 4>(S, m, 0);
+                }
+                break;
               case QMLB_FOP_CTRL1: {
-                cx<T> mm[4];
                 const int ctl = parity_at(fo.j1);
                 const unsigned sm = st.par[fo.j1].smask;
                 dispatch1<T, FRAME_R>(fo.j0, [&](auto B) {
                   constexpr int BIT = decltype(B)::value;
-                  const cx<T>* mv = m + (fo.nvar > 1 ? 4 * cj[BIT] : 0);
-#pragma unroll
-                  for (int i = 0; i < 4; ++i) mm[i] = mv[i];
-                  frame_ctrl1<T, BIT>(S, mm, sm, ctl);
+                  frame_ctrl1<T, BIT>(S, m, sm, ctl);
                 });
                 break;
               }
               case QMLB_FOP_DIAG: {
                 const uint8_t* idx = reinterpret_cast<const uint8_t*>(&st.ops[o + 1]);
-                int lb = 0;        // local value of slot 0
-                unsigned flip[8];  // per op bit: which slots see it flipped
-                for (int a = 0; a < fo.k; ++a) {
-                  lb |= parity_at(idx[a]) << (fo.k - 1 - a);
-                  flip[a] = st.par[idx[a]].smask;
-                }
+                int lb = 0;  // local value of slot 0
+                for (int a = 0; a < fo.k; ++a) lb |= parity_at(idx[a]) << (fo.k - 1 - a);
 #pragma unroll
                 for (int v = 0; v < FRAME_D; ++v) {
                   int loc = lb;
                   for (int a = 0; a < fo.k; ++a)
-                    loc ^= (int)((flip[a] >> v) & 1u) << (fo.k - 1 - a);
+                    loc ^= (int)((st.par[idx[a]].smask >> v) & 1u) << (fo.k - 1 - a);
                   const cx<T> d = m[loc];
                   const T r = S.re(v), q = S.im(v);
                   S.re(v) = d.x * r - d.y * q;
@@ -298,8 +495,7 @@ __global__ void __launch_bounds__(THREADS, THREADS == 512 ? 1 : 2)
             }
           }
 
-#pragma unroll
-          for (int v = 0; v < FRAME_D; ++v) tile[base ^ st.eoff[v]] = mk<T>(S.re(v), S.im(v));
+          frame_store<T>(S, tile, base, st);
         }
       }
       __syncthreads();

@@ -4,10 +4,10 @@
 
 namespace qmlb {
 
-template <int THREADS, bool HEAVY>
+template <int THREADS, bool HEAVY, bool WIDE = false>
 static cudaError_t launch_frame_t(const qmlb_program* p, const RunArgs& R, const FrameProg& F,
                                   const cx<QMLB_T>* premats, void* out, cudaStream_t st) {
-  auto kern = k_frame<QMLB_T, THREADS, HEAVY>;
+  auto kern = k_frame<QMLB_T, THREADS, HEAVY, WIDE>;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -62,6 +62,8 @@ cudaError_t QMLB_LAUNCH_FRAME(const qmlb_program* p, const RunArgs& R, const voi
     if (p->frame_threads == 128) return launch_frame_t<128, true>(p, R, F, pm, out, st);
   } else {
     if (p->frame_threads == 512) return launch_frame_t<512, false>(p, R, F, pm, out, st);
+    if (p->frame_threads == 256 && F.teams == 1 && F.tile_bits >= 13)
+      return launch_frame_t<256, false, true>(p, R, F, pm, out, st);
     if (p->frame_threads == 256) return launch_frame_t<256, false>(p, R, F, pm, out, st);
     if (p->frame_threads == 128) return launch_frame_t<128, false>(p, R, F, pm, out, st);
   }

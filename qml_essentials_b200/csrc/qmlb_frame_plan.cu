@@ -2,6 +2,7 @@
 // SUBPASS / RELAYOUT steps (qmlb_frame_types.h).  Pure host code - no CUDA call - so the
 // CPU test-suite can check every schedule through qmlb_plan_describe.
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -120,14 +121,85 @@ void fold_into(Frame& F, const qmlb_op& o, const OpInfo& f) {
   }
 }
 
+// Structure of a matrix source that the host can prove without evaluating angles.
+// real: every entry has zero imaginary part; xshape (4x4): only entries with v == u or
+// v == (u ^ 3) are non-zero (the 1-qubit Pauli / damping channels on (ket, bra)).
+struct Shape {
+  bool real = false, xshape = false;
+};
+
+bool const_block(const qmlb_program* p, int off, int n, bool* real, bool* xshape, int d) {
+  *real = true;
+  *xshape = d == 4;
+  for (int i = 0; i < n; ++i) {
+    const double re = p->consts[2 * (size_t)(off + i)], im = p->consts[2 * (size_t)(off + i) + 1];
+    if (im != 0.0) *real = false;
+    if (d == 4 && (re != 0.0 || im != 0.0)) {
+      const int v = i >> 2, u = i & 3;
+      if (v != u && v != (u ^ 3)) *xshape = false;
+    }
+  }
+  return true;
+}
+
+Shape shape_of(const qmlb_program* p, int sid, int depth = 0) {
+  Shape out;
+  if (depth > 4) return out;
+  const qmlb_source& s = p->sources[sid];
+  const int d = 1 << s.k;
+  switch (s.kind) {
+    case QMLB_SRC_CONST: {
+      if (s.flags & QMLB_FLAG_DIAGVEC) return out;
+      bool r, x;
+      const_block(p, s.a0, d * d, &r, &x, d);
+      out.real = r;
+      out.xshape = r && x && s.k == 2;
+      return out;
+    }
+    case QMLB_SRC_TRIG: {
+      const int axis = (s.flags >> QMLB_FLAG_ROT_SHIFT) & 3;
+      if (s.k == 1 && axis != 0) {
+        out.real = axis == 2;  // RY
+        return out;
+      }
+      bool r0, r1, r2, x;
+      const_block(p, s.a0, d * d, &r0, &x, 0);
+      const_block(p, s.a1, d * d, &r1, &x, 0);
+      const_block(p, s.a2, d * d, &r2, &x, 0);
+      out.real = r0 && r1 && r2;
+      return out;
+    }
+    case QMLB_SRC_PRE:
+      return shape_of(p, p->pre[s.a2].src, depth + 1);
+    case QMLB_SRC_CHAIN:
+    case QMLB_SRC_SUPER: {
+      out.real = true;
+      out.xshape = s.kind == QMLB_SRC_SUPER;
+      for (int t = 0; t < s.a1; ++t) {
+        const int id = p->items[s.a0 + t];
+        const Shape it = shape_of(p, id, depth + 1);
+        out.real = out.real && it.real;
+        // U (x) conj(U) of a 2x2 is X-shaped only for diagonal / anti-diagonal U: not tracked
+        out.xshape = out.xshape && it.xshape && p->sources[id].k == 2;
+      }
+      out.xshape = out.xshape && out.real;
+      return out;
+    }
+    default:
+      return out;
+  }
+}
+
 struct Builder {
   qmlb_program* p;
   std::vector<OpInfo> info;
   std::vector<char> done;
-  std::vector<int> premat_off;  // per program op
+  std::vector<int> premat_off;     // per program op
+  std::vector<int> matlist_index;  // per program op: its entry in p->stream_matlist
   Frame F;
   int N, T, G;
   int mat_cap;
+  bool resident = false;   // matrices of the whole element stay in shared memory
   std::vector<FrameStep> steps;
   std::vector<std::vector<int>> step_ops;  // program-op indices per step (describe)
 
@@ -163,6 +235,62 @@ struct Builder {
     steps.push_back(s);
     step_ops.emplace_back();
     F.set_permutation(pos);
+  }
+
+  // Layout change to the permutation frame `pos`.  Across a cluster it is split so that the
+  // distributed-shared-memory traffic is COALESCED: (A) a tile-local shuffle undoes the
+  // folded linear maps and parks the bits that leave next to where the arriving bits will
+  // sit, (B) a pure exchange of bit POSITIONS between cluster rank and tile - consecutive
+  // destinations then read consecutive remote addresses (runs of 2^t amplitudes).
+  void relayout_to(const std::vector<int>& want, bool exact) {
+    if (G == 0) {
+      emit_relayout(want);
+      steps.back().mat_entries = 1;
+      return;
+    }
+    std::vector<int> victims, incoming;
+    for (int j = 0; j < N; ++j) {
+      if (!F.outer(j) && want[j] >= T) victims.push_back(j);
+      if (F.outer(j) && want[j] < T) incoming.push_back(j);
+    }
+    // (B) lands the arriving bits on the TOP tile positions: the other tile bits keep their
+    // relative order below them
+    std::vector<int> posB(want);
+    {
+      std::vector<int> tile_bits;
+      for (int j = 0; j < N; ++j)
+        if (want[j] < T) tile_bits.push_back(j);
+      auto is_in = [&](int j) {
+        return std::find(incoming.begin(), incoming.end(), j) != incoming.end();
+      };
+      std::stable_sort(tile_bits.begin(), tile_bits.end(), [&](int a2, int b2) {
+        if (is_in(a2) != is_in(b2)) return is_in(b2);  // arriving bits last = highest
+        return want[a2] < want[b2];
+      });
+      for (size_t r = 0; r < tile_bits.size(); ++r) posB[tile_bits[r]] = (int)r;
+    }
+    std::vector<int> posA(posB);
+    for (int j = 0; j < N; ++j)
+      if (F.outer(j)) posA[j] = top_bit(F.col[j]);  // outer bits stay where they are
+    for (size_t i = 0; i < victims.size() && i < incoming.size(); ++i)
+      posA[victims[i]] = posB[incoming[i]];
+    auto differs = [&](const std::vector<int>& x, const std::vector<int>& y) {
+      for (int j = 0; j < N; ++j)
+        if (x[j] != y[j]) return true;
+      return false;
+    };
+    bool local_needed = false;
+    for (int j = 0; j < N; ++j)
+      if (F.col[j] != (1ull << posA[j])) local_needed = true;
+    if (local_needed) {
+      emit_relayout(posA);
+      steps.back().mat_entries = 1;  // tile-local: CTA barriers suffice
+    }
+    if (differs(posA, posB)) emit_relayout(posB);
+    if (exact && differs(posB, want)) {
+      emit_relayout(want);
+      steps.back().mat_entries = 1;
+    }
   }
 
   int run();
@@ -219,10 +347,7 @@ bool Builder::build_step() {
       ok = FRAME_R + (int)par_try.size() <= FRAME_MAX_PAR;
     }
     const int need_slots = o.kind == QMLB_OP_DIAG ? 2 : 1;
-    int var = 1;
-    if (o.kind == QMLB_OP_MAT && o.k <= 2) var = 1 << o.k;
-    if (o.kind == QMLB_OP_CTRL1) var = 2;
-    const int e = f.entries * var;
+    const int e = resident ? 0 : f.entries;
     if (ok) ok = slots + need_slots <= FRAME_MAX_OPS && entries + e <= mat_cap;
     if (!ok) {
       blocked |= f.bits;
@@ -242,6 +367,17 @@ bool Builder::build_step() {
     // bits outside the group, highest mask first so the lanes keep the low addresses)
     std::vector<int> gb(pinned);
     auto in_gb = [&](int j) { return std::find(gb.begin(), gb.end(), j) != gb.end(); };
+    // 2-bit ops first, each on an adjacent register pair (1,0) / (3,2) in its own bit
+    // order: the kernel's fast path for the (ket, bra) superoperators of density programs
+    if (gb.empty())
+      for (int i : picked) {
+        const qmlb_op& o = p->ops[i];
+        if (o.kind != QMLB_OP_MAT || o.k != 2) continue;
+        const bool a = in_gb(o.bits[0]), b = in_gb(o.bits[1]);
+        if (a || b || (gb.size() & 1) || gb.size() + 2 > (size_t)FRAME_R) continue;
+        gb.push_back(o.bits[1]);  // least significant local bit on the lower register bit
+        gb.push_back(o.bits[0]);
+      }
     for (int j = 0; j < N; ++j)
       if ((S >> j & 1) && !in_gb(j)) gb.push_back(j);
     {
@@ -326,30 +462,37 @@ bool Builder::build_step() {
       std::memset(&fo, 0, sizeof(fo));
       fo.k = (uint8_t)o.k;
       fo.premat_off = premat_off[i];
-      fo.smem_off = used;
-      fo.nvar = 1;
+      fo.smem_off = resident ? premat_off[i] : used;
+      if (o.kind != QMLB_OP_DIAG) {
+        const Shape sh = shape_of(p, o.src);
+        fo.shape = sh.xshape && o.kind == QMLB_OP_MAT && o.k == 2
+                       ? QMLB_FSHAPE_XREAL
+                       : (sh.real ? QMLB_FSHAPE_REAL : QMLB_FSHAPE_FULL);
+      }
       if (o.kind == QMLB_OP_MAT && o.k == 1) {
         fo.code = QMLB_FOP_MAT1;
         fo.j0 = (uint8_t)regpos[o.bits[0]];
-        if (has_c(fo.j0)) fo.nvar = 2;
+        fo.has_c = has_c(fo.j0);
       } else if (o.kind == QMLB_OP_MAT && o.k == 2) {
         fo.code = QMLB_FOP_MAT2;
         const int p0 = regpos[o.bits[0]], p1 = regpos[o.bits[1]];
         fo.j0 = (uint8_t)std::max(p0, p1);
         fo.j1 = (uint8_t)std::min(p0, p1);
         fo.flags = p0 < p1 ? 1 : 0;
-        if (has_c(fo.j0) || has_c(fo.j1)) fo.nvar = 4;
+        fo.has_c = has_c(fo.j0) || has_c(fo.j1);
+        // the evaluated matrix is stored with the roles of its two bits already swapped
+        p->stream_matlist[matlist_index[i]].swap2 = fo.flags & 1;
       } else if (o.kind == QMLB_OP_MAT) {
         fo.code = QMLB_FOP_MATK;
       } else if (o.kind == QMLB_OP_CTRL1) {
         fo.code = QMLB_FOP_CTRL1;
         fo.j0 = (uint8_t)regpos[o.bits[1]];
         fo.j1 = (uint8_t)par_index(o.bits[0]);
-        if (has_c(fo.j0)) fo.nvar = 2;
+        fo.has_c = has_c(fo.j0);
       } else {
         fo.code = QMLB_FOP_DIAG;
       }
-      used += info[i].entries * fo.nvar;
+      used += info[i].entries;
       s.ops[slot++] = fo;
       if (o.kind == QMLB_OP_DIAG) {
         FrameOp aux;
@@ -363,6 +506,38 @@ bool Builder::build_step() {
     }
     s.n_ops = slot;
     s.mat_entries = used;
+    // fast-path classification (see FrameStep::fast)
+    {
+      bool d2 = true, m1 = true, all_real = true;
+      int sA = -1, sB = -1, mask = 0;
+      for (int o = 0; o < slot; ++o) {
+        const FrameOp& fo = s.ops[o];
+        if (fo.code == QMLB_FOP_MAT2 && fo.j0 == 1 && fo.j1 == 0 && sA < 0) {
+          sA = fo.shape;
+          s.foff[0] = fo.smem_off;
+        } else if (fo.code == QMLB_FOP_MAT2 && fo.j0 == 3 && fo.j1 == 2 && sB < 0) {
+          sB = fo.shape;
+          s.foff[1] = fo.smem_off;
+        } else {
+          d2 = false;
+        }
+        if (fo.code == QMLB_FOP_MAT1 && !(mask >> fo.j0 & 1)) {
+          mask |= 1 << fo.j0;
+          all_real = all_real && fo.shape != QMLB_FSHAPE_FULL;
+        } else {
+          m1 = false;
+        }
+      }
+      if (d2 && slot > 0) {
+        s.fast = 16 + 4 * (sA + 1) + (sB + 1);
+      } else if (m1 && slot > 0) {
+        s.fast = 64 + 16 * (all_real ? 1 : 0) + mask;
+        for (int o = 0; o < slot; ++o) s.foff[s.ops[o].j0] = s.ops[o].smem_off;
+      } else {
+        s.fast = 0;
+        for (int j = 0; j < 4; ++j) s.foff[j] = 0;
+      }
+    }
     steps.push_back(s);
     step_ops.push_back(ops_of_step);
   }
@@ -393,7 +568,7 @@ int Builder::run() {
       for (int j = 0; j < N; ++j)
         if (F.col[j] != (1ull << pos[j])) same = false;
       if (same || ++guard > 4096) return QMLB_ERR_UNSUPPORTED;
-      emit_relayout(pos);
+      relayout_to(pos, false);
     }
     remaining = count_left();
   }
@@ -404,7 +579,7 @@ int Builder::run() {
   if (!ident) {
     std::vector<int> pos(N);
     for (int j = 0; j < N; ++j) pos[j] = j;
-    emit_relayout(pos);
+    relayout_to(pos, true);
   }
   return QMLB_OK;
 }
@@ -428,42 +603,64 @@ int plan_frame(qmlb_program* p) {
   // geometry
   int threads, team_bits, teams;
   if (B.T - FRAME_R >= 8) {
-    threads = B.T >= 13 ? 512 : 256;
-    team_bits = B.T >= 13 ? 9 : 8;
+    // one item per thread; QMLB_FRAME_THREADS=256: two items per thread at 255 registers
+    const char* ev = std::getenv("QMLB_FRAME_THREADS");
+    const bool wide = B.T >= 13 && !(ev && std::atoi(ev) == 256);
+    threads = wide ? 512 : 256;
+    team_bits = wide ? 9 : 8;
     teams = 1;
   } else {
     threads = 256;
     team_bits = B.T - FRAME_R;
     teams = threads >> team_bits;
   }
-  int biggest = 1;
+  // evaluated matrices of one element (premat row): every gate op, program order
+  int row = 0, biggest = 1;
   for (size_t i = 0; i < p->ops.size(); ++i) {
-    const qmlb_op& o = p->ops[i];
-    int var = 1;
-    if (o.kind == QMLB_OP_MAT && o.k <= 2) var = 1 << o.k;
-    if (o.kind == QMLB_OP_CTRL1) var = 2;
-    biggest = std::max(biggest, B.info[i].entries * var);
+    if (p->ops[i].kind == QMLB_OP_PERM) continue;
+    row += B.info[i].entries;
+    biggest = std::max(biggest, B.info[i].entries);
   }
-  const size_t budget = 200 * 1024;
+  // Shared memory: [tiles | matrices | step records, tables].  Preferred: the element's
+  // whole row of matrices stays resident (one copy per element, no per-step staging);
+  // else a per-step staging area.
+  const size_t budget = 216 * 1024;
+  const size_t fixed = 2 * sizeof(FrameStep) + (256 + 64) * sizeof(uint32_t) + 64 * sizeof(double);
   const size_t tile_bytes = (size_t(1) << B.T) * cs;
-  int cap = teams == 1 ? 1024 : 96;
-  cap = std::max(cap, biggest);
-  while (teams > 1 && (size_t)teams * (tile_bytes + (size_t)cap * cs) + 4096 > budget) teams >>= 1;
-  if ((size_t)teams * (tile_bytes + (size_t)cap * cs) + 4096 > budget) {
-    cap = (int)((budget - 4096 - tile_bytes) / cs);
-    if (cap < biggest) return QMLB_ERR_UNSUPPORTED;
+  auto fits = [&](int tm, int cap) {
+    return (size_t)tm * (tile_bytes + (size_t)cap * cs) + fixed <= budget;
+  };
+  int cap = std::max(row, 1);
+  bool resident = true;
+  if (!fits(teams, cap)) {
+    int tm = teams;
+    while (tm > 1 && (tm << team_bits) > 128 && !fits(tm, cap)) tm >>= 1;
+    if (fits(tm, cap)) {
+      teams = tm;
+    } else {
+      resident = false;
+      cap = std::max(biggest, teams == 1 ? 1024 : 96);
+      while (teams > 1 && !fits(teams, cap)) teams >>= 1;
+      if (!fits(teams, cap)) {
+        cap = (int)((budget - fixed - tile_bytes) / cs);
+        if (cap < biggest) return QMLB_ERR_UNSUPPORTED;
+      }
+    }
   }
-  if (teams > 1) threads = teams << team_bits;
+  if (teams > 1 || team_bits < 8) threads = teams << team_bits;
   if (threads < 32) return QMLB_ERR_UNSUPPORTED;
   B.mat_cap = cap;
+  B.resident = resident;
 
   // evaluated matrices of one element: every gate op, program order
   B.premat_off.assign(p->ops.size(), 0);
+  B.matlist_index.assign(p->ops.size(), -1);
   p->stream_matlist.clear();
-  int row = 0;
+  row = 0;
   for (size_t i = 0; i < p->ops.size(); ++i) {
     if (p->ops[i].kind == QMLB_OP_PERM) continue;
     B.premat_off[i] = row;
+    B.matlist_index[i] = (int)p->stream_matlist.size();
     StreamMatOp mo{};
     mo.src = p->ops[i].src;
     mo.off = row;
@@ -486,6 +683,7 @@ int plan_frame(qmlb_program* p) {
   fp.team_bits = team_bits;
   fp.teams = teams;
   fp.mat_cap = cap;
+  fp.mat_resident = resident ? 1 : 0;
   fp.premat_row = row;
   fp.density = p->density;
   fp.n_qubits = p->n_qubits;
@@ -495,8 +693,7 @@ int plan_frame(qmlb_program* p) {
   for (const qmlb_op& o : p->ops)
     if (o.kind == QMLB_OP_MAT && o.k >= 3) p->frame_heavy = true;
   // [tiles | matrices | 2 step records | relayout tables | reduction scratch]
-  p->frame_smem = (size_t)teams * (tile_bytes + (size_t)cap * cs) + 2 * sizeof(FrameStep) +
-                  (256 + 64) * sizeof(uint32_t) + 64 * sizeof(double);
+  p->frame_smem = (size_t)teams * (tile_bytes + (size_t)cap * cs) + fixed;
   return QMLB_OK;
 }
 
@@ -506,17 +703,18 @@ std::string describe_frame(const qmlb_program* p) {
   s += "frame tile_bits " + std::to_string(fp.tile_bits) + " outer_bits " +
        std::to_string(fp.outer_bits) + " team_bits " + std::to_string(fp.team_bits) +
        " teams " + std::to_string(fp.teams) + " threads " + std::to_string(p->frame_threads) +
-       " mat_cap " + std::to_string(fp.mat_cap) + " premat_row " + std::to_string(fp.premat_row) +
+       " mat_cap " + std::to_string(fp.mat_cap) + " resident " + std::to_string(fp.mat_resident) +
+       " premat_row " + std::to_string(fp.premat_row) +
        " smem " + std::to_string(p->frame_smem) + "\n";
   for (size_t i = 0; i < p->frame_steps.size(); ++i) {
     const FrameStep& st = p->frame_steps[i];
     if (st.kind == QMLB_FSTEP_RELAYOUT) {
-      s += "relayout";
+      s += st.mat_entries ? "relayout local" : "relayout";
       for (int b = 0; b < fp.n_bits; ++b) s += " " + std::to_string((unsigned long long)st.qcol[b]);
       s += "\n";
       continue;
     }
-    s += "subpass pivots";
+    s += "subpass fast " + std::to_string(st.fast) + " pivots";
     for (int j = 0; j < FRAME_R; ++j) s += " " + std::to_string(st.pivots[j]);
     s += " eoff";
     for (int v = 0; v < FRAME_D; ++v) s += " " + std::to_string(st.eoff[v]);
@@ -530,8 +728,9 @@ std::string describe_frame(const qmlb_program* p) {
       const FrameOp& fo = st.ops[o];
       s += " " + std::to_string(p->frame_step_ops[i][t++]) + ":" + std::to_string(fo.code) + ":" +
            std::to_string(fo.k) + ":" + std::to_string(fo.j0) + ":" + std::to_string(fo.j1) + ":" +
-           std::to_string(fo.nvar) + ":" + std::to_string(fo.flags) + ":" +
-           std::to_string(fo.premat_off) + ":" + std::to_string(fo.smem_off);
+           std::to_string(fo.has_c) + ":" + std::to_string(fo.flags) + ":" +
+           std::to_string(fo.premat_off) + ":" + std::to_string(fo.smem_off) + ":" +
+           std::to_string(fo.shape);
       if (fo.code == QMLB_FOP_DIAG) {
         const uint8_t* idx = reinterpret_cast<const uint8_t*>(&st.ops[o + 1]);
         s += ":";

@@ -19,8 +19,9 @@
 // the logical value of bit j at address p is parity(p & row_j(A^-1)).  A register group is
 // therefore described by its masks (eoff = all XOR combinations), the pivot positions of
 // the span of the masks (items enumerate the indices that are zero there) and the parity
-// rows; when a parity row reaches outside the group the item sees the gate with its local
-// value XOR c, which is looked up as one of 2^k pre-permuted matrix VARIANTS.
+// rows; when a parity row reaches outside the group, slot 0 of an item would hold local
+// value c instead of 0 - the item then simply starts at base ^ eoff[c] (eoff is linear in
+// the slot number), after which slot v holds logical value v for every item.
 #pragma once
 #include <stdint.h>
 
@@ -41,12 +42,17 @@ constexpr int FRAME_MAX_BITS = 40;
 #define QMLB_FOP_CTRL1 3  // 2x2 on register bit j0 where parity row j1 reads 1
 #define QMLB_FOP_DIAG 4   // diagonal over k parity rows (their indices sit in the next slot)
 
+#define QMLB_FSHAPE_FULL 0   // general complex matrix
+#define QMLB_FSHAPE_REAL 1   // every entry real (RY chains, Pauli channels): half the FMAs
+#define QMLB_FSHAPE_XREAL 2  // 4x4, real, only v == u and v == u ^ 3 (depolarizing, flips, damping)
+
 struct FrameOp {           // 16 bytes
   uint8_t code, k, j0, j1;
-  uint16_t nvar;           // matrix variants in shared memory: 1 or 2^k
+  uint8_t shape;           // QMLB_FSHAPE_*: structure known at plan time
+  uint8_t has_c;           // some register bit of the op can see a flipped local value
   uint16_t flags;          // bit 0: MAT2 whose two logical bits sit in reversed register order
   int32_t premat_off;      // offset of the op's matrix in the element's row of evaluated matrices
-  int32_t smem_off;        // offset (complex entries) in the step's matrix area
+  int32_t smem_off;        // offset (complex entries) of the matrix in shared memory
 };
 
 // logical bit value at physical index (outer, local) of slot v of an item:
@@ -57,7 +63,7 @@ struct FramePar {
 };
 
 struct FrameStep {  // 1024 bytes, loaded into shared memory by the CTA that runs it
-  int32_t kind, n_ops, mat_entries, n_par;
+  int32_t kind, n_ops, mat_entries, n_par;  // RELAYOUT: mat_entries = 1 -> tile-local shuffle
   uint32_t pivots[FRAME_R];           // ascending: items have zeros at these tile positions
   uint32_t eoff[FRAME_D];             // slot v lives at tile index base ^ eoff[v]
   FramePar par[FRAME_MAX_PAR];
@@ -65,7 +71,16 @@ struct FrameStep {  // 1024 bytes, loaded into shared memory by the CTA that run
   // RELAYOUT: the amplitude that ends at physical index d comes from physical index
   // XOR of qcol[b] over the set bits b of d (bits >= tile_bits select the CTA of the cluster)
   uint64_t qcol[FRAME_MAX_BITS];
-  int32_t pad[8];
+  // SUBPASS fast paths (straight-line item bodies, no op interpreter):
+  //   fast = 16 + 4 * (sA + 1) + (sB + 1): at most one 4x4 on register pair (1,0) with shape
+  //          sA and one on (3,2) with shape sB (-1 = absent); foff[0] / foff[1] = their
+  //          matrix offsets
+  //   fast = 64 + 16 * real + mask: only 2x2 ops, at most one per register bit (mask), all
+  //          real (1) or treated as full (0); foff[j] = matrix offset of the op on bit j
+  //   fast = 0: generic interpreter
+  int32_t fast;
+  int32_t foff[4];
+  uint32_t eoffb_unused[3];
 };
 static_assert(sizeof(FrameStep) == 1024, "FrameStep is loaded as 256 words");
 
@@ -78,6 +93,7 @@ struct FrameProg {
   int32_t team_bits;   // log2(threads working on one tile)
   int32_t teams;       // tiles per CTA (1 when the CTA or cluster holds one state)
   int32_t mat_cap;     // matrix entries per team in shared memory
+  int32_t mat_resident;  // 1: the element's whole row of matrices is staged once per element
   int32_t premat_row;  // evaluated-matrix entries per element
   int32_t out_mode;    // 0: complex state in index order, 1: probabilities, 2: Z-string expvals
   int32_t density, n_qubits, n_obs;

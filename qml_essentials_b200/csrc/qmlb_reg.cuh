@@ -341,7 +341,7 @@ __global__ void __launch_bounds__(128, reg_min_ctas<T, N>()) k_reg(DevProg P, Ru
 #pragma unroll
         for (int i = 0; i < D; ++i) {
           T sn, cs;
-          sincos_t((T)(-P.consts[s.a0 + i] * th), &sn, &cs);
+          sincos_angle(-P.consts[s.a0 + i] * th, &sn, &cs);
           const T r = S.re(i), q = S.im(i);
           S.re(i) = cs * r - sn * q;
           S.im(i) = cs * q + sn * r;
@@ -365,9 +365,9 @@ __global__ void __launch_bounds__(128, reg_min_ctas<T, N>()) k_reg(DevProg P, Ru
       if (s.kind == QMLB_SRC_DIAGPH) {
         const double th = eval_angle(P, R, rows, s.angle);
         T sn, cs;
-        sincos_t((T)(-P.consts[s.a0] * th), &sn, &cs);
+        sincos_angle(-P.consts[s.a0] * th, &sn, &cs);
         m[0] = mk<T>(cs, sn);
-        sincos_t((T)(-P.consts[s.a0 + 1] * th), &sn, &cs);
+        sincos_angle(-P.consts[s.a0 + 1] * th, &sn, &cs);
         m[3] = mk<T>(cs, sn);
       } else {
         m[0] = ld_const<T>(P.consts, s.a0);

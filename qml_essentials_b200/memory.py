@@ -12,6 +12,12 @@ chip, otherwise in one HBM buffer that is the output itself for ``state`` /
 
 and the budget is the free HBM of the current device (180 GB on a B200) instead
 of ``psutil`` host memory.  Everything is plain integer arithmetic.
+
+The figure is an UPPER bound that does not know which kernel strategy the library will
+plan: besides the state it budgets the per-element table of evaluated gate matrices the
+batched on-chip / streaming kernels keep (``n_ops`` matrices of up to 4x4 entries).
+``Script`` itself chunks on the exact number the library reports
+(``qmlb_workspace_bytes`` through ``CudaExecutor.peak_bytes``).
 """
 
 from __future__ import annotations
@@ -28,8 +34,9 @@ log = logging.getLogger(__name__)
 # kept for interface compatibility (memory.py:23); there are no JIT caches to clear
 CLEAR_CACHES_BETWEEN_CHUNKS: bool = False
 
-# a state up to this size is evolved entirely in shared memory / registers
-ON_CHIP_STATE_BYTES = 160 * 1024
+# a statevector of at most this many qubits is evolved in registers by one thread
+# (qmlb_reg.cuh) and never touches a workspace when the result is reduced in registers
+REGISTER_QUBITS = 5
 _SAFETY = 1.1
 
 
@@ -76,12 +83,13 @@ def estimate_peak_bytes(
     out = _output_bytes(type, batch_size, dim, elem, real_elem, n_obs)
     evolves_density = bool(use_density)
     st = state_bytes(n_qubits, evolves_density, elem)
-    if st <= ON_CHIP_STATE_BYTES:
-        work = 0
-    elif (type == "density" and evolves_density) or (type == "state" and not evolves_density):
-        work = 0  # evolved in place inside the output buffer
+    in_place = (type == "density" and evolves_density) or (type == "state" and not evolves_density)
+    if not evolves_density and n_qubits <= REGISTER_QUBITS and type != "density":
+        work = 0  # registers; <Z>, probabilities and the state are written directly
     else:
-        work = batch_size * st
+        # evaluated matrices per element (<= 4x4 complex per op) + the state unless the
+        # output buffer is the state
+        work = batch_size * (max(n_ops, 1) * 16 * elem + (0 if in_place else st))
     return int((out + work) * _SAFETY)
 
 

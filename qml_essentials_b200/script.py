@@ -416,14 +416,30 @@ class Script:
         return out
 
     # -- execution ----------------------------------------------------------------
-    def _chunk_size(self, cache_key, plan: _Plan, type: str, n_obs: int, batch: int) -> int:
-        """Largest chunk that fits in HBM, memoised per batch size (script.py:331-356)."""
+    def _chunk_size(self, cache_key, plan: _Plan, type: str, n_obs: int, batch: int,
+                    ex=None, host_args=None) -> int:
+        """Largest chunk that fits in HBM, memoised per batch size (script.py:331-356).
+        With a device executor the figure is exact (the library reports the workspace of
+        the strategy it planned); the arithmetic model of ``memory.py`` is the fallback."""
         mem_key = ("_mem", cache_key, batch)
         chunk = self._jit_cache.get(mem_key)
         if chunk is None:
-            chunk = memory.compute_chunk_size(
-                plan.n_qubits, batch, type, plan.density_program, n_obs, n_ops=plan.n_ops
-            )
+            if ex is not None and hasattr(ex, "peak_bytes") and host_args is not None:
+                avail = int(memory.available_memory_bytes() * 0.8)
+                full = ex.peak_bytes(plan, host_args, batch)
+                if full <= avail:
+                    chunk = batch
+                else:
+                    probe = min(batch, 1024)
+                    per = max(1, -(-ex.peak_bytes(plan, host_args, probe) // probe))
+                    chunk = int(max(1, min(batch, avail // per)))
+                    memory.log.info(
+                        f"Computation requires ~{full / 1024**3:.2f} GB which does not fit in "
+                        f"~{avail / 1024**3:.2f} GB. Using chunk size {chunk}.")
+            else:
+                chunk = memory.compute_chunk_size(
+                    plan.n_qubits, batch, type, plan.density_program, n_obs, n_ops=plan.n_ops
+                )
             self._jit_cache[mem_key] = chunk
         return chunk
 
@@ -450,7 +466,7 @@ class Script:
         ex = self.executor or get_executor()
         host_args = self._device_args(plan, args, in_axes, batch)
         chunk = self._chunk_size(cache_key, plan, "probs" if for_shots else type,
-                                 len(obs), batch)
+                                 len(obs), batch, ex, host_args)
         if for_shots:
             keys = rng.split(key, batch)  # script.py:481
             uniforms = rng.choice_uniforms(keys, int(shots))

@@ -27,7 +27,8 @@ def parse(text):
     for line in lines[2:]:
         tok = line.split()
         if tok[0] == "relayout":
-            steps.append(("relayout", [int(x) for x in tok[1:]]))
+            local = tok[1] == "local"
+            steps.append(("relayout", [int(x) for x in tok[(2 if local else 1):]], local))
             continue
         assert tok[0] == "subpass"
         ip, ie, ipar, io = (tok.index(k) for k in ("pivots", "eoff", "par", "ops"))
@@ -37,12 +38,29 @@ def parse(text):
         ops = []
         for ent in tok[io + 1:]:
             f = ent.split(":")
-            rec = dict(zip(("index", "code", "k", "j0", "j1", "nvar", "flags", "premat_off",
-                            "smem_off"), (int(x) for x in f[:9])))
-            rec["idx"] = [int(x) for x in f[9].split(",")] if len(f) > 9 else []
+            rec = dict(zip(("index", "code", "k", "j0", "j1", "has_c", "flags", "premat_off",
+                            "smem_off", "shape"), (int(x) for x in f[:10])))
+            rec["idx"] = [int(x) for x in f[10].split(",")] if len(f) > 10 else []
             ops.append(rec)
-        steps.append(("subpass", piv, eoff, par, ops))
+        steps.append(("subpass", piv, eoff, par, ops, int(tok[tok.index("fast") + 1])))
     return geo, steps
+
+
+def _check_fast(fast, ops):
+    """The kernel's straight-line item bodies must describe exactly the ops of the step."""
+    if fast >= 64:
+        real, mask = (fast - 64) >> 4, (fast - 64) & 15
+        assert all(o["code"] == FOP_MAT1 for o in ops)
+        assert sorted(o["j0"] for o in ops) == [j for j in range(4) if mask >> j & 1]
+        assert not real or all(o["shape"] >= 1 for o in ops)
+    elif fast >= 16:
+        sa, sb = ((fast - 16) >> 2) - 1, ((fast - 16) & 3) - 1
+        want = {(1, 0): sa, (3, 2): sb}
+        assert all(o["code"] == FOP_MAT2 for o in ops) and len(ops) <= 2
+        got = {(o["j0"], o["j1"]): o["shape"] for o in ops}
+        assert got == {k: v for k, v in want.items() if v >= 0}
+    else:
+        assert fast == 0
 
 
 def _deposit(w, piv):
@@ -87,9 +105,16 @@ def emulate(prog, text, args, batch):
             for b in range(N):
                 src ^= np.where((d >> b) & 1, qcol[b], 0)
             assert np.array_equal(np.sort(src), d), "relayout is not a permutation"
+            if step[2]:
+                assert np.array_equal(src >> T, d >> T), "tile-local shuffle crosses CTAs"
+            elif G > 0:
+                # exchange of bit positions: 32 consecutive destinations read 32 consecutive
+                # sources (coalesced distributed-shared-memory traffic)
+                assert np.array_equal(src & 31, d & 31), "cluster exchange is not coalesced"
             st = st[:, src]
             continue
-        _, piv, eoff, par, ops = step
+        _, piv, eoff, par, ops, fast = step
+        _check_fast(fast, ops)
         assert sorted(piv) == piv and len(set(piv)) == R
         base = _deposit(items.copy(), piv)
         assert base.max() <= tile_mask
@@ -98,20 +123,37 @@ def emulate(prog, text, args, batch):
         for rank in range(1 << G):
             slots = (rank << T) | (base[:, None] ^ np.asarray(eoff, dtype=np.int64)[None, :])
             np.add.at(touched, slots.ravel(), 1)
-            S = new[:, slots]  # (batch, items, 16)
 
             def par_at(pi_):
                 rloc, rout, _ = par[pi_]
                 return _parity(base & rloc) ^ (bin(rank & rout).count("1") & 1)
 
+            # slot 0 would hold local value c: start the item at base ^ eoff[c] instead
+            c0 = sum(par_at(j) << j for j in range(R))
+            ebase = base ^ np.asarray(eoff, dtype=np.int64)[c0]
+            slots = (rank << T) | (ebase[:, None] ^ np.asarray(eoff, dtype=np.int64)[None, :])
+            S = new[:, slots]
+
+            def par_at(pi_, _b=ebase):  # noqa: F811  (parities of the shifted item base)
+                rloc, rout, _ = par[pi_]
+                return _parity(_b & rloc) ^ (bin(rank & rout).count("1") & 1)
+
             cj = [par_at(j) for j in range(R)]
+            assert not any(c.any() for c in cj), "shifted items must see unflipped values"
             for o in ops:
                 M = matrix(o["index"])
                 code, k = o["code"], o["k"]
+                if o["shape"] >= 1:  # the planner's structural claims about the matrix
+                    assert np.abs(M.imag).max() == 0.0, "matrix claimed real"
+                if o["shape"] == 2:
+                    for v in range(4):
+                        for u in range(4):
+                            if v != u and v != (u ^ 3):
+                                assert np.abs(M[:, v, u]).max() == 0.0, "matrix claimed X-shaped"
                 if code == FOP_MAT1:
                     j = o["j0"]
-                    c = cj[j] if o["nvar"] > 1 else np.zeros_like(base)
-                    assert o["nvar"] > 1 or not cj[j].any()
+                    c = cj[j]
+                    assert o["has_c"] or not cj[j].any()
                     out = S.copy()
                     for v in range(D):
                         lv = ((v >> j) & 1) ^ c
@@ -123,8 +165,8 @@ def emulate(prog, text, args, batch):
                 elif code == FOP_MAT2:
                     ja, jb = o["j0"], o["j1"]
                     assert ja > jb
-                    c = ((cj[ja] << 1) | cj[jb]) if o["nvar"] > 1 else np.zeros_like(base)
-                    assert o["nvar"] > 1 or not (cj[ja].any() or cj[jb].any())
+                    c = (cj[ja] << 1) | cj[jb]
+                    assert o["has_c"] or not c.any()
 
                     def sw(x):
                         return ((x & 1) << 1) | (x >> 1) if o["flags"] & 1 else x
@@ -151,7 +193,8 @@ def emulate(prog, text, args, batch):
                     S = out
                 elif code == FOP_CTRL1:
                     j = o["j0"]
-                    c = cj[j] if o["nvar"] > 1 else np.zeros_like(base)
+                    c = cj[j]
+                    assert o["has_c"] or not c.any()
                     ctl = par_at(o["j1"])
                     sm = par[o["j1"]][2]
                     out = S.copy()

@@ -108,8 +108,10 @@ def test_stream_scheduler_invariants(lib, n, L, ct, precision, noise):
     op it shares a bit with (qmlb_plan_describe, host only)."""
     plan = _plan_of(n, L, ct, precision, "expval", noise)
     prog = plan.program
+    # states of up to 2^17 amplitudes are planned for the on-chip frame engine; the streamed
+    # scheduler (what larger states and the qubit-sharded path use) is forced here
     text = backend.plan_describe(lib, prog, plan.out_type, plan.obs_recs, plan.obs_pool,
-                                 precision)
+                                 precision, flags=backend.QMLB_DESC_FORCE_STREAM)
     lines = text.strip().split("\n")
     assert lines[0] == "strategy 2"
     R = 4
@@ -151,9 +153,10 @@ def test_stream_scheduler_invariants(lib, n, L, ct, precision, noise):
 
 
 def test_plan_strategies_by_size(lib):
-    """n <= 5 -> registers, mid sizes -> shared memory, beyond -> streamed passes; the
-    force flag used by the qubit-sharded path always streams."""
-    for n, want in ((4, 0), (9, 1), (16, 2)):
+    """n <= 5 -> registers, up to 2^16 (c128) / 2^17 (c64) amplitudes -> on-chip frame
+    engine (one CTA or a cluster), beyond -> streamed passes; the force flag used by the
+    qubit-sharded path always streams."""
+    for n, want in ((4, 0), (9, 3), (16, 3), (18, 2)):
         plan = _plan_of(n, 1, "Hardware_Efficient", "complex128")
         text = backend.plan_describe(lib, plan.program, plan.out_type, plan.obs_recs,
                                      plan.obs_pool, "complex128")

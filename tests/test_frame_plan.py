@@ -74,12 +74,18 @@ def test_cluster_schedules(lib, n, L, ct, typ, noise, precision):
 
 def test_config4_schedule_shape(lib):
     """BASELINE config 4 (8 qubits, 4 layers, depolarizing + amplitude damping): 472 tape
-    ops -> at most 100 sub-passes and 12 cluster exchanges; every CX is folded (no
-    permutation op reaches the kernel)."""
+    ops -> at most 100 sub-passes and 12 coalesced cluster exchanges (each preceded by a
+    tile-local shuffle); every CX is folded (no permutation op reaches the kernel)."""
     ex, err = _both(lib, 8, 4, "Strongly_Entangling", "expval", NOISE, B_I=1, B_P=1)
     geo, steps = fe.parse(ex.steps[0])
     assert (geo["tile_bits"], geo["outer_bits"], geo["threads"]) == (13, 3, 512)
     n_sub = sum(1 for s in steps if s[0] == "subpass")
-    n_rel = sum(1 for s in steps if s[0] == "relayout")
-    assert n_sub <= 100 and n_rel <= 12
+    n_exch = sum(1 for s in steps if s[0] == "relayout" and not s[2])
+    n_local = sum(1 for s in steps if s[0] == "relayout" and s[2])
+    assert n_sub <= 100 and n_exch <= 12 and n_local <= 14
+    # every (ket, bra) superoperator sits on a canonical register pair (kernel fast path)
+    for s in steps:
+        if s[0] == "subpass":
+            assert all((o["j0"], o["j1"]) in ((3, 2), (1, 0)) for o in s[4] if o["code"] == 1)
+            assert s[5] >= 16  # straight-line fast path
     assert err < 1e-12

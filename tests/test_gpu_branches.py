@@ -183,3 +183,26 @@ def test_stream_kernel_with_64bit_indices():
     assert r.returncode == 0, r.stderr[-2000:]
     errs = [float(v) for v in r.stdout.split("ERRS")[1].split()]
     assert errs[0] < 1e-5 and errs[1] < 1e-10 and errs[2] < 1e-10, errs
+
+
+@pytest.mark.parametrize("typ", ["expval", "probs", "state", "density"])
+def test_memory_model_bounds_the_library_workspace(typ):
+    """ADVICE r1 (memory.py): the arithmetic estimate must not fall below what the library
+    allocates for the strategy it planned - mid-size states live in a workspace whenever
+    the result is not the evolved state itself."""
+    import test_cabi
+    from qml_essentials_b200 import backend, memory
+
+    ex = get_executor()
+    for n in (6, 8, 10, 12, 13, 15):
+        plan = test_cabi._plan_of(n, 1, "Hardware_Efficient", "complex128", typ)
+        if typ == "density" and n > 10:
+            continue
+        h = ex.handle_for(plan)
+        batch = 1000
+        args = (backend._Arg * 4)()
+        for i in range(4):
+            args[i] = backend._Arg(None, 0, 1, batch)
+        ws = ex.lib.qmlb_workspace_bytes(h.ptr, args, 4, batch)
+        est = memory.estimate_peak_bytes(n, batch, typ, False, n_obs=n, n_ops=plan.n_ops)
+        assert est >= ws, (n, typ, est, ws)

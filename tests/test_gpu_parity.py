@@ -128,8 +128,12 @@ def test_chunked_equals_full_on_device(monkeypatch):
         x = np.linspace(-1, 1, 37)
         full = m(inputs=x, execution_type="density")
         m2 = Model(4, 2, "Circuit_19")
-        monkeypatch.setattr(memory, "compute_chunk_size", lambda *a, **k: 10)
+        # Script chunks on the library's exact workspace figure (CudaExecutor.peak_bytes):
+        # pretend the device has 60 kB free -> about 10 elements per chunk
+        monkeypatch.setattr(memory, "available_memory_bytes", lambda: 60_000)
         assert np.array_equal(full, m2(inputs=x, execution_type="density"))
+        chunks = [v for k, v in m2.script._jit_cache.items() if k[0] == "_mem"]
+        assert chunks and 1 <= chunks[0] < 37
 
 
 def test_full_size_cfg2_invariants_and_sample_parity():
