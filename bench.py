@@ -2,26 +2,29 @@
 circuit evals/sec, batched).
 
 Workload (BASELINE.json configs[1], SURVEY.md section 8(d) cfg 2, grid B "dense"):
-``Model(n_qubits=4, n_layers=4, "Hardware_Efficient")``, expval on all 4 qubits,
-1024 parameter samples (NumPy default_rng(1000), uniform[0, 2pi)) x a 264-point
-input grid (``Coefficients._fourier_transform`` with mfs=8) = 270 336 circuit
-evaluations per step, complex128.
+``Coefficients.get_spectrum`` on ``Model(n_qubits=4, n_layers=4, "Hardware_Efficient")``,
+expval on all 4 qubits, 1024 parameter samples (NumPy default_rng(1000), uniform[0, 2pi)) x a
+264-point input grid (``mfs=8``) = 270 336 circuit evaluations per step, complex128.
+
+A STEP (identical at every GPU count) = the circuit kernels (k_pre x2, k_reg) over the batch
+resident in HBM, the grid DFT (k_grid_dft: mean over qubits + transform, what get_spectrum
+returns) and the FCC sufficient statistics over the samples (k_coef_moments); with N > 1 the
+statistics (a few KB) cross ranks in a one-shot all-reduce over peer-mapped symmetric memory
+(k_allreduce_oneshot) - no library collective inside the step.
 
 One JSON line on stdout (rank 0):
-  value     evals/s with params/inputs resident in HBM (kernel launches only, CUDA events)
-  e2e       evals/s through Model.__call__ with host NumPy arrays: H2D of params+inputs
-            and D2H of the (264, 1024, 4) float64 result inside the timed region
-  roofline  dominant kernel (k_reg<double,4>) against the FP64 FMA peak measured on the
-            same GPU by qmlb_fma_peak (MEASURED_PEAKS.json has no FMA figure)
-  cpu_baseline  the reference-faithful CPU restatement (oracle, one batched einsum per
-            tape op, torch-CPU complex128, all host threads) on a bounded sample
-``--impl reference`` times only that CPU restatement (the reference itself needs JAX,
+  value     evals/s of the step, arguments resident in HBM (CUDA events, graph replay)
+  e2e       evals/s through Coefficients.get_spectrum(model, mfs=8, ...) with host NumPy
+            params / grid in and the host coefficient array out (H2D + D2H in the timed region)
+  roofline  dominant kernel (k_reg<double,4>) against the FP64 FMA peak measured on the same
+            GPU by qmlb_fma_peak (MEASURED_PEAKS.json has no FMA figure)
+  cpu_baseline  the reference-faithful CPU restatement (oracle: one batched einsum per tape
+            op, torch-CPU complex128, all host threads, + numpy FFT) on the same workload
+  config_1 / config_3 / config_4   device-resident evals/s of the other small-n BASELINE
+            configs (k_reg, k_frame single-CTA, k_frame cluster)
+  gate_pass config 5 at n = 32 (k_fstream tile passes): HBM GB/s per pass, s per circuit
+``--impl reference`` times only the CPU restatement (the reference itself needs JAX,
 which this image does not have - DESIGN.md).
-
-Multi-GPU (torchrun): weak scaling - every rank evaluates its own 1024 parameter
-samples (independent circuits, no data-path collective), then one small NCCL
-all-reduce of the per-frequency coefficient statistics (sum and sum of squares of
-the 264-point mean-expval signal), which is what FCC averages need.
 """
 
 from __future__ import annotations
@@ -39,6 +42,9 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+WORKLOAD = ("BASELINE configs[1] / SURVEY 8(d) cfg2 grid B: Coefficients.get_spectrum on "
+            "Model(4,4,'Hardware_Efficient'), expval on 4 qubits, 1024 param samples "
+            "(default_rng(1000+rank)) x 264-point input grid per GPU")
 N_QUBITS, N_LAYERS, ANSATZ = 4, 4, "Hardware_Efficient"
 N_PARAM_SAMPLES, MFS = 1024, 8
 ALGO_FLOP_PER_EVAL = 26624  # 76 one-qubit + 20 CX dense gates, n = 4
@@ -91,8 +97,9 @@ class ClockSampler(threading.Thread):
 
 
 def oracle_cpu_evals_per_s(params, inputs, n_param_sample, threads, repeats=2):
-    """Reference-faithful CPU restatement on a bounded sample: all grid points x
-    `n_param_sample` parameter sets, one batched einsum per tape op (torch-CPU)."""
+    """Reference-faithful CPU restatement: all grid points x `n_param_sample` parameter
+    sets, one batched einsum per tape op (torch-CPU), <Z_q> and the grid FFT of
+    Coefficients._fourier_transform (numpy) - the whole get_spectrum workload."""
     from oracle import circuits as oc
     from oracle import sim as osim
 
@@ -110,6 +117,7 @@ def oracle_cpu_evals_per_s(params, inputs, n_param_sample, threads, repeats=2):
         pt = probs.reshape((B,) + (2,) * N_QUBITS)
         ev = np.stack([pt.sum(axis=tuple(a + 1 for a in range(N_QUBITS) if a != q))
                        @ np.array([1.0, -1.0]) for q in range(N_QUBITS)], axis=1)
+        np.fft.fft(ev.reshape(B_I, B_P, N_QUBITS).mean(axis=2), axis=0)  # coefficients.py:135
         dt = time.perf_counter() - t0
         best = dt if best is None else min(best, dt)
     return B / best, ev.reshape(B_I, B_P, N_QUBITS), f"{B_I} grid points x {B_P} param sets"
@@ -163,7 +171,12 @@ def gate_pass_leg(ex, n_qubits, reps, dev):
                 "state_gib": state_bytes / 2 ** 30, "passes": passes,
                 "device_ops": handle.n_device_ops, "ms_per_circuit": ms,
                 "ms_per_pass": ms / passes, "bytes_per_pass": 2 * state_bytes,
-                "achieved_gbs": algo_bytes / (ms * 1e-3) / 1e9, "kernel": "k_stream<float,5>",
+                "achieved_gbs": algo_bytes / (ms * 1e-3) / 1e9,
+                "kernel": {4: "k_fstream<float> (2^13-amplitude tiles, TMA bulk copies, CX "
+                              "folded into the frame)",
+                           2: "k_stream<float,4,lean> (4-bit register groups)"}.get(
+                               handle.strategy, f"strategy {handle.strategy}"),
+                "strategy": handle.strategy,
                 "checks": {"abs_expval_le_1": norm_ok, "repeatable": same}}
     finally:
         config.set_precision(prev)
@@ -207,6 +220,101 @@ def sharded_leg(world, rank, local_bits=30):
         config.set_precision(prev)
 
 
+class _Spy:
+    """Captures the (plan, host arguments, batch) of a Model call so the same launch can be
+    replayed on device-resident arguments."""
+
+    def __init__(self, inner):
+        self.inner, self.last = inner, None
+
+    def __getattr__(self, k):
+        return getattr(self.inner, k)
+
+    def execute(self, plan, host_args, batch, chunk=None, to_host=True):
+        self.last = (plan, host_args, batch)
+        return self.inner.execute(plan, host_args, batch, chunk, to_host)
+
+
+def staged_ms(ex, model, reps=5, **call_kw):
+    """Device time (CUDA events) of one qmlb_run over HBM-resident arguments."""
+    import torch
+    import warnings
+
+    spy = _Spy(ex)
+    model.script.executor = spy
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        model(**call_kw)
+    plan, host_args, batch = spy.last
+    call = ex.stage(plan, host_args, batch)
+    call.launch()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(reps):
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        call.launch()
+        e.record()
+        torch.cuda.synchronize()
+        ts.append(s.elapsed_time(e))
+    model.script.executor = None
+    return float(np.mean(ts)), batch, call.h
+
+
+def config_legs(ex, peak_f64_tf):
+    """The other small-n BASELINE configs, device-resident (SURVEY 8(d) cfg 1, 3, 4).
+    `achieved` uses the ALGORITHMIC (dense, unfused tape) flop counts of SURVEY 8(d)."""
+    from qml_essentials_b200 import config
+    from qml_essentials_b200.model import Model
+
+    prev = config.get_precision()
+    config.set_precision("complex128")
+    out = {}
+    try:
+        rng = np.random.default_rng(1000)
+        cases = {
+            "config_1": (lambda: Model(2, 1, "Circuit_19"), lambda m: dict(
+                params=rng.uniform(0, 2 * np.pi, (1, *m._params_shape)),
+                inputs=np.linspace(-np.pi, np.pi, 1024).reshape(-1, 1)), 1040,
+                "Model(2,1,'Circuit_19') expval, 1024 inputs x 1 param set", "k_reg<double,2>"),
+            "config_3": (lambda: Model(6, 3, "Circuit_15"), lambda m: dict(
+                params=rng.uniform(0, 2 * np.pi, (20000, *m._params_shape)),
+                execution_type="state"), 135168,
+                "Model(6,3,'Circuit_15') statevectors of 20 000 parameter sets "
+                "(expressibility / Meyer-Wallach input)", "k_frame<double,256> (64 states per CTA)"),
+            "config_4": (lambda: Model(8, 4, "Strongly_Entangling"), lambda m: dict(
+                params=rng.uniform(0, 2 * np.pi, (1, *m._params_shape)),
+                inputs=np.linspace(-np.pi, np.pi, 4096).reshape(-1, 1),
+                noise_params={"Depolarizing": 0.01, "AmplitudeDamping": 0.02},
+                execution_type="density"), 2.69e9,
+                "Model(8,4,'Strongly_Entangling') noisy density matrices, batch 4096 "
+                "(4 GiB written once)", "k_frame<double,256,wide> (cluster of 8 CTAs, DSMEM)"),
+        }
+        for name, (mk_model, mk_kw, flop, what, kernel) in cases.items():
+            try:
+                import warnings
+
+                with warnings.catch_warnings():
+                    warnings.simplefilter("ignore")
+                    m = mk_model()
+                ms, batch, h = staged_ms(ex, m, **mk_kw(m))
+                tf = flop * batch / (ms * 1e-3) / 1e12
+                out[name] = {"workload": what, "evals_per_s": batch / (ms * 1e-3),
+                             "device_ms": ms, "batch": batch, "strategy": h.strategy,
+                             "steps_or_passes": h.n_passes, "kernel": kernel,
+                             "roofline": {"bound": "fp64_fma", "achieved": tf,
+                                          "peak": peak_f64_tf, "unit": "TFLOP/s",
+                                          "frac": tf / peak_f64_tf if peak_f64_tf else None,
+                                          "note": "algorithmic flops of the dense unfused tape "
+                                                  "(SURVEY 8(d)); the kernels fold CX and fuse "
+                                                  "channels, so they execute fewer"}}
+            except Exception as exc:  # noqa: BLE001
+                out[name] = {"error": f"{type(exc).__name__}: {exc}"[:300]}
+    finally:
+        config.set_precision(prev)
+    return out
+
+
 def hbm_peak_gbs():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -224,7 +332,7 @@ def run_reference(args, json_out):
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     model, params, inputs = workload()
-    n_sample = 256
+    n_sample = params.shape[0]  # the full workload of the GPU arm (same config)
     times = []
     for i in range(args.warmup + args.steps):
         t0 = time.perf_counter()
@@ -239,9 +347,9 @@ def run_reference(args, json_out):
         "ms_per_step": 1e3 * sum(times) / len(times), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "complex128 (f64)",
         "data": "synthetic",
-        "config": {"workload": "cfg2: Model(4,4,Hardware_Efficient) expval, 264-point grid",
-                   "evals_per_step": B, "note": "reference-faithful CPU restatement (no "
-                   "XLA): the reference needs JAX, absent from this image"},
+        "config": {"workload": WORKLOAD, "evals_per_step_per_gpu": B,
+                   "note": "reference-faithful CPU restatement (no XLA): the reference needs "
+                           "JAX, absent from this image"},
         "cpu_baseline": {"value": value, "unit": "evals/s", "cores": cores, "kind": "port",
                          "sample": sample},
         "e2e": {"value": value, "unit": "evals/s", "h2d_bytes_per_step": 0,
@@ -271,6 +379,8 @@ def main():
     ap.add_argument("--precision", default="complex128", choices=["complex128", "complex64"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly")
+    ap.add_argument("--no-config-legs", action="store_true",
+                    help="skip the config 1 / 3 / 4 device-resident legs")
     ap.add_argument("--gate-pass-qubits", type=int, default=-1,
                     help="n for the HBM gate-pass leg (default: 32 on 1 GPU, 30 per rank "
                          "otherwise; 0 disables)")
@@ -303,27 +413,59 @@ def main():
     n_freq = B_I
 
     # ---- plan + stage (device-resident arguments) --------------------------------
+    import ctypes as C
+
+    spy = _Spy(ex)
+    model.script.executor = spy
     model(params=params, inputs=inputs)  # records + compiles the plan, creates the program
-    plan = next(p for p in model.script._jit_cache.values()
-                if hasattr(p, "program") and p.device)
-    # rebuild the device call exactly as Script does, but keep it resident
-    obs = model._build_obs()[1]
-    ax_p, ax_i, ax_r = model._batch_axes(B)
-    in_axes = (ax_p, ax_i, ax_r, script.BatchAxis(0, 1, B, B), None)
-    host_args = model.script._device_args(
-        plan, (params, inputs, model.pulse_params, script.LazyKeys(model.random_key, B),
-               model.enc_params), in_axes, B)
+    model.script.executor = None
+    plan, host_args, _ = spy.last
     call = ex.stage(plan, host_args, B)
-    stats = torch.zeros(2 * n_freq, dtype=torch.float64, device=dev)
     flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=dev)
+
+    # FCC statistics of the frequencies the circuit can carry (0 .. degree // 2): what a
+    # batch-sharded Fourier fingerprint has to combine across ranks
+    K = model.degree[0] // 2 + 1
+    rows = torch.arange(K, dtype=torch.int32, device=dev)
+    n_stat = 2 * (2 * K + K * K)  # complex128 as pairs of doubles
+    coef = torch.empty((B_I, B_P), dtype=torch.complex128 if args.precision == "complex128"
+                       else torch.complex64, device=dev)
+    moments = torch.empty(n_stat, dtype=torch.float64, device=dev)
+    reduced = torch.empty(n_stat, dtype=torch.float64, device=dev)
+    dt_code = 1 if args.precision == "complex128" else 0
+    lib = ex.lib
+    collective = "none (1 GPU)"
+    peer_ptrs = None
+    if world > 1:
+        try:
+            import torch.distributed._symmetric_memory as symm
+
+            nbytes = int(lib.qmlb_allreduce_buffer_bytes(n_stat))
+            sbuf = symm.empty((nbytes + 7) // 8, dtype=torch.float64, device=dev)
+            sbuf.zero_()
+            hdl = symm.rendezvous(sbuf, dist.group.WORLD)
+            torch.cuda.synchronize()
+            dist.barrier()
+            peer_ptrs = (C.c_void_p * world)(*[int(q) for q in hdl.buffer_ptrs])
+            collective = "one-shot all-reduce over symmetric memory (k_allreduce_oneshot)"
+        except Exception as exc:  # noqa: BLE001
+            print(f"[bench] symmetric memory unavailable ({exc}); using NCCL", file=sys.stderr)
+            collective = "NCCL all_reduce"
 
     def step_device():
         out = call.launch()  # (B, 4) expvals, flat order b = i * B_P + p
-        if world > 1:
-            sig = out.view(B_I, B_P, N_QUBITS).mean(dim=2)  # mean expval per (x, sample)
-            stats[:n_freq] = sig.sum(dim=1)
-            stats[n_freq:] = (sig * sig).sum(dim=1)
-            dist.all_reduce(stats)
+        st = torch.cuda.current_stream(dev).cuda_stream
+        rc = lib.qmlb_grid_dft(out.data_ptr(), dt_code, B_I, B_P, N_QUBITS, coef.data_ptr(), st)
+        rc |= lib.qmlb_coef_moments(coef.data_ptr(), dt_code, rows.data_ptr(), K, B_P,
+                                    moments.data_ptr(), st)
+        if world > 1 and peer_ptrs is not None:
+            rc |= lib.qmlb_allreduce_peer(peer_ptrs, world, rank, n_stat, moments.data_ptr(),
+                                          reduced.data_ptr(), st)
+        elif world > 1:
+            reduced.copy_(moments)
+            dist.all_reduce(reduced)
+        if rc != 0:
+            raise RuntimeError(lib.qmlb_last_error().decode())
         return out
 
     def barrier():
@@ -390,15 +532,19 @@ def main():
     torch.cuda.synchronize()
     kern_ms = sum(s.elapsed_time(e) for s, e in kev) / args.steps
 
-    # ---- end to end through Model.__call__ (host arrays in, host array out) --------
+    # ---- end to end through Coefficients.get_spectrum (host arrays in, host array out) ----
+    from qml_essentials_b200.coefficients import Coefficients
+
+    model.params = params
     for _ in range(args.warmup):
-        res = model(params=params, inputs=inputs)
+        spec, freqs = Coefficients.get_spectrum(model, mfs=MFS, shift=True, trim=True)
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        res = model(params=params, inputs=inputs)
+        spec, freqs = Coefficients.get_spectrum(model, mfs=MFS, shift=True, trim=True)
     barrier()
     e2e_s = time.perf_counter() - t0
+    res = model(params=params, inputs=inputs)  # raw expvals for the CPU cross-check below
 
     # ---- HBM-streaming regime: GB/s per fused gate pass (every rank: its own state) ----
     gp = None
@@ -422,6 +568,10 @@ def main():
 
     # measured while every rank is still alive (the ranks leave right after the last collective)
     peak_tf = ex.fma_peak_tflops(args.precision) if rank == 0 else None
+    cfg_legs = None
+    if rank == 0 and not args.no_config_legs:
+        torch.cuda.empty_cache()
+        cfg_legs = config_legs(ex, ex.fma_peak_tflops("complex128"))
 
     t = torch.tensor([dev_ms, e2e_s * 1e3, gp_ms], dtype=torch.float64, device=dev)
     if world > 1:
@@ -441,18 +591,21 @@ def main():
             "vs_baseline": None, "dtype": "complex128 (f64)" if prec64 else "complex64 (f32)",
             "data": "synthetic",
             "config": {
-                "workload": "BASELINE configs[1] / SURVEY 8(d) cfg2 grid B: Model(4,4,"
-                            "'Hardware_Efficient') expval on 4 qubits, 1024 param samples "
-                            "(default_rng(1000+rank)) x 264-point input grid per GPU",
+                "workload": WORKLOAD,
                 "evals_per_step_per_gpu": B, "cache": "L2 flushed (512 MiB write) between "
                 "timed iterations", "parallelism": f"batch-sharded x{world}",
                 "launch": "CUDA graph replay" if graph is not None else "eager",
+                "step": "k_pre x2, k_reg, k_grid_dft, k_coef_moments"
+                        + (", k_allreduce_oneshot" if peer_ptrs is not None else ""),
+                "collective": collective, "stat_bytes": n_stat * 8,
             },
             "e2e": {"value": e2e_value, "unit": "evals/s",
                     "h2d_bytes_per_step": int(params.nbytes + inputs.nbytes),
-                    "d2h_bytes_per_step": int(res.nbytes),
+                    "d2h_bytes_per_step": int(B_I * B_P * (16 if prec64 else 8)),
                     "ms_per_step": e2e_ms / args.steps,
-                    "api": "Model.__call__(params, inputs) with NumPy arrays"},
+                    "api": "Coefficients.get_spectrum(model, mfs=8, shift=True, trim=True) "
+                           "with model.params = NumPy (1024, 5, 12); returns the host "
+                           "coefficient array " + str(tuple(spec.shape))},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {
@@ -460,10 +613,11 @@ def main():
                 "kernel": f"k_reg<{'double' if prec64 else 'float'},4>",
                 "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
                 "frac": achieved_tf / peak_tf,
-                # dram__bytes_read.sum + dram__bytes_write.sum per launch from the ncu --set full
-                # capture of this kernel (profiles/r1_final_kreg_v5_smem_ops_full_summary.txt):
-                # parameters + hoisted tables in, the 8.6 MB of results still in L2
                 "traffic": 1666304 if prec64 else None,
+                "traffic_source": "ncu --set full capture of this kernel, not measured in "
+                                  "this run (profiles/r1_final_kreg_v5_smem_ops_full_summary"
+                                  ".txt): parameters + hoisted tables in; the 8.6 MB of "
+                                  "results stay in L2",
                 "kernel_ms": kern_ms,
                 "note": "achieved = algorithmic (unfused, dense) 26624 flop/eval x 270336 "
                         "evals / CUDA-event launch time; peak = qmlb_fma_peak measured on "
@@ -480,22 +634,39 @@ def main():
             line["gate_pass"] = gp
         if sh is not None:
             line["qubit_sharded"] = sh
-        if not args.no_cpu_baseline and world == 1:
+        if cfg_legs:
+            line.update(cfg_legs)
+        if not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
-            cpu_v, cpu_ev, sample = oracle_cpu_evals_per_s(params, inputs, 256, cores)
-            err = float(np.abs(res[:, :256, :] - cpu_ev).max())
+            cpu_v, cpu_ev, sample = oracle_cpu_evals_per_s(params, inputs, B_P, cores)
+            err = float(np.abs(res - cpu_ev).max())
             line["cpu_baseline"] = {"value": cpu_v, "unit": "evals/s", "cores": cores,
                                     "kind": "port", "sample": sample,
                                     "max_abs_err_vs_gpu": err}
         json_out.write(json.dumps(line) + "\n")
         json_out.flush()
     if world > 1:
-        # The NCCL communicator is referenced by the captured CUDA graph; tearing the
-        # process group down with it alive can block.  Everything is reported: leave
-        # without the collective shutdown.
+        # orderly shutdown: drop the captured graph, then the process group.  The step graph
+        # no longer holds an NCCL collective (round 1 left through os._exit because
+        # destroying the communicator under a live graph could block); a watchdog still
+        # bounds the teardown so a stuck collective cannot hold the node.
+        graph = None
         torch.cuda.synchronize()
-        sys.stderr.flush()
-        os._exit(0)
+        done = threading.Event()
+
+        def _teardown():
+            try:
+                dist.barrier()
+                dist.destroy_process_group()
+            finally:
+                done.set()
+
+        t_down = threading.Thread(target=_teardown, daemon=True)
+        t_down.start()
+        if not done.wait(60):
+            print("[bench] process-group teardown timed out; leaving", file=sys.stderr)
+            sys.stderr.flush()
+            os._exit(0)
 
 
 if __name__ == "__main__":

@@ -263,6 +263,33 @@ int qmlb_purity(const void* states, int dtype, int is_density, int64_t batch,
 int qmlb_overlap_fidelity(const void* states, int dtype, int64_t half, int32_t n_qubits,
                           void* out, void* stream);
 
+/* Device post-processing of the Fourier-analysis callers.
+ *
+ * qmlb_grid_dft: the transform of Coefficients._fourier_transform (coefficients.py:128-150)
+ * for ONE input feature.  ev: (n_x, n_p, n_obs) real expectation values (real of the given
+ * precision) as `Model.__call__` returns them for an n_x-point input grid and n_p parameter
+ * samples; out[k][p] = (1 / n_x) sum_x mean_obs(ev[x][p][:]) exp(-2 pi i k x / n_x) for
+ * k = 0 .. n_x - 1 (numpy.fft order), (n_x, n_p) complex of the given precision. */
+int qmlb_grid_dft(const void* ev, int dtype, int32_t n_x, int64_t n_p, int32_t n_obs, void* out,
+                  void* stream);
+
+/* Additive sufficient statistics of the FCC correlation estimators
+ * (coefficients.py:1346-1498) over the n_p samples of K selected coefficient rows
+ * (rows[i] indexes the first axis of coef, a (*, n_p) complex array of the given
+ * precision): out (complex128, 2K + K*K entries) = [sum_p c_i | sum_p |c_i|^2 |
+ * sum_p conj(c_i) c_j].  These are what crosses ranks in a batch-sharded run. */
+int qmlb_coef_moments(const void* coef, int dtype, const int32_t* rows, int32_t K, int64_t n_p,
+                      void* out, void* stream);
+
+/* One-shot all-reduce (sum, float64) over peer-mapped symmetric buffers: peer_buf[r] is the
+ * address, valid in this process, of rank r's buffer of qmlb_allreduce_buffer_bytes(n) bytes
+ * (zero-initialised once); `in` and `out` are local, n doubles each.  One launch per rank
+ * on n_peers (2..8) GPUs; every rank obtains the same bits (rank-order summation).  If a
+ * peer does not arrive within ~2^28 polls the result is NaN instead of a hang. */
+size_t qmlb_allreduce_buffer_bytes(int64_t n);
+int qmlb_allreduce_peer(const void* const* peer_buf, int32_t n_peers, int32_t rank, int64_t n,
+                        const double* in, double* out, void* stream);
+
 /* Measurement aid: sustained FMA throughput of this GPU in the given real
  * precision (TFLOP/s), used as the roofline denominator of the register-resident
  * regime.  Blocks until done. */

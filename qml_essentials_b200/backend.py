@@ -32,7 +32,8 @@ EXPORTED_SYMBOLS = (
     "qmlb_program_destroy", "qmlb_program_info", "qmlb_workspace_bytes", "qmlb_run",
     "qmlb_sample", "qmlb_purity", "qmlb_overlap_fidelity", "qmlb_fma_peak",
     "qmlb_evolve", "qmlb_zsums", "qmlb_zsums_workspace_bytes", "qmlb_plan_describe",
-    "qmlb_evolve_peer",
+    "qmlb_evolve_peer", "qmlb_grid_dft", "qmlb_coef_moments", "qmlb_allreduce_buffer_bytes",
+    "qmlb_allreduce_peer",
 )
 QMLB_DESC_FORCE_STREAM = 1
 
@@ -100,6 +101,14 @@ def load_library(path: str = LIB_PATH) -> C.CDLL:
     lib.qmlb_evolve_peer.argtypes = [C.c_void_p, C.POINTER(_Arg), C.c_int32, C.c_void_p,
                                      C.POINTER(C.c_void_p), C.c_int32, C.c_int32, C.c_void_p,
                                      C.c_size_t, C.c_void_p]
+    lib.qmlb_grid_dft.argtypes = [C.c_void_p, C.c_int, C.c_int32, C.c_int64, C.c_int32,
+                                  C.c_void_p, C.c_void_p]
+    lib.qmlb_coef_moments.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int32, C.c_int64,
+                                      C.c_void_p, C.c_void_p]
+    lib.qmlb_allreduce_buffer_bytes.argtypes = [C.c_int64]
+    lib.qmlb_allreduce_buffer_bytes.restype = C.c_size_t
+    lib.qmlb_allreduce_peer.argtypes = [C.POINTER(C.c_void_p), C.c_int32, C.c_int32, C.c_int64,
+                                        C.c_void_p, C.c_void_p, C.c_void_p]
     lib.qmlb_plan_describe.argtypes = [C.POINTER(_Desc), C.c_char_p, C.c_size_t]
     lib.qmlb_zsums.argtypes = [C.c_void_p, C.c_int, C.c_int64, C.c_int32, C.c_void_p,
                                C.c_void_p, C.c_size_t, C.c_void_p]
@@ -370,6 +379,35 @@ class CudaExecutor:
         if rc != 0:
             raise BackendError(f"qmlb_overlap_fidelity: {self.lib.qmlb_last_error().decode()}")
         return out
+
+    def grid_dft(self, ev):
+        """(n_x, n_p, n_obs) real device expvals -> (n_x, n_p) complex coefficients
+        (mean over observables, DFT along the grid axis, 1/n_x normalisation)."""
+        torch = self.torch
+        n_x, n_p, n_obs = ev.shape
+        dt = QMLB_C128 if ev.dtype == torch.float64 else QMLB_C64
+        out = torch.empty((n_x, n_p), dtype=torch.complex128 if dt else torch.complex64,
+                          device=ev.device)
+        rc = self.lib.qmlb_grid_dft(ev.data_ptr(), dt, n_x, n_p, n_obs, out.data_ptr(),
+                                    torch.cuda.current_stream(ev.device).cuda_stream)
+        if rc != 0:
+            raise BackendError(f"qmlb_grid_dft: {self.lib.qmlb_last_error().decode()}")
+        return out
+
+    def coef_moments(self, coef, rows):
+        """Sufficient statistics over the samples of the selected coefficient rows:
+        ``(sum c_i, sum |c_i|^2, sum conj(c_i) c_j)`` as complex128 device tensors."""
+        torch = self.torch
+        K, n_p = len(rows), coef.shape[1]
+        dt = QMLB_C128 if coef.dtype == torch.complex128 else QMLB_C64
+        idx = torch.as_tensor(np.asarray(rows, dtype=np.int32), device=coef.device)
+        out = torch.empty(2 * K + K * K, dtype=torch.complex128, device=coef.device)
+        rc = self.lib.qmlb_coef_moments(coef.data_ptr(), dt, idx.data_ptr(), K, n_p,
+                                        out.data_ptr(),
+                                        torch.cuda.current_stream(coef.device).cuda_stream)
+        if rc != 0:
+            raise BackendError(f"qmlb_coef_moments: {self.lib.qmlb_last_error().decode()}")
+        return out[:K], out[K:2 * K].real, out[2 * K:].reshape(K, K)
 
     def fma_peak_tflops(self, precision: str) -> float:
         v = C.c_double()

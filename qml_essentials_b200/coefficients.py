@@ -21,6 +21,7 @@ from __future__ import annotations
 
 import logging
 import math
+import os
 from functools import reduce
 from typing import Any, List, Optional, Tuple, Union
 
@@ -83,10 +84,28 @@ class Coefficients:
         axes = [np.arange(0, stop, step[i]) for i in range(F)]
         grid = np.array(np.meshgrid(*axes)).T.reshape(-1, F)
 
+        freqs = [np.fft.fftfreq(int(mts * n_freqs[i]), 1 / n_freqs[i]) for i in range(F)]
+
+        # One input feature, expectation values averaged over the observables: the mean and
+        # the DFT along the grid axis run on the GPU (qmlb_grid_dft) right behind the circuit
+        # kernel, and only the coefficients leave the device.
+        # QMLB_HOST_FFT=1 keeps the reference's host route (numpy.fft.fftn).
+        if (F == 1 and kwargs.get("execution_type", "expval") == "expval"
+                and kwargs.get("force_mean", False) and model.shots is None
+                and os.environ.get("QMLB_HOST_FFT") != "1"):
+            from .script import get_executor
+
+            ex = model.script.executor or get_executor()
+            if hasattr(ex, "grid_dft"):
+                kw = {k: v for k, v in kwargs.items() if k != "force_mean"}
+                ev = model.device_result(inputs=grid, **kw)
+                n_x = axes[0].shape[0]
+                coef = ex.grid_dft(ev.reshape(n_x, -1, ev.shape[-1]))
+                return np.asarray(coef.cpu().numpy()).squeeze(), freqs
+
         out = np.asarray(model(inputs=grid, **kwargs))
         out = out.reshape(*[a.shape[0] for a in axes], -1).squeeze()
         coeffs = np.fft.fftn(out, axes=list(range(F)))
-        freqs = [np.fft.fftfreq(int(mts * n_freqs[i]), 1 / n_freqs[i]) for i in range(F)]
         return coeffs / math.prod(out.shape[0:F]), freqs
 
     @classmethod
@@ -162,6 +181,22 @@ class _Stats:
         a2 = np.abs(safe) ** 2
         self.sum_ax2 = a2.T @ fm
         self.sum_ay2 = fm.T @ a2
+
+    @classmethod
+    def from_moments(cls, n: int, s1, s2, cc) -> "_Stats":
+        """The same object from the moments the device reduces (``qmlb_coef_moments``) over
+        ``n`` complete (finite) complex samples of K coefficients: ``s1[i] = sum c_i``,
+        ``s2[i] = sum |c_i|^2``, ``cc[i][j] = sum conj(c_i) c_j``."""
+        self = cls.__new__(cls)
+        s1, s2, cc = np.asarray(s1), np.asarray(s2, dtype=np.float64), np.asarray(cc)
+        K = s1.shape[0]
+        self.nobs = np.full((K, K), float(n))
+        self.sum_x = np.repeat(s1[:, None], K, axis=1)
+        self.sum_y = np.repeat(s1[None, :], K, axis=0)
+        self.sum_cxy = cc
+        self.sum_ax2 = np.repeat(s2[:, None], K, axis=1)
+        self.sum_ay2 = np.repeat(s2[None, :], K, axis=0)
+        return self
 
     def allreduce(self) -> "_Stats":
         """One all-reduce of the concatenated K x K blocks across ranks."""

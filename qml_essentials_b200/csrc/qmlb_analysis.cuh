@@ -1,0 +1,150 @@
+// Device post-processing of the Fourier-analysis callers: the
+// grid DFT of Coefficients._fourier_transform (coefficients.py:128-150), the additive
+// sufficient statistics the FCC correlation estimators need (coefficients.py:1346-1498), and
+// a one-shot all-reduce of those statistics over peer-mapped (symmetric) memory - so that a
+// Fourier-fingerprint step returns kilobytes and crosses ranks without a library collective.
+#pragma once
+
+#include "qmlb_device.cuh"
+
+namespace qmlb {
+
+constexpr int DFT_PCOLS = 32;  // parameter samples per CTA
+
+// out[k][p] = (1 / n_x) * sum_x s[x][p] * exp(-2 pi i k x / n_x),
+// s[x][p] = mean over the n_obs observables of ev[x][p][:]   (ev: (n_x, n_p, n_obs) real)
+// One CTA = DFT_PCOLS samples x all frequencies; the signal tile and the twiddle table sit
+// in shared memory (double precision throughout), x is summed in index order.
+template <typename T>
+__global__ void __launch_bounds__(256) k_grid_dft(const T* __restrict__ ev, int n_x, int64_t n_p,
+                                                  int n_obs, cx<T>* __restrict__ out) {
+  extern __shared__ __align__(16) unsigned char dsm[];
+  double* sig = reinterpret_cast<double*>(dsm);                  // [n_x][DFT_PCOLS]
+  double2* tw = reinterpret_cast<double2*>(sig + (size_t)n_x * DFT_PCOLS);  // [n_x]
+  const int64_t p0 = (int64_t)blockIdx.x * DFT_PCOLS;
+  for (int i = threadIdx.x; i < n_x * DFT_PCOLS; i += blockDim.x) {
+    const int x = i / DFT_PCOLS, c = i % DFT_PCOLS;
+    double m = 0.0;
+    if (p0 + c < n_p) {
+      const T* row = ev + ((size_t)x * n_p + (p0 + c)) * n_obs;
+      for (int q = 0; q < n_obs; ++q) m += (double)row[q];
+      m /= (double)n_obs;
+    }
+    sig[i] = m;
+  }
+  for (int j = threadIdx.x; j < n_x; j += blockDim.x) {
+    double s, c;
+    sincospi(-2.0 * (double)j / (double)n_x, &s, &c);
+    tw[j] = make_double2(c, s);
+  }
+  __syncthreads();
+  const int c = threadIdx.x % DFT_PCOLS;
+  const double inv = 1.0 / (double)n_x;
+  for (int k = threadIdx.x / DFT_PCOLS; k < n_x; k += blockDim.x / DFT_PCOLS) {
+    double re = 0.0, im = 0.0;
+    int idx = 0;  // (k * x) mod n_x
+    for (int x = 0; x < n_x; ++x) {
+      const double v = sig[x * DFT_PCOLS + c];
+      const double2 w = tw[idx];
+      re = fma(v, w.x, re);
+      im = fma(v, w.y, im);
+      idx += k;
+      if (idx >= n_x) idx -= n_x;
+    }
+    if (p0 + c < n_p) out[(size_t)k * n_p + p0 + c] = mk<T>((T)(re * inv), (T)(im * inv));
+  }
+}
+
+// Moments over the sample axis of selected coefficient rows (coef: (n_k_total, n_p) complex):
+//   out[i]             = sum_p c_i(p)                 i < K
+//   out[K + i]         = sum_p |c_i(p)|^2 (real)
+//   out[2K + i*K + j]  = sum_p conj(c_i(p)) * c_j(p)
+// complex128 accumulators, p in index order (bitwise reproducible).
+template <typename T>
+__global__ void k_coef_moments(const cx<T>* __restrict__ coef, const int32_t* __restrict__ rows,
+                               int K, int64_t n_p, double2* __restrict__ out) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (int64_t)K * K + 2 * K) return;
+  if (t < 2 * K) {
+    const int i = (int)(t % K);
+    const cx<T>* ci = coef + (size_t)rows[i] * n_p;
+    double re = 0.0, im = 0.0;
+    if (t < K) {
+      for (int64_t p = 0; p < n_p; ++p) {
+        re += (double)ci[p].x;
+        im += (double)ci[p].y;
+      }
+    } else {
+      for (int64_t p = 0; p < n_p; ++p) re += (double)ci[p].x * ci[p].x + (double)ci[p].y * ci[p].y;
+    }
+    out[t] = make_double2(re, im);
+    return;
+  }
+  const int i = (int)((t - 2 * K) / K), j = (int)((t - 2 * K) % K);
+  const cx<T>* ci = coef + (size_t)rows[i] * n_p;
+  const cx<T>* cj = coef + (size_t)rows[j] * n_p;
+  double re = 0.0, im = 0.0;
+  for (int64_t p = 0; p < n_p; ++p) {
+    const double ar = ci[p].x, ai = ci[p].y, br = cj[p].x, bi = cj[p].y;
+    re += ar * br + ai * bi;   // conj(a) * b
+    im += ar * bi - ai * br;
+  }
+  out[t] = make_double2(re, im);
+}
+
+// One-shot all-reduce (sum) of n doubles over peer-mapped buffers, ONE CTA per rank.
+// Layout of every rank's symmetric buffer: [16 x uint64 arrival flags | 1 x uint64 epoch |
+// pad to 256 B | 2 x n doubles (payload, double-buffered by epoch parity)].  Every rank
+// copies its input into its own payload, publishes the epoch to every peer's flag slot and
+// waits until every peer has published the same epoch, then sums the payloads in rank order
+// (identical on every rank).  A rank can run at most one epoch ahead of the slowest reader,
+// which is what the two payload buffers cover.
+struct PeerReduce {
+  void* buf[8];
+  int32_t n_peers, rank;
+  int64_t n;
+};
+
+__global__ void __launch_bounds__(256) k_allreduce_oneshot(PeerReduce R,
+                                                           const double* __restrict__ in,
+                                                           double* __restrict__ out) {
+  __shared__ unsigned long long s_epoch;
+  __shared__ int s_ok;
+  unsigned long long* mine = static_cast<unsigned long long*>(R.buf[R.rank]);
+  if (threadIdx.x == 0) {
+    s_epoch = mine[16] + 1ull;
+    mine[16] = s_epoch;
+    s_ok = 1;
+  }
+  __syncthreads();
+  const unsigned long long epoch = s_epoch;
+  const int64_t n = R.n;
+  auto payload = [&](int r) {
+    return reinterpret_cast<double*>(static_cast<unsigned char*>(R.buf[r]) + 256) +
+           (epoch & 1ull) * n;
+  };
+  double* my = payload(R.rank);
+  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) my[i] = in[i];
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x < R.n_peers) {
+    unsigned long long* flag = static_cast<unsigned long long*>(R.buf[threadIdx.x]) + R.rank;
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(flag), "l"(epoch) : "memory");
+    const unsigned long long* wait = mine + threadIdx.x;
+    unsigned long long seen = 0;
+    long long spins = 0;
+    do {
+      asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(wait) : "memory");
+    } while (seen < epoch && ++spins < (1ll << 28));
+    if (seen < epoch) s_ok = 0;  // a peer never arrived: poison the result instead of hanging
+  }
+  __syncthreads();
+  const bool ok = s_ok != 0;
+  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+    double s = 0.0;
+    for (int r = 0; r < R.n_peers; ++r) s += __ldcv(payload(r) + i);  // peer data: bypass L1
+    out[i] = ok ? s : __longlong_as_double(0x7ff8000000000000ll);
+  }
+}
+
+}  // namespace qmlb

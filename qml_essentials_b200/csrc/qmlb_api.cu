@@ -9,6 +9,7 @@
 #include <vector>
 
 #include "qmlb_internal.h"
+#include "qmlb_analysis.cuh"
 #include "qmlb_measure.cuh"
 #include "qmlb_reg.cuh"
 
@@ -583,6 +584,8 @@ int upload(qmlb_program* p) {
   return QMLB_OK;
 }
 
+bool z1_fast(const qmlb_program* p);
+
 int plan(qmlb_program* p) {
   int dev = 0;
   if (cudaGetDevice(&dev) == cudaSuccess) {
@@ -634,6 +637,17 @@ int plan(qmlb_program* p) {
       return QMLB_OK;
     }
     if (force == 3) return fail(QMLB_ERR_UNSUPPORTED, "program outside the frame engine's envelope");
+  }
+
+  // ---- strategy 4: streaming frame engine (tiles of an HBM-resident state) ------------
+  if ((force < 0 || force == 4) && !p->force_stream && z1_fast(p) &&
+      env_int("QMLB_FSTREAM", 1)) {
+    if (plan_frame_stream(p) == QMLB_OK) {
+      p->strategy = 4;
+      p->direct_out = false;  // the state sits in the workspace; <Z_q> by the sweep below
+      return QMLB_OK;
+    }
+    if (force == 4) return fail(QMLB_ERR_UNSUPPORTED, "program outside the streaming frame engine");
   }
 
   // ---- strategy 1: whole state in shared memory ---------------------------------
@@ -767,8 +781,13 @@ int launch_measure(const qmlb_program* p, const cx<T>* state, int64_t batch, voi
       k_expval_z1<T><<<dim3((unsigned)ctas, (unsigned)nb), 256, 0, st>>>(
           state + ((size_t)b0 << p->n_qubits), partial + (size_t)b0 * ctas * 33, p->n_qubits);
     }
+    BitMap map;
+    for (int b = 0; b < 40; ++b)
+      map.pos[b] = (int8_t)(p->strategy == 4 && b < (int)p->fstream_final_hpos.size()
+                                ? p->fstream_final_hpos[b]
+                                : b);
     k_expval_z1_final<T><<<(unsigned)((n_out + 255) / 256), 256, 0, st>>>(
-        p->dev, partial, static_cast<T*>(out), batch, ctas);
+        p->dev, partial, static_cast<T*>(out), batch, ctas, map);
   } else if (p->out_type == QMLB_OUT_EXPVAL) {
     const int chunks = expval_chunks(p, batch);
     const int n_obs = (int)p->obs.size();
@@ -810,7 +829,7 @@ size_t pre_layout(const qmlb_program* p, const qmlb_arg* a, int64_t batch, bool 
 
 // batched streaming runs keep a table of every (element, op) matrix
 size_t premats_bytes(const qmlb_program* p, int64_t batch) {
-  if (!(p->strategy == 3 || (p->strategy == 2 && batch > 1))) return 0;
+  if (!(p->strategy == 3 || p->strategy == 4 || (p->strategy == 2 && batch > 1))) return 0;
   return ((size_t)batch * p->stream_mat_row * cs_of(p->dtype) + 255) & ~size_t(255);
 }
 
@@ -914,6 +933,12 @@ int run_typed(const qmlb_program* p, RunArgs& R, void* out, void* workspace, siz
                 (state_layout(p, R.batch, &part_off) - premats_bytes(p, R.batch));
     int rc = evolve_stream<T>(p, R, state, 1, premats, st);
     if (rc != QMLB_OK) return rc;
+  } else if (p->strategy == 4) {
+    unsigned char* premats = static_cast<unsigned char*>(workspace) + tab_bytes +
+                             (state_layout(p, R.batch, &part_off) - premats_bytes(p, R.batch));
+    const bool f64 = std::is_same<T, double>::value;
+    CUDA_TRY((f64 ? launch_stream_mats_f64 : launch_stream_mats_f32)(p, R, premats, st));
+    CUDA_TRY((f64 ? launch_fstream_f64 : launch_fstream_f32)(p, R, state, premats, 1, st));
   } else if (p->strategy == 3) {
     // [tables | state + partials | evaluated matrices]: one launch evaluates every matrix
     // of every element, one launch runs the whole tape on chip
@@ -976,7 +1001,7 @@ int qmlb_plan_describe(const qmlb_program_desc* d, char* buf, size_t buflen) {
       }
       s += "\n";
     }
-  } else if (prog.strategy == 3) {
+  } else if (prog.strategy == 3 || prog.strategy == 4) {
     s += describe_frame(&prog);
   } else if (prog.strategy == 1) {
     s += "smem_bytes " + std::to_string(prog.smem) + " teams " + std::to_string(prog.teams) + "\n";
@@ -1039,6 +1064,7 @@ int qmlb_program_info(const qmlb_program* p, int32_t* strategy, int32_t* n_passe
     *n_passes = p->strategy == 0   ? 1
                 : p->strategy == 2 ? (int32_t)p->stream_passes.size()
                 : p->strategy == 3 ? (int32_t)p->frame_steps.size()
+                : p->strategy == 4 ? (int32_t)p->fstream_passes.size()
                                    : (int32_t)p->passes.size();
   if (n_device_ops) *n_device_ops = (int32_t)p->ops.size();
   return QMLB_OK;
@@ -1239,6 +1265,72 @@ int qmlb_overlap_fidelity(const void* states, int dtype, int64_t half, int32_t n
   else
     k_overlap<float><<<(unsigned)half, 256, 0, st>>>(
         static_cast<const cx<float>*>(states), half, n_qubits, static_cast<float*>(out));
+  CUDA_TRY(cudaGetLastError());
+  return QMLB_OK;
+}
+
+int qmlb_grid_dft(const void* ev, int dtype, int32_t n_x, int64_t n_p, int32_t n_obs, void* out,
+                  void* stream) {
+  if (!ev || !out) return fail(QMLB_ERR_INVALID, "null argument");
+  if (n_x < 1 || n_p < 1 || n_obs < 1) return fail(QMLB_ERR_INVALID, "empty grid");
+  const size_t smem = (size_t)n_x * DFT_PCOLS * sizeof(double) + (size_t)n_x * sizeof(double2);
+  if (smem > 200 * 1024) return fail(QMLB_ERR_UNSUPPORTED, "grid too long for the on-chip DFT");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const unsigned grid = (unsigned)((n_p + DFT_PCOLS - 1) / DFT_PCOLS);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  if (dtype == QMLB_C128) {
+    if (smem > 48 * 1024)
+      CUDA_TRY(cudaFuncSetAttribute(k_grid_dft<double>,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_grid_dft<double><<<grid, 256, smem, st>>>(static_cast<const double*>(ev), n_x, n_p, n_obs,
+                                                static_cast<cx<double>*>(out));
+  } else {
+    if (smem > 48 * 1024)
+      CUDA_TRY(cudaFuncSetAttribute(k_grid_dft<float>,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_grid_dft<float><<<grid, 256, smem, st>>>(static_cast<const float*>(ev), n_x, n_p, n_obs,
+                                               static_cast<cx<float>*>(out));
+  }
+  CUDA_TRY(cudaGetLastError());
+  return QMLB_OK;
+}
+
+int qmlb_coef_moments(const void* coef, int dtype, const int32_t* rows, int32_t K, int64_t n_p,
+                      void* out, void* stream) {
+  if (!coef || !rows || !out) return fail(QMLB_ERR_INVALID, "null argument");
+  if (K < 1 || n_p < 1) return fail(QMLB_ERR_INVALID, "empty selection");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int64_t total = (int64_t)K * K + 2 * K;
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  if (dtype == QMLB_C128)
+    k_coef_moments<double><<<(unsigned)((total + 127) / 128), 128, 0, st>>>(
+        static_cast<const cx<double>*>(coef), rows, K, n_p, static_cast<double2*>(out));
+  else
+    k_coef_moments<float><<<(unsigned)((total + 127) / 128), 128, 0, st>>>(
+        static_cast<const cx<float>*>(coef), rows, K, n_p, static_cast<double2*>(out));
+  CUDA_TRY(cudaGetLastError());
+  return QMLB_OK;
+}
+
+size_t qmlb_allreduce_buffer_bytes(int64_t n) {
+  return 256 + 2 * (size_t)std::max<int64_t>(n, 0) * sizeof(double);
+}
+
+int qmlb_allreduce_peer(const void* const* peer_buf, int32_t n_peers, int32_t rank, int64_t n,
+                        const double* in, double* out, void* stream) {
+  if (!peer_buf || !in || !out) return fail(QMLB_ERR_INVALID, "null argument");
+  if (n_peers < 2 || n_peers > 8 || rank < 0 || rank >= n_peers || n < 1)
+    return fail(QMLB_ERR_INVALID, "peer count must be 2..8, rank inside it, n >= 1");
+  PeerReduce R{};
+  for (int i = 0; i < n_peers; ++i) {
+    if (!peer_buf[i]) return fail(QMLB_ERR_INVALID, "null peer pointer");
+    R.buf[i] = const_cast<void*>(peer_buf[i]);
+  }
+  R.n_peers = n_peers;
+  R.rank = rank;
+  R.n = n;
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  k_allreduce_oneshot<<<1, 256, 0, static_cast<cudaStream_t>(stream)>>>(R, in, out);
   CUDA_TRY(cudaGetLastError());
   return QMLB_OK;
 }

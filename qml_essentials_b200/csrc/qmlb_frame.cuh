@@ -270,6 +270,112 @@ __device__ __forceinline__ void frame_dispatch_m1(int code, cx<T>* tile, const c
   }
 }
 
+
+// generic interpreter of a SUBPASS: any mix of 2x2 / 4x4 / dense 3-4 bit / controlled /
+// diagonal ops (steps the straight-line fast paths do not cover)
+template <typename T, bool HEAVY>
+__device__ __noinline__ void frame_items_generic(cx<T>* tile, const cx<T>* mats,
+                                                 const FrameStep& st, unsigned rank,
+                                                 uint32_t tlane, uint32_t tsize,
+                                                 uint32_t n_items) {
+        uint32_t piv[FRAME_R];
+#pragma unroll
+  for (int j = 0; j < FRAME_R; ++j) piv[j] = st.pivots[j];
+  for (uint32_t it = tlane; it < n_items; it += tsize) {
+    const uint32_t base = frame_item_base(st, it, piv, rank);
+    RegState<T, FRAME_R> S;
+    frame_load<T>(S, tile, base, st);
+    auto parity_at = [&](int pi) -> int {
+      return (__popc(base & st.par[pi].rloc) ^ __popc(rank & st.par[pi].rout)) & 1;
+    };
+#pragma unroll 1
+    for (int o = 0; o < st.n_ops; ++o) {
+      const FrameOp fo = st.ops[o];
+      const cx<T>* m = mats + fo.smem_off;
+      switch (fo.code) {
+        case QMLB_FOP_MAT1:
+          dispatch1<T, FRAME_R>(fo.j0, [&](auto B) {
+            constexpr int BIT = decltype(B)::value;
+            if (fo.shape != QMLB_FSHAPE_FULL)
+              frame_mat1<T, BIT, QMLB_FSHAPE_REAL>(S, m);
+            else
+              frame_mat1<T, BIT, QMLB_FSHAPE_FULL>(S, m);
+          });
+          break;
+        case QMLB_FOP_MAT2: {
+          auto on_pair = [&](auto JA, auto JB) {
+            constexpr int A_ = decltype(JA)::value, B_ = decltype(JB)::value;
+            if constexpr (A_ > B_) {
+              if (fo.shape == QMLB_FSHAPE_XREAL)
+                frame_mat2<T, A_, B_, QMLB_FSHAPE_XREAL>(S, m);
+              else if (fo.shape == QMLB_FSHAPE_REAL)
+                frame_mat2<T, A_, B_, QMLB_FSHAPE_REAL>(S, m);
+              else
+                frame_mat2<T, A_, B_, QMLB_FSHAPE_FULL>(S, m);
+            }
+          };
+          // the planner seats 2-bit ops on the register pairs (3,2) / (1,0)
+          if (fo.j0 == 3 && fo.j1 == 2)
+            on_pair(std::integral_constant<int, 3>{}, std::integral_constant<int, 2>{});
+          else if (fo.j0 == 1 && fo.j1 == 0)
+            on_pair(std::integral_constant<int, 1>{}, std::integral_constant<int, 0>{});
+          else
+            dispatch2<T, FRAME_R>(fo.j0, fo.j1, on_pair);
+          break;
+        }
+        case QMLB_FOP_MATK:
+          if constexpr (HEAVY) {
+            if (fo.k == 3)
+              frame_matk<T, 3>(S, m, 0);
+            else
+              frame_matk<T, 4>(S, m, 0);
+          }
+          break;
+        case QMLB_FOP_CTRL1: {
+          const int ctl = parity_at(fo.j1);
+          const unsigned sm = st.par[fo.j1].smask;
+          dispatch1<T, FRAME_R>(fo.j0, [&](auto B) {
+            constexpr int BIT = decltype(B)::value;
+            frame_ctrl1<T, BIT>(S, m, sm, ctl);
+          });
+          break;
+        }
+        case QMLB_FOP_DIAG: {
+          const uint8_t* idx = reinterpret_cast<const uint8_t*>(&st.ops[o + 1]);
+          int lb = 0;  // local value of slot 0
+          for (int a = 0; a < fo.k; ++a) lb |= parity_at(idx[a]) << (fo.k - 1 - a);
+#pragma unroll
+          for (int v = 0; v < FRAME_D; ++v) {
+            int loc = lb;
+            for (int a = 0; a < fo.k; ++a)
+              loc ^= (int)((st.par[idx[a]].smask >> v) & 1u) << (fo.k - 1 - a);
+            const cx<T> d = m[loc];
+            const T r = S.re(v), q = S.im(v);
+            S.re(v) = d.x * r - d.y * q;
+            S.im(v) = d.x * q + d.y * r;
+          }
+          ++o;
+          break;
+        }
+      }
+    }
+
+    frame_store<T>(S, tile, base, st);
+  }
+}
+
+template <typename T, bool HEAVY>
+__device__ __forceinline__ void frame_subpass(cx<T>* tile, const cx<T>* mats, const FrameStep& st,
+                                              unsigned outer, uint32_t tlane, uint32_t tsize,
+                                              uint32_t n_items) {
+  if (!HEAVY && st.fast >= 64)
+    frame_dispatch_m1<T>(st.fast - 64, tile, mats, st, outer, tlane, tsize, n_items);
+  else if (!HEAVY && st.fast >= 16)
+    frame_dispatch_d2<T>(st.fast - 16, tile, mats, st, outer, tlane, tsize, n_items);
+  else
+    frame_items_generic<T, HEAVY>(tile, mats, st, outer, tlane, tsize, n_items);
+}
+
 // RELAYOUT gather: destination d of this thread <- source (rank, index) through the GF(2)
 // map; PER amplitudes per thread held in registers across the cluster barrier
 template <typename T, int PER, typename Cluster>
@@ -386,12 +492,17 @@ __global__ void __launch_bounds__(THREADS, (THREADS == 512 || WIDE) ? 1 : 2)
         else
           __syncthreads();
         const int per = (int)(tile_n >> F.team_bits);
-        if (per == 16)
+        if (per == 16) {
           frame_relayout<T, 16>(tile, cluster, across, rank, Tb, F.team_bits, tlane, cmine,
                                 tab_lo, tab_hi);
-        else
+        } else if (per == 32) {
           frame_relayout<T, 32>(tile, cluster, across, rank, Tb, F.team_bits, tlane, cmine,
                                 tab_lo, tab_hi);
+        } else {
+          if constexpr (WIDE && sizeof(T) == 4)  // complex64, 2^14 amplitudes, 256 threads
+            frame_relayout<T, 64>(tile, cluster, across, rank, Tb, F.team_bits, tlane, cmine,
+                                  tab_lo, tab_hi);
+        }
         __syncthreads();  // the next reader of this tile is this CTA (or a later relayout)
         continue;
       }
@@ -408,96 +519,7 @@ __global__ void __launch_bounds__(THREADS, (THREADS == 512 || WIDE) ? 1 : 2)
         __syncthreads();
       }
 
-      if (valid && !HEAVY && st.fast >= 64) {
-        frame_dispatch_m1<T>(st.fast - 64, tile, mats, st, rank, tlane, tsize, n_items);
-      } else if (valid && !HEAVY && st.fast >= 16) {
-        frame_dispatch_d2<T>(st.fast - 16, tile, mats, st, rank, tlane, tsize, n_items);
-      } else if (valid) {
-        uint32_t piv[FRAME_R];
-#pragma unroll
-        for (int j = 0; j < FRAME_R; ++j) piv[j] = st.pivots[j];
-        for (uint32_t it = tlane; it < n_items; it += tsize) {
-          const uint32_t base = frame_item_base(st, it, piv, rank);
-          RegState<T, FRAME_R> S;
-          frame_load<T>(S, tile, base, st);
-          auto parity_at = [&](int pi) -> int {
-            return (__popc(base & st.par[pi].rloc) ^ __popc(rank & st.par[pi].rout)) & 1;
-          };
-#pragma unroll 1
-          for (int o = 0; o < st.n_ops; ++o) {
-            const FrameOp fo = st.ops[o];
-            const cx<T>* m = mats + fo.smem_off;
-            switch (fo.code) {
-              case QMLB_FOP_MAT1:
-                dispatch1<T, FRAME_R>(fo.j0, [&](auto B) {
-                  constexpr int BIT = decltype(B)::value;
-                  if (fo.shape != QMLB_FSHAPE_FULL)
-                    frame_mat1<T, BIT, QMLB_FSHAPE_REAL>(S, m);
-                  else
-                    frame_mat1<T, BIT, QMLB_FSHAPE_FULL>(S, m);
-                });
-                break;
-              case QMLB_FOP_MAT2: {
-                auto on_pair = [&](auto JA, auto JB) {
-                  constexpr int A_ = decltype(JA)::value, B_ = decltype(JB)::value;
-                  if constexpr (A_ > B_) {
-                    if (fo.shape == QMLB_FSHAPE_XREAL)
-                      frame_mat2<T, A_, B_, QMLB_FSHAPE_XREAL>(S, m);
-                    else if (fo.shape == QMLB_FSHAPE_REAL)
-                      frame_mat2<T, A_, B_, QMLB_FSHAPE_REAL>(S, m);
-                    else
-                      frame_mat2<T, A_, B_, QMLB_FSHAPE_FULL>(S, m);
-                  }
-                };
-                // the planner seats 2-bit ops on the register pairs (3,2) / (1,0)
-                if (fo.j0 == 3 && fo.j1 == 2)
-                  on_pair(std::integral_constant<int, 3>{}, std::integral_constant<int, 2>{});
-                else if (fo.j0 == 1 && fo.j1 == 0)
-                  on_pair(std::integral_constant<int, 1>{}, std::integral_constant<int, 0>{});
-                else
-                  dispatch2<T, FRAME_R>(fo.j0, fo.j1, on_pair);
-                break;
-              }
-              case QMLB_FOP_MATK:
-                if constexpr (HEAVY) {
-                  if (fo.k == 3)
-                    frame_matk<T, 3>(S, m, 0);
-                  else
-                    frame_matk<T, 4>(S, m, 0);
-                }
-                break;
-              case QMLB_FOP_CTRL1: {
-                const int ctl = parity_at(fo.j1);
-                const unsigned sm = st.par[fo.j1].smask;
-                dispatch1<T, FRAME_R>(fo.j0, [&](auto B) {
-                  constexpr int BIT = decltype(B)::value;
-                  frame_ctrl1<T, BIT>(S, m, sm, ctl);
-                });
-                break;
-              }
-              case QMLB_FOP_DIAG: {
-                const uint8_t* idx = reinterpret_cast<const uint8_t*>(&st.ops[o + 1]);
-                int lb = 0;  // local value of slot 0
-                for (int a = 0; a < fo.k; ++a) lb |= parity_at(idx[a]) << (fo.k - 1 - a);
-#pragma unroll
-                for (int v = 0; v < FRAME_D; ++v) {
-                  int loc = lb;
-                  for (int a = 0; a < fo.k; ++a)
-                    loc ^= (int)((st.par[idx[a]].smask >> v) & 1u) << (fo.k - 1 - a);
-                  const cx<T> d = m[loc];
-                  const T r = S.re(v), q = S.im(v);
-                  S.re(v) = d.x * r - d.y * q;
-                  S.im(v) = d.x * q + d.y * r;
-                }
-                ++o;
-                break;
-              }
-            }
-          }
-
-          frame_store<T>(S, tile, base, st);
-        }
-      }
+      if (valid) frame_subpass<T, HEAVY>(tile, mats, st, rank, tlane, tsize, n_items);
       __syncthreads();
     }
 

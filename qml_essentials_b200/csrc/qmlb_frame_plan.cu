@@ -295,6 +295,59 @@ struct Builder {
 
   int run();
   bool build_step();
+
+  // ---- streaming mode: the state lives in HBM, a pass works on tiles of 2^T amplitudes ----
+  // The HBM layout is always a bit permutation (hpos).  A tile holds the `L` lowest HBM
+  // positions (contiguous runs: what the bulk copies move) plus T - L freely chosen ones;
+  // the other N - T positions number the tiles ("outer", virtual positions T..N-1).
+  int L = 0;
+  std::vector<int> hpos;                 // logical bit -> HBM bit position
+  std::vector<int> tp, opos;             // virtual tile index / outer index -> HBM position
+  std::vector<FramePassHost> passes;
+  std::vector<int> final_hpos;
+
+  void start_pass(bool init) {
+    std::vector<char> in_tile(N, 0);
+    for (int i = 0; i < T; ++i) in_tile[tp[i]] = 1;
+    opos.clear();
+    for (int b = 0; b < N; ++b)
+      if (!in_tile[b]) opos.push_back(b);
+    std::vector<int> pos(N);
+    for (int j = 0; j < N; ++j) {
+      const int h = hpos[j];
+      auto it = std::find(tp.begin(), tp.end(), h);
+      pos[j] = it != tp.end() ? (int)(it - tp.begin())
+                              : T + (int)(std::find(opos.begin(), opos.end(), h) - opos.begin());
+    }
+    F.set_permutation(pos);
+    FramePassHost ps;
+    ps.first_step = (int)steps.size();
+    ps.n_steps = 0;
+    ps.init = init;
+    ps.tp = tp;
+    ps.opos = opos;
+    passes.push_back(ps);
+  }
+
+  // flush the frame of the current pass to a pure permutation that puts the logical bits in
+  // `at[i]` (virtual tile index i -> logical bit) and record where everything now lives
+  void close_pass(const std::vector<int>& at) {
+    std::vector<int> pos(N);
+    for (int j = 0; j < N; ++j)
+      if (F.outer(j)) pos[j] = top_bit(F.col[j]);
+    for (int i = 0; i < T; ++i) pos[at[i]] = i;
+    bool needed = false;
+    for (int j = 0; j < N; ++j)
+      if (F.col[j] != (1ull << pos[j])) needed = true;
+    if (needed) {
+      emit_relayout(pos);
+      steps.back().mat_entries = 1;
+    }
+    for (int i = 0; i < T; ++i) hpos[at[i]] = tp[i];
+    passes.back().n_steps = (int)steps.size() - passes.back().first_step;
+  }
+
+  int run_stream();
 };
 
 // One SUBPASS (plus the folds that follow it).  Returns false when nothing could be done.
@@ -584,7 +637,155 @@ int Builder::run() {
   return QMLB_OK;
 }
 
+int Builder::run_stream() {
+  done.assign(p->ops.size(), 0);
+  F.N = N;
+  F.T = T;
+  // initial HBM layout (|0..0> is invariant under bit permutations): soonest-needed bits
+  // on the low positions, i.e. inside the first tile
+  {
+    std::vector<int> nn = next_need();
+    std::vector<int> order(N);
+    for (int j = 0; j < N; ++j) order[j] = j;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return nn[a] < nn[b]; });
+    hpos.assign(N, 0);
+    for (int r = 0; r < N; ++r) hpos[order[r]] = r;
+    tp.resize(T);
+    for (int i = 0; i < T; ++i) tp[i] = i;
+  }
+  start_pass(true);
+  auto left = [&]() {
+    size_t n = 0;
+    for (char d : done) n += d ? 0 : 1;
+    return n;
+  };
+  int guard = 0;
+  while (left() > 0) {
+    if (build_step()) continue;
+    if (++guard > 4096) return QMLB_ERR_UNSUPPORTED;
+    // stuck: choose the next tile.  The T - L freely chosen positions can change, so at most
+    // T - L bits arrive; the bits that stay are the soonest-needed ones of the current tile.
+    std::vector<int> nn = next_need();
+    std::vector<int> order(N);
+    for (int j = 0; j < N; ++j) order[j] = j;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
+      if (nn[a] != nn[b]) return nn[a] < nn[b];
+      return !F.outer(a) && F.outer(b);
+    });
+    std::vector<int> incoming, staying;
+    for (int r = 0; r < N && (int)(incoming.size() + staying.size()) < T; ++r) {
+      const int j = order[r];
+      if (F.outer(j)) {
+        if ((int)incoming.size() < T - L && nn[j] < (1 << 30)) incoming.push_back(j);
+      } else {
+        staying.push_back(j);
+      }
+    }
+    for (int r = 0; r < N && (int)(incoming.size() + staying.size()) < T; ++r) {
+      const int j = order[r];
+      if (!F.outer(j) && std::find(staying.begin(), staying.end(), j) == staying.end())
+        staying.push_back(j);
+    }
+    if (incoming.empty()) return QMLB_ERR_UNSUPPORTED;
+    std::vector<int> leaving;
+    for (int j = 0; j < N; ++j)
+      if (!F.outer(j) && std::find(staying.begin(), staying.end(), j) == staying.end())
+        leaving.push_back(j);
+    // staying bits: the low run first, then the lowest high tile indices; leaving bits on
+    // the highest tile indices (those HBM positions drop out of the next tile)
+    std::vector<int> at(T);
+    for (size_t i = 0; i < staying.size(); ++i) at[i] = staying[i];
+    for (size_t i = 0; i < leaving.size(); ++i) at[staying.size() + i] = leaving[i];
+    close_pass(at);
+    std::vector<int> ntp;
+    for (size_t i = 0; i < staying.size(); ++i) ntp.push_back(tp[i]);
+    for (int j : incoming) ntp.push_back(hpos[j]);
+    std::sort(ntp.begin(), ntp.end());
+    tp = ntp;
+    start_pass(false);
+  }
+  {
+    std::vector<int> at;
+    for (int j = 0; j < N; ++j)
+      if (!F.outer(j)) at.push_back(j);
+    close_pass(at);
+  }
+  final_hpos = hpos;
+  return QMLB_OK;
+}
+
 }  // namespace
+
+// Streaming form of the frame engine (strategy 4): the state stays in HBM, every pass moves
+// tiles of 2^T amplitudes through shared memory with bulk copies and runs the pass' steps on
+// them.  Fills p->fstream_* ; QMLB_ERR_UNSUPPORTED -> fall back to the register-group stream.
+int plan_frame_stream(qmlb_program* p) {
+  const int N = p->n_bits;
+  const size_t cs = p->dtype == QMLB_C128 ? 16 : 8;
+  const char* et = std::getenv("QMLB_FSTREAM_TILE_BITS");
+  const char* el = std::getenv("QMLB_FSTREAM_LOW_BITS");
+  const int T = et ? std::atoi(et) : (p->dtype == QMLB_C128 ? 12 : 13);
+  const int L = el ? std::atoi(el) : (p->dtype == QMLB_C128 ? 5 : 6);  // 512-byte runs
+  if (N < T + 1 || N > 40 || T < 10 || T > 14 || L < 4 || L > T - 4) return QMLB_ERR_UNSUPPORTED;
+  Builder B;
+  B.p = p;
+  if (!analyse(p, B.info)) return QMLB_ERR_UNSUPPORTED;
+  for (const qmlb_op& o : p->ops)
+    if (o.kind == QMLB_OP_MAT && o.k >= 3) return QMLB_ERR_UNSUPPORTED;
+  B.N = N;
+  B.T = T;
+  B.G = N - T;
+  B.L = L;
+  int row = 0;
+  B.premat_off.assign(p->ops.size(), 0);
+  B.matlist_index.assign(p->ops.size(), -1);
+  p->stream_matlist.clear();
+  for (size_t i = 0; i < p->ops.size(); ++i) {
+    if (p->ops[i].kind == QMLB_OP_PERM) continue;
+    B.premat_off[i] = row;
+    B.matlist_index[i] = (int)p->stream_matlist.size();
+    StreamMatOp mo{};
+    mo.src = p->ops[i].src;
+    mo.off = row;
+    mo.swap2 = 0;
+    p->stream_matlist.push_back(mo);
+    row += B.info[i].entries;
+  }
+  p->stream_mat_row = row;
+  // all matrices of an element stay in shared memory next to the tile
+  const size_t tile_bytes = (size_t(1) << T) * cs;
+  if (tile_bytes + (size_t)row * cs > 96 * 1024) return QMLB_ERR_UNSUPPORTED;
+  B.mat_cap = std::max(row, 1);
+  B.resident = true;
+  const int rc = B.run_stream();
+  if (rc != QMLB_OK) return rc;
+  int max_steps = 1;
+  for (const FramePassHost& ps : B.passes) max_steps = std::max(max_steps, ps.n_steps);
+  p->frame_steps = std::move(B.steps);
+  p->frame_step_ops = std::move(B.step_ops);
+  p->fstream_passes = std::move(B.passes);
+  p->fstream_final_hpos = B.final_hpos;
+  FrameProg& fp = p->frame;
+  std::memset(&fp, 0, sizeof(fp));
+  fp.n_steps = (int)p->frame_steps.size();
+  fp.n_bits = N;
+  fp.tile_bits = T;
+  fp.outer_bits = N - T;
+  fp.team_bits = 8;
+  fp.teams = 1;
+  fp.mat_cap = B.mat_cap;
+  fp.mat_resident = 1;
+  fp.premat_row = row;
+  fp.density = p->density;
+  fp.n_qubits = p->n_qubits;
+  fp.n_obs = (int)p->obs.size();
+  p->fstream_low_bits = L;
+  p->frame_threads = 256;
+  // [tile | matrices | step records of the longest pass | relayout tables | mbarrier]
+  p->frame_smem = tile_bytes + (size_t)B.mat_cap * cs + (size_t)max_steps * sizeof(FrameStep) +
+                  (256 + 64) * sizeof(uint32_t) + 64;
+  return QMLB_OK;
+}
 
 // Fills p->frame_* ; returns QMLB_ERR_UNSUPPORTED (without touching the error string) when
 // the program is outside the engine's envelope so that plan() can fall back.
@@ -603,9 +804,11 @@ int plan_frame(qmlb_program* p) {
   // geometry
   int threads, team_bits, teams;
   if (B.T - FRAME_R >= 8) {
-    // one item per thread; QMLB_FRAME_THREADS=256: two items per thread at 255 registers
+    // T >= 13: 256 threads with two items each at up to 255 registers (measured 4-5 % faster
+    // than 512 threads x one item at 128 registers, which spills); QMLB_FRAME_THREADS=512
+    // selects the latter
     const char* ev = std::getenv("QMLB_FRAME_THREADS");
-    const bool wide = B.T >= 13 && !(ev && std::atoi(ev) == 256);
+    const bool wide = B.T >= 13 && ev && std::atoi(ev) == 512;
     threads = wide ? 512 : 256;
     team_bits = wide ? 9 : 8;
     teams = 1;
@@ -700,6 +903,19 @@ int plan_frame(qmlb_program* p) {
 std::string describe_frame(const qmlb_program* p) {
   std::string s;
   const FrameProg& fp = p->frame;
+  if (!p->fstream_passes.empty()) {
+    s += "fstream low_bits " + std::to_string(p->fstream_low_bits) + " final_hpos";
+    for (int h : p->fstream_final_hpos) s += " " + std::to_string(h);
+    s += "\n";
+    for (const FramePassHost& ps : p->fstream_passes) {
+      s += "pass init " + std::to_string(ps.init ? 1 : 0) + " first " +
+           std::to_string(ps.first_step) + " steps " + std::to_string(ps.n_steps) + " tp";
+      for (int b : ps.tp) s += " " + std::to_string(b);
+      s += " opos";
+      for (int b : ps.opos) s += " " + std::to_string(b);
+      s += "\n";
+    }
+  }
   s += "frame tile_bits " + std::to_string(fp.tile_bits) + " outer_bits " +
        std::to_string(fp.outer_bits) + " team_bits " + std::to_string(fp.team_bits) +
        " teams " + std::to_string(fp.teams) + " threads " + std::to_string(p->frame_threads) +

@@ -33,6 +33,13 @@ struct QmlbStreamPassHost {
   qmlb::StreamPass dev{};
 };
 
+// one HBM pass of the streaming frame engine (strategy 4)
+struct FramePassHost {
+  int first_step = 0, n_steps = 0;
+  bool init = false;           // the pass starts from |0..0> instead of reading the state
+  std::vector<int> tp, opos;   // tile index / tile number bit -> HBM bit position (ascending)
+};
+
 struct qmlb_program {
   int n_qubits = 0, n_bits = 0, density = 0, dtype = 0, out_type = 0;
   std::vector<qmlb_op> ops;
@@ -72,6 +79,11 @@ struct qmlb_program {
   int frame_out_mode = 0;
   bool frame_heavy = false;  // a dense op on 3-4 bits
   size_t frame_smem = 0;
+
+  // strategy 4: streaming frame engine (tiles of an HBM-resident state)
+  std::vector<FramePassHost> fstream_passes;
+  std::vector<int> fstream_final_hpos;   // logical bit -> HBM position after the last pass
+  int fstream_low_bits = 0;
 
   void* blob = nullptr;
   qmlb::DevProg dev{};
@@ -124,7 +136,12 @@ cudaError_t launch_frame_f32(const qmlb_program* p, const RunArgs& R, const void
                              void* out, int out_mode, cudaStream_t st);
 cudaError_t launch_frame_f64(const qmlb_program* p, const RunArgs& R, const void* premats,
                              void* out, int out_mode, cudaStream_t st);
+cudaError_t launch_fstream_f32(const qmlb_program* p, const RunArgs& R, void* state,
+                               const void* premats, int init_mode, cudaStream_t st);
+cudaError_t launch_fstream_f64(const qmlb_program* p, const RunArgs& R, void* state,
+                               const void* premats, int init_mode, cudaStream_t st);
 int plan_frame(qmlb_program* p);                 // QMLB_OK or QMLB_ERR_UNSUPPORTED (fall back)
+int plan_frame_stream(qmlb_program* p);
 std::string describe_frame(const qmlb_program* p);
 cudaError_t tile_set_smem_f32(size_t bytes);
 cudaError_t tile_set_smem_f64(size_t bytes);

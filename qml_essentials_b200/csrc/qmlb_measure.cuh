@@ -242,14 +242,21 @@ __global__ void __launch_bounds__(256) k_expval_z1(const cx<T>* __restrict__ st,
 }
 
 // out[bl][j] = total - 2 * S_{bit(j)} summed over CTAs in index order
+// where each logical state bit lives in memory (identity unless a streamed tile program left
+// the state in a permuted bit order)
+struct BitMap {
+  int8_t pos[40];
+};
+
 template <typename T>
 __global__ void k_expval_z1_final(DevProg P, const double* __restrict__ partial,
-                                  T* __restrict__ out, int64_t batch, int ctas) {
+                                  T* __restrict__ out, int64_t batch, int ctas,
+                                  const BitMap map) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= batch * P.n_obs) return;
   const int64_t bl = i / P.n_obs;
   const int j = (int)(i % P.n_obs);
-  const int bit = 63 - __clzll((unsigned long long)P.obs[j].zmask);
+  const int bit = map.pos[63 - __clzll((unsigned long long)P.obs[j].zmask)];
   double tot = 0, sq = 0;
   for (int c = 0; c < ctas; ++c) {
     const double* row = partial + ((size_t)bl * ctas + c) * 33;

@@ -20,12 +20,24 @@ R, D = 4, 16
 
 def parse(text):
     lines = text.strip().split("\n")
-    assert lines[0] == "strategy 3", lines[0]
-    head = lines[1].split()
-    geo = {head[i]: int(head[i + 1]) for i in range(1, len(head), 2)}
+    assert lines[0] in ("strategy 3", "strategy 4"), lines[0]
+    geo = {"passes": []}
     steps = []
-    for line in lines[2:]:
+    for line in lines[1:]:
         tok = line.split()
+        if tok[0] == "frame":
+            geo.update({tok[i]: int(tok[i + 1]) for i in range(1, len(tok), 2)})
+            continue
+        if tok[0] == "fstream":
+            geo["low_bits"] = int(tok[2])
+            geo["final_hpos"] = [int(x) for x in tok[4:]]
+            continue
+        if tok[0] == "pass":
+            it, io = tok.index("tp"), tok.index("opos")
+            geo["passes"].append(dict(init=int(tok[2]), first=int(tok[4]), steps=int(tok[6]),
+                                      tp=[int(x) for x in tok[it + 1:io]],
+                                      opos=[int(x) for x in tok[io + 1:]]))
+            continue
         if tok[0] == "relayout":
             local = tok[1] == "local"
             steps.append(("relayout", [int(x) for x in tok[(2 if local else 1):]], local))
@@ -95,6 +107,27 @@ def emulate(prog, text, args, batch):
 
     st = np.zeros((batch, 1 << N), dtype=np.complex128)
     st[:, 0] = 1.0
+    if geo["passes"]:  # streamed tiles: HBM layout <-> (tile number, tile index) per pass
+        idx = np.arange(1 << N, dtype=np.int64)
+        for ps in geo["passes"]:
+            assert ps["tp"][:geo["low_bits"]] == list(range(geo["low_bits"]))
+            assert sorted(ps["tp"] + ps["opos"]) == list(range(N))
+            hbm = np.zeros(1 << N, dtype=np.int64)
+            for i, b in enumerate(ps["tp"] + ps["opos"]):
+                hbm |= ((idx >> i) & 1) << b
+            virt = st[:, hbm]
+            virt = _run_steps(virt, steps[ps["first"]:ps["first"] + ps["steps"]], T, G, N,
+                              matrix, batch, local_only=True)
+            st = np.empty_like(virt)
+            st[:, hbm] = virt
+        logical = np.zeros(1 << N, dtype=np.int64)  # HBM index of logical index l
+        for j, h in enumerate(geo["final_hpos"]):
+            logical |= ((idx >> j) & 1) << h
+        return st[:, logical]
+    return _run_steps(st, steps, T, G, N, matrix, batch)
+
+
+def _run_steps(st, steps, T, G, N, matrix, batch, local_only=False):
     tile_mask = (1 << T) - 1
     items = np.arange(1 << (T - R), dtype=np.int64)
     for step in steps:
@@ -105,6 +138,7 @@ def emulate(prog, text, args, batch):
             for b in range(N):
                 src ^= np.where((d >> b) & 1, qcol[b], 0)
             assert np.array_equal(np.sort(src), d), "relayout is not a permutation"
+            assert step[2] or not local_only, "a streamed pass can only shuffle inside the tile"
             if step[2]:
                 assert np.array_equal(src >> T, d >> T), "tile-local shuffle crosses CTAs"
             elif G > 0:
@@ -242,7 +276,7 @@ class FrameEmuExecutor:
         args = [(a[0], a[1], a[2]) if a is not None else (None, 1, 1) for a in host_args]
         text = backend.plan_describe(self.lib, plan.program, plan.out_type, plan.obs_recs,
                                      plan.obs_pool, plan.precision)
-        if text.startswith("strategy 3"):
+        if text.startswith(("strategy 3", "strategy 4")):
             st = emulate(plan.program, text, args, batch)
             self.frame_runs += 1
             self.steps.append(text)

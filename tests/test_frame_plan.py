@@ -78,7 +78,7 @@ def test_config4_schedule_shape(lib):
     tile-local shuffle); every CX is folded (no permutation op reaches the kernel)."""
     ex, err = _both(lib, 8, 4, "Strongly_Entangling", "expval", NOISE, B_I=1, B_P=1)
     geo, steps = fe.parse(ex.steps[0])
-    assert (geo["tile_bits"], geo["outer_bits"], geo["threads"]) == (13, 3, 512)
+    assert (geo["tile_bits"], geo["outer_bits"], geo["threads"]) == (13, 3, 256)
     n_sub = sum(1 for s in steps if s[0] == "subpass")
     n_exch = sum(1 for s in steps if s[0] == "relayout" and not s[2])
     n_local = sum(1 for s in steps if s[0] == "relayout" and s[2])
@@ -89,3 +89,41 @@ def test_config4_schedule_shape(lib):
             assert all((o["j0"], o["j1"]) in ((3, 2), (1, 0)) for o in s[4] if o["code"] == 1)
             assert s[5] >= 16  # straight-line fast path
     assert err < 1e-12
+
+
+@pytest.mark.parametrize("n,L,ct,precision", [
+    (12, 2, "Hardware_Efficient", "complex128"),
+    (14, 3, "Hardware_Efficient", "complex128"),
+    (13, 2, "Circuit_19", "complex128"),
+    (12, 2, "Strongly_Entangling", "complex128"),
+    (13, 1, "Circuit_9", "complex128"),
+])
+def test_streamed_tile_schedules(lib, monkeypatch, n, L, ct, precision):
+    """Strategy 4 (state in HBM, tile passes): with the tile shrunk to 2^10 amplitudes the
+    emulator can run whole schedules - HBM bit layout per pass, bits that stay / arrive /
+    leave between passes, final bit map of the <Z> sweep."""
+    monkeypatch.setenv("QMLB_FSTREAM_TILE_BITS", "10")
+    monkeypatch.setenv("QMLB_FSTREAM_LOW_BITS", "5")
+    monkeypatch.setenv("QMLB_FRAME", "0")
+    ex, err = _both(lib, n, L, ct, "expval", None, precision, B_I=1, B_P=2)
+    assert ex.frame_runs == 1 and ex.steps[0].startswith("strategy 4")
+    geo, steps = fe.parse(ex.steps[0])
+    assert len(geo["passes"]) >= 2 and sorted(geo["final_hpos"]) == list(range(n))
+    assert sum(p["steps"] for p in geo["passes"]) == len(steps)
+    assert err < 1e-12
+
+
+def test_config5_pass_count(lib):
+    """BASELINE config 5 (32 qubits, 8 layers Hardware_Efficient, complex64): 1 408 tape
+    gates -> at most 20 HBM passes (the register-group stream of round 1 needed 77), every
+    step on a straight-line fast path."""
+    import test_cabi
+
+    plan = test_cabi._plan_of(32, 8, "Hardware_Efficient", "complex64")
+    text = backend.plan_describe(lib, plan.program, plan.out_type, plan.obs_recs, plan.obs_pool,
+                                 "complex64")
+    assert text.startswith("strategy 4")
+    geo, steps = fe.parse(text)
+    assert len(geo["passes"]) <= 20
+    assert all(s[5] >= 64 for s in steps if s[0] == "subpass")
+    assert all(s[2] for s in steps if s[0] == "relayout")

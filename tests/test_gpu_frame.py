@@ -95,3 +95,38 @@ def test_frame_engine_is_selected():
         h = backend.ProgramHandle(ex.lib, plan.program, plan.out_type, plan.obs_recs,
                                   plan.obs_pool, "complex128")
         assert h.strategy == 3
+
+
+@pytest.mark.parametrize("precision", ["complex128", "complex64"])
+@pytest.mark.parametrize("n,L,ct,B_I,B_P", [
+    (18, 2, "Hardware_Efficient", 1, 1),
+    (18, 1, "Hardware_Efficient", 2, 2),
+    (19, 1, "Circuit_19", 1, 1),
+    (18, 1, "Strongly_Entangling", 1, 2),
+])
+def test_streamed_tiles_parity(precision, n, L, ct, B_I, B_P):
+    """Strategy 4: HBM-resident state, tile passes through shared memory moved by bulk (TMA)
+    copies - against the oracle."""
+    err = pc.case_model(n, L, ct, B_I, B_P, "expval", precision=precision)
+    assert err < pc.TOL[precision]
+
+
+def test_streamed_tiles_equal_register_group_stream(monkeypatch):
+    """n = 24: the tile passes (strategy 4) and round 1's register-group passes
+    (QMLB_FSTREAM=0 -> strategy 2) are independent schedules of the same circuit."""
+    from qml_essentials_b200 import backend
+    import test_cabi
+
+    ex = get_executor()
+    outs = {}
+    for fs in ("1", "0"):
+        monkeypatch.setenv("QMLB_FSTREAM", fs)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            m = Model(24, 3, "Hardware_Efficient", precision="complex64")
+            params = np.random.default_rng(3).uniform(0, 2 * np.pi, (1, *m._params_shape))
+            outs[fs] = np.asarray(m(params=params, inputs=np.array([[0.5]])))
+        plan = [p for p in m.script._jit_cache.values() if hasattr(p, "program") and p.device][-1]
+        assert list(plan.device.values())[0].strategy == (4 if fs == "1" else 2)
+    assert np.abs(outs["1"] - outs["0"]).max() < 2e-5
+    assert np.all(np.abs(outs["1"]) <= 1 + 1e-5)
