@@ -213,9 +213,27 @@ def sharded_leg(world, rank, local_bits=30):
         torch.cuda.synchronize()
         dist.barrier()
         dt = time.perf_counter() - t0
-        return {"workload": f"Model({n},8,'Hardware_Efficient') complex64 expval, qubit-sharded "
-                            f"over {world} GPUs ({local_bits} local bits)", "n_qubits": n,
-                "seconds": dt, **se.stats, "abs_expval_le_1": bool(np.all(np.abs(ev) <= 1 + 1e-4))}
+        res = {"workload": f"Model({n},8,'Hardware_Efficient') complex64 expval, qubit-sharded "
+                           f"over {world} GPUs ({local_bits} local bits)", "n_qubits": n,
+               "seconds": dt, **se.stats, "abs_expval_le_1": bool(np.all(np.abs(ev) <= 1 + 1e-4))}
+        # parity on hardware: the same kind of circuit at n = 28, sharded over all ranks vs
+        # evolved on ONE GPU (rank 0, streaming frame engine)
+        try:
+            m28 = Model(n_qubits=28, n_layers=8, circuit_type="Hardware_Efficient")
+            p28 = np.random.default_rng(7).uniform(0.0, 2 * np.pi, (1, *m28._params_shape))
+            m28.script.executor = ShardedExecutor()
+            sh28 = np.asarray(m28(params=p28, inputs=inputs)).reshape(-1)
+            torch.cuda.synchronize()
+            dist.barrier()
+            if rank == 0:
+                m28.script.executor = None
+                one = np.asarray(m28(params=p28, inputs=inputs)).reshape(-1)
+                res["max_abs_err_vs_single_gpu"] = float(np.abs(sh28 - one).max())
+                res["parity_check"] = "n = 28, same circuit family, all ranks vs rank 0 alone"
+            dist.barrier()
+        except Exception as exc:  # noqa: BLE001
+            res["parity_check_error"] = f"{type(exc).__name__}: {exc}"[:200]
+        return res
     finally:
         config.set_precision(prev)
 
@@ -455,7 +473,8 @@ def main():
     def step_device():
         out = call.launch()  # (B, 4) expvals, flat order b = i * B_P + p
         st = torch.cuda.current_stream(dev).cuda_stream
-        rc = lib.qmlb_grid_dft(out.data_ptr(), dt_code, B_I, B_P, N_QUBITS, coef.data_ptr(), st)
+        rc = lib.qmlb_grid_dft(out.data_ptr(), dt_code, B_I, B_P, N_QUBITS, None,
+                               coef.data_ptr(), st)
         rc |= lib.qmlb_coef_moments(coef.data_ptr(), dt_code, rows.data_ptr(), K, B_P,
                                     moments.data_ptr(), st)
         if world > 1 and peer_ptrs is not None:
@@ -476,6 +495,12 @@ def main():
     for _ in range(args.warmup):
         step_device()
     barrier()
+    collective_err = None
+    if world > 1 and peer_ptrs is not None:  # the one-shot all-reduce against NCCL's
+        want = moments.clone()
+        dist.all_reduce(want)
+        torch.cuda.synchronize()
+        collective_err = float((reduced - want).abs().max())
 
     # The step is launch-bound at this size (k_pre x2 + k_reg + the statistics kernels + one
     # small NCCL all-reduce): capture it once in a CUDA graph and replay it.
@@ -560,7 +585,9 @@ def main():
     if world > 1 and gp_n > 0:
         torch.cuda.empty_cache()
         try:
-            sh = sharded_leg(world, rank, min(gp_n, 30))
+            # 8 GPUs: BASELINE configs[4] - n = 35, 32 local bits (32 GiB shard + exchange
+            # buffer per GPU); fewer ranks: 30 local bits
+            sh = sharded_leg(world, rank, 32 if world == 8 and gp_n >= 30 else min(gp_n, 30))
         except Exception as exc:  # noqa: BLE001
             sh = {"error": f"{type(exc).__name__}: {exc}"[:300]}
     clocks = sampler.stop() if rank == 0 else None
@@ -598,6 +625,7 @@ def main():
                 "step": "k_pre x2, k_reg, k_grid_dft, k_coef_moments"
                         + (", k_allreduce_oneshot" if peer_ptrs is not None else ""),
                 "collective": collective, "stat_bytes": n_stat * 8,
+                "collective_max_abs_err_vs_nccl": collective_err,
             },
             "e2e": {"value": e2e_value, "unit": "evals/s",
                     "h2d_bytes_per_step": int(params.nbytes + inputs.nbytes),

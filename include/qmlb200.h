@@ -268,10 +268,13 @@ int qmlb_overlap_fidelity(const void* states, int dtype, int64_t half, int32_t n
  * qmlb_grid_dft: the transform of Coefficients._fourier_transform (coefficients.py:128-150)
  * for ONE input feature.  ev: (n_x, n_p, n_obs) real expectation values (real of the given
  * precision) as `Model.__call__` returns them for an n_x-point input grid and n_p parameter
- * samples; out[k][p] = (1 / n_x) sum_x mean_obs(ev[x][p][:]) exp(-2 pi i k x / n_x) for
- * k = 0 .. n_x - 1 (numpy.fft order), (n_x, n_p) complex of the given precision. */
-int qmlb_grid_dft(const void* ev, int dtype, int32_t n_x, int64_t n_p, int32_t n_obs, void* out,
-                  void* stream);
+ * samples; coefficient k = (1 / n_x) sum_x mean_obs(ev[x][p][:]) exp(-2 pi i k x / n_x) for
+ * k = 0 .. n_x - 1 (numpy.fft order) is written to out[row_of[k]][p] (row_of == NULL: row k;
+ * row_of[k] < 0: dropped) - a device array of n_x entries that lets the caller fold
+ * get_spectrum's fftshift / trim (coefficients.py:72-84) into the store.  out: (rows, n_p)
+ * complex of the given precision. */
+int qmlb_grid_dft(const void* ev, int dtype, int32_t n_x, int64_t n_p, int32_t n_obs,
+                  const int32_t* row_of, void* out, void* stream);
 
 /* Additive sufficient statistics of the FCC correlation estimators
  * (coefficients.py:1346-1498) over the n_p samples of K selected coefficient rows

@@ -102,7 +102,7 @@ def load_library(path: str = LIB_PATH) -> C.CDLL:
                                      C.POINTER(C.c_void_p), C.c_int32, C.c_int32, C.c_void_p,
                                      C.c_size_t, C.c_void_p]
     lib.qmlb_grid_dft.argtypes = [C.c_void_p, C.c_int, C.c_int32, C.c_int64, C.c_int32,
-                                  C.c_void_p, C.c_void_p]
+                                  C.c_void_p, C.c_void_p, C.c_void_p]
     lib.qmlb_coef_moments.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int32, C.c_int64,
                                       C.c_void_p, C.c_void_p]
     lib.qmlb_allreduce_buffer_bytes.argtypes = [C.c_int64]
@@ -257,6 +257,7 @@ class CudaExecutor:
                 "execution path")
         self.lib = load_library()
         self.torch = torch
+        self._cache = {}
         self.device = torch.device("cuda", torch.cuda.current_device() if device is None
                                    else device)
 
@@ -380,19 +381,40 @@ class CudaExecutor:
             raise BackendError(f"qmlb_overlap_fidelity: {self.lib.qmlb_last_error().decode()}")
         return out
 
-    def grid_dft(self, ev):
-        """(n_x, n_p, n_obs) real device expvals -> (n_x, n_p) complex coefficients
-        (mean over observables, DFT along the grid axis, 1/n_x normalisation)."""
+    def grid_dft(self, ev, order=None):
+        """(n_x, n_p, n_obs) real device expvals -> complex coefficients (mean over
+        observables, DFT along the grid axis, 1/n_x normalisation).  ``order``: the
+        frequencies (numpy.fft indices) wanted, in output-row order - shift / trim folded
+        into the store; default all of them in numpy.fft order."""
         torch = self.torch
         n_x, n_p, n_obs = ev.shape
         dt = QMLB_C128 if ev.dtype == torch.float64 else QMLB_C64
-        out = torch.empty((n_x, n_p), dtype=torch.complex128 if dt else torch.complex64,
+        n_rows, row_of = n_x, None
+        if order is not None:
+            order = np.asarray(order, dtype=np.int64)
+            n_rows = len(order)
+            table = np.full(n_x, -1, dtype=np.int32)
+            table[order] = np.arange(n_rows, dtype=np.int32)
+            key = ("dft_rows", n_x, order.tobytes())
+            row_of = self._cache.get(key)
+            if row_of is None:
+                row_of = self._cache[key] = torch.from_numpy(table).to(ev.device)
+        out = torch.empty((n_rows, n_p), dtype=torch.complex128 if dt else torch.complex64,
                           device=ev.device)
-        rc = self.lib.qmlb_grid_dft(ev.data_ptr(), dt, n_x, n_p, n_obs, out.data_ptr(),
+        rc = self.lib.qmlb_grid_dft(ev.data_ptr(), dt, n_x, n_p, n_obs,
+                                    row_of.data_ptr() if row_of is not None else None,
+                                    out.data_ptr(),
                                     torch.cuda.current_stream(ev.device).cuda_stream)
         if rc != 0:
             raise BackendError(f"qmlb_grid_dft: {self.lib.qmlb_last_error().decode()}")
         return out
+
+    def to_host(self, t) -> np.ndarray:
+        """Device tensor -> NumPy through pinned staging."""
+        host = self.torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+        host.copy_(t, non_blocking=True)
+        self.torch.cuda.current_stream(t.device).synchronize()
+        return host.numpy()
 
     def coef_moments(self, coef, rows):
         """Sufficient statistics over the samples of the selected coefficient rows:

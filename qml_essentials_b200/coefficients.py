@@ -42,22 +42,21 @@ class Coefficients:
         kwargs.setdefault("force_mean", True)
         kwargs.setdefault("execution_type", "expval")
 
-        coeffs, freqs = cls._fourier_transform(model, mfs=mfs, mts=mts, **kwargs)
-
-        if not np.isclose(np.sum(coeffs).imag, 0.0, atol=1.0e-6):
-            raise ValueError(
-                f"Spectrum is not real. Imaginary part of coefficients is: {np.sum(coeffs).imag}")
-
-        if trim:
-            for ax in range(model.n_input_feat):
-                if coeffs.shape[ax] % 2 == 0:
-                    mid = len(coeffs) // 2  # same index rule as coefficients.py:76-77
-                    coeffs = np.delete(coeffs, mid, axis=ax)
-                    freqs = [np.delete(f, len(f) // 2, axis=ax) for f in freqs]
-
-        if shift:
-            coeffs = np.fft.fftshift(coeffs, axes=list(range(model.n_input_feat)))
-            freqs = list(np.fft.fftshift(np.asarray(freqs)))
+        dev = cls._device_spectrum(model, mfs, mts, shift, trim, **kwargs)
+        if dev is not None:
+            coeffs, freqs = dev
+        else:
+            coeffs, freqs = cls._fourier_transform(model, mfs=mfs, mts=mts, **kwargs)
+            cls._check_real(coeffs)
+            if trim:
+                for ax in range(model.n_input_feat):
+                    if coeffs.shape[ax] % 2 == 0:
+                        mid = len(coeffs) // 2  # same index rule as coefficients.py:76-77
+                        coeffs = np.delete(coeffs, mid, axis=ax)
+                        freqs = [np.delete(f, len(f) // 2, axis=ax) for f in freqs]
+            if shift:
+                coeffs = np.fft.fftshift(coeffs, axes=list(range(model.n_input_feat)))
+                freqs = list(np.fft.fftshift(np.asarray(freqs)))
 
         if numerical_cap is not None and numerical_cap > 0:
             coeffs = np.where(np.abs(coeffs) < numerical_cap, np.zeros_like(coeffs), coeffs)
@@ -73,6 +72,53 @@ class Coefficients:
             freqs = freqs[0]
         return coeffs, freqs
 
+    @staticmethod
+    def _check_real(coeffs) -> None:
+        if not np.isclose(np.sum(coeffs).imag, 0.0, atol=1.0e-6):
+            raise ValueError(
+                f"Spectrum is not real. Imaginary part of coefficients is: {np.sum(coeffs).imag}")
+
+    @classmethod
+    def _device_spectrum(cls, model: Model, mfs: int, mts: int, shift: bool, trim: bool,
+                         **kwargs: Any):
+        """One input feature, expectation values averaged over the observables: the mean
+        over qubits, the DFT along the grid axis AND get_spectrum's trim / shift run on the
+        GPU right behind the circuit kernel (``qmlb_grid_dft`` writes coefficient k to the
+        row it has after ``np.delete`` / ``np.fft.fftshift``, coefficients.py:72-84), so only
+        the final coefficient array leaves the device.  Returns ``None``
+        when the host route of the reference applies (several features, shots, other
+        execution types, ``QMLB_HOST_FFT=1``)."""
+        if (model.n_input_feat != 1 or kwargs.get("execution_type") != "expval"
+                or not kwargs.get("force_mean", False) or model.shots is not None
+                or os.environ.get("QMLB_HOST_FFT") == "1"):
+            return None
+        from .script import get_executor
+
+        ex = model.script.executor or get_executor()
+        if not hasattr(ex, "grid_dft"):
+            return None
+        n_freqs = mfs * model.degree[0]
+        grid = np.arange(0, 2 * mts * np.pi, 2 * np.pi / n_freqs).reshape(-1, 1)
+        n_x = grid.shape[0]
+        freqs = np.fft.fftfreq(int(mts * n_freqs), 1 / n_freqs)
+        order = np.arange(n_x)
+        if trim and n_x % 2 == 0:
+            order = np.delete(order, n_x // 2)
+            freqs = np.delete(freqs, len(freqs) // 2)
+        if shift:
+            order = np.fft.fftshift(order)
+            freqs = np.fft.fftshift(freqs)
+        kw = {k: v for k, v in kwargs.items() if k != "force_mean"}
+        ev = model.device_result(inputs=grid, **kw)
+        coef = ex.grid_dft(ev.reshape(n_x, -1, ev.shape[-1]), order)
+        coeffs = np.asarray(ex.to_host(coef)).squeeze()
+        # the kernel writes coefficient n - k as the conjugate of coefficient k, so the
+        # imaginary parts cancel pairwise; only the self-conjugate rows (k = 0, n / 2) can
+        # carry the imbalance the reference tests for (coefficients.py:66-70)
+        self_conj = [r for r, k in enumerate(order) if (2 * k) % n_x == 0]
+        cls._check_real(coeffs[self_conj])
+        return coeffs, [freqs]
+
     @classmethod
     def _fourier_transform(cls, model: Model, mfs: int, mts: int, **kwargs: Any):
         """Sample the model on an equidistant grid and transform
@@ -85,23 +131,6 @@ class Coefficients:
         grid = np.array(np.meshgrid(*axes)).T.reshape(-1, F)
 
         freqs = [np.fft.fftfreq(int(mts * n_freqs[i]), 1 / n_freqs[i]) for i in range(F)]
-
-        # One input feature, expectation values averaged over the observables: the mean and
-        # the DFT along the grid axis run on the GPU (qmlb_grid_dft) right behind the circuit
-        # kernel, and only the coefficients leave the device.
-        # QMLB_HOST_FFT=1 keeps the reference's host route (numpy.fft.fftn).
-        if (F == 1 and kwargs.get("execution_type", "expval") == "expval"
-                and kwargs.get("force_mean", False) and model.shots is None
-                and os.environ.get("QMLB_HOST_FFT") != "1"):
-            from .script import get_executor
-
-            ex = model.script.executor or get_executor()
-            if hasattr(ex, "grid_dft"):
-                kw = {k: v for k, v in kwargs.items() if k != "force_mean"}
-                ev = model.device_result(inputs=grid, **kw)
-                n_x = axes[0].shape[0]
-                coef = ex.grid_dft(ev.reshape(n_x, -1, ev.shape[-1]))
-                return np.asarray(coef.cpu().numpy()).squeeze(), freqs
 
         out = np.asarray(model(inputs=grid, **kwargs))
         out = out.reshape(*[a.shape[0] for a in axes], -1).squeeze()

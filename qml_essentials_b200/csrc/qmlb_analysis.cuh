@@ -9,17 +9,21 @@
 
 namespace qmlb {
 
-constexpr int DFT_PCOLS = 32;  // parameter samples per CTA
+constexpr int DFT_PCOLS = 8;  // parameter samples per CTA
 
-// out[k][p] = (1 / n_x) * sum_x s[x][p] * exp(-2 pi i k x / n_x),
+// out[row_of[k]][p] = (1 / n_x) * sum_x s[x][p] * exp(-2 pi i k x / n_x),
 // s[x][p] = mean over the n_obs observables of ev[x][p][:]   (ev: (n_x, n_p, n_obs) real)
 // One CTA = DFT_PCOLS samples x all frequencies; the signal tile and the twiddle table sit
-// in shared memory (double precision throughout), x is summed in index order.
+// in shared memory (double precision throughout), x is summed in index order.  The signal
+// is real, so only k <= n_x / 2 is summed and coefficient n_x - k is written as the
+// conjugate.  row_of (optional) places frequency k on an output row of the caller's choice
+// (-1 = not wanted): get_spectrum's shift / trim cost nothing.
 template <typename T>
 __global__ void __launch_bounds__(256) k_grid_dft(const T* __restrict__ ev, int n_x, int64_t n_p,
-                                                  int n_obs, cx<T>* __restrict__ out) {
+                                                  int n_obs, const int32_t* __restrict__ row_of,
+                                                  cx<T>* __restrict__ out) {
   extern __shared__ __align__(16) unsigned char dsm[];
-  double* sig = reinterpret_cast<double*>(dsm);                  // [n_x][DFT_PCOLS]
+  double* sig = reinterpret_cast<double*>(dsm);                             // [n_x][DFT_PCOLS]
   double2* tw = reinterpret_cast<double2*>(sig + (size_t)n_x * DFT_PCOLS);  // [n_x]
   const int64_t p0 = (int64_t)blockIdx.x * DFT_PCOLS;
   for (int i = threadIdx.x; i < n_x * DFT_PCOLS; i += blockDim.x) {
@@ -40,7 +44,7 @@ __global__ void __launch_bounds__(256) k_grid_dft(const T* __restrict__ ev, int 
   __syncthreads();
   const int c = threadIdx.x % DFT_PCOLS;
   const double inv = 1.0 / (double)n_x;
-  for (int k = threadIdx.x / DFT_PCOLS; k < n_x; k += blockDim.x / DFT_PCOLS) {
+  for (int k = threadIdx.x / DFT_PCOLS; k <= n_x / 2; k += blockDim.x / DFT_PCOLS) {
     double re = 0.0, im = 0.0;
     int idx = 0;  // (k * x) mod n_x
     for (int x = 0; x < n_x; ++x) {
@@ -51,7 +55,15 @@ __global__ void __launch_bounds__(256) k_grid_dft(const T* __restrict__ ev, int 
       idx += k;
       if (idx >= n_x) idx -= n_x;
     }
-    if (p0 + c < n_p) out[(size_t)k * n_p + p0 + c] = mk<T>((T)(re * inv), (T)(im * inv));
+    if (p0 + c < n_p) {
+      const int r0 = row_of ? row_of[k] : k;
+      if (r0 >= 0) out[(size_t)r0 * n_p + p0 + c] = mk<T>((T)(re * inv), (T)(im * inv));
+      const int km = (n_x - k) % n_x;
+      if (km != k) {
+        const int r1 = row_of ? row_of[km] : km;
+        if (r1 >= 0) out[(size_t)r1 * n_p + p0 + c] = mk<T>((T)(re * inv), (T)(-im * inv));
+      }
+    }
   }
 }
 
@@ -59,37 +71,42 @@ __global__ void __launch_bounds__(256) k_grid_dft(const T* __restrict__ ev, int 
 //   out[i]             = sum_p c_i(p)                 i < K
 //   out[K + i]         = sum_p |c_i(p)|^2 (real)
 //   out[2K + i*K + j]  = sum_p conj(c_i(p)) * c_j(p)
-// complex128 accumulators, p in index order (bitwise reproducible).
+// One WARP per output: lanes stride over the samples (coalesced), complex128 accumulators,
+// fixed xor-shuffle tree - bitwise reproducible.
 template <typename T>
-__global__ void k_coef_moments(const cx<T>* __restrict__ coef, const int32_t* __restrict__ rows,
-                               int K, int64_t n_p, double2* __restrict__ out) {
-  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(256) k_coef_moments(const cx<T>* __restrict__ coef,
+                                                      const int32_t* __restrict__ rows, int K,
+                                                      int64_t n_p, double2* __restrict__ out) {
+  const int64_t t = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
   if (t >= (int64_t)K * K + 2 * K) return;
+  double re = 0.0, im = 0.0;
   if (t < 2 * K) {
-    const int i = (int)(t % K);
-    const cx<T>* ci = coef + (size_t)rows[i] * n_p;
-    double re = 0.0, im = 0.0;
+    const cx<T>* ci = coef + (size_t)rows[t % K] * n_p;
     if (t < K) {
-      for (int64_t p = 0; p < n_p; ++p) {
+      for (int64_t p = lane; p < n_p; p += 32) {
         re += (double)ci[p].x;
         im += (double)ci[p].y;
       }
     } else {
-      for (int64_t p = 0; p < n_p; ++p) re += (double)ci[p].x * ci[p].x + (double)ci[p].y * ci[p].y;
+      for (int64_t p = lane; p < n_p; p += 32)
+        re += (double)ci[p].x * ci[p].x + (double)ci[p].y * ci[p].y;
     }
-    out[t] = make_double2(re, im);
-    return;
+  } else {
+    const int i = (int)((t - 2 * K) / K), j = (int)((t - 2 * K) % K);
+    const cx<T>* ci = coef + (size_t)rows[i] * n_p;
+    const cx<T>* cj = coef + (size_t)rows[j] * n_p;
+    for (int64_t p = lane; p < n_p; p += 32) {
+      const double ar = ci[p].x, ai = ci[p].y, br = cj[p].x, bi = cj[p].y;
+      re += ar * br + ai * bi;  // conj(a) * b
+      im += ar * bi - ai * br;
+    }
   }
-  const int i = (int)((t - 2 * K) / K), j = (int)((t - 2 * K) % K);
-  const cx<T>* ci = coef + (size_t)rows[i] * n_p;
-  const cx<T>* cj = coef + (size_t)rows[j] * n_p;
-  double re = 0.0, im = 0.0;
-  for (int64_t p = 0; p < n_p; ++p) {
-    const double ar = ci[p].x, ai = ci[p].y, br = cj[p].x, bi = cj[p].y;
-    re += ar * br + ai * bi;   // conj(a) * b
-    im += ar * bi - ai * br;
+  for (int off = 16; off > 0; off >>= 1) {
+    re += __shfl_xor_sync(0xffffffffu, re, off);
+    im += __shfl_xor_sync(0xffffffffu, im, off);
   }
-  out[t] = make_double2(re, im);
+  if (lane == 0) out[t] = make_double2(re, im);
 }
 
 // One-shot all-reduce (sum) of n doubles over peer-mapped buffers, ONE CTA per rank.

@@ -1269,8 +1269,8 @@ int qmlb_overlap_fidelity(const void* states, int dtype, int64_t half, int32_t n
   return QMLB_OK;
 }
 
-int qmlb_grid_dft(const void* ev, int dtype, int32_t n_x, int64_t n_p, int32_t n_obs, void* out,
-                  void* stream) {
+int qmlb_grid_dft(const void* ev, int dtype, int32_t n_x, int64_t n_p, int32_t n_obs,
+                  const int32_t* row_of, void* out, void* stream) {
   if (!ev || !out) return fail(QMLB_ERR_INVALID, "null argument");
   if (n_x < 1 || n_p < 1 || n_obs < 1) return fail(QMLB_ERR_INVALID, "empty grid");
   const size_t smem = (size_t)n_x * DFT_PCOLS * sizeof(double) + (size_t)n_x * sizeof(double2);
@@ -1283,13 +1283,13 @@ int qmlb_grid_dft(const void* ev, int dtype, int32_t n_x, int64_t n_p, int32_t n
       CUDA_TRY(cudaFuncSetAttribute(k_grid_dft<double>,
                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k_grid_dft<double><<<grid, 256, smem, st>>>(static_cast<const double*>(ev), n_x, n_p, n_obs,
-                                                static_cast<cx<double>*>(out));
+                                                row_of, static_cast<cx<double>*>(out));
   } else {
     if (smem > 48 * 1024)
       CUDA_TRY(cudaFuncSetAttribute(k_grid_dft<float>,
                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k_grid_dft<float><<<grid, 256, smem, st>>>(static_cast<const float*>(ev), n_x, n_p, n_obs,
-                                               static_cast<cx<float>*>(out));
+                                               row_of, static_cast<cx<float>*>(out));
   }
   CUDA_TRY(cudaGetLastError());
   return QMLB_OK;
@@ -1303,10 +1303,10 @@ int qmlb_coef_moments(const void* coef, int dtype, const int32_t* rows, int32_t 
   const int64_t total = (int64_t)K * K + 2 * K;
   g_launches.fetch_add(1, std::memory_order_relaxed);
   if (dtype == QMLB_C128)
-    k_coef_moments<double><<<(unsigned)((total + 127) / 128), 128, 0, st>>>(
+    k_coef_moments<double><<<(unsigned)((total * 32 + 255) / 256), 256, 0, st>>>(
         static_cast<const cx<double>*>(coef), rows, K, n_p, static_cast<double2*>(out));
   else
-    k_coef_moments<float><<<(unsigned)((total + 127) / 128), 128, 0, st>>>(
+    k_coef_moments<float><<<(unsigned)((total * 32 + 255) / 256), 256, 0, st>>>(
         static_cast<const cx<float>*>(coef), rows, K, n_p, static_cast<double2*>(out));
   CUDA_TRY(cudaGetLastError());
   return QMLB_OK;

@@ -648,8 +648,10 @@ int Builder::run_stream() {
     std::vector<int> order(N);
     for (int j = 0; j < N; ++j) order[j] = j;
     std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return nn[a] < nn[b]; });
+    // ... soonest-needed on the HIGHEST tile positions: register groups then sit above the
+    // lane bits and the shared-memory accesses of a warp stay contiguous (no bank conflicts)
     hpos.assign(N, 0);
-    for (int r = 0; r < N; ++r) hpos[order[r]] = r;
+    for (int r = 0; r < N; ++r) hpos[order[r]] = r < T ? T - 1 - r : r;
     tp.resize(T);
     for (int i = 0; i < T; ++i) tp[i] = i;
   }
@@ -693,8 +695,10 @@ int Builder::run_stream() {
         leaving.push_back(j);
     // staying bits: the low run first, then the lowest high tile indices; leaving bits on
     // the highest tile indices (those HBM positions drop out of the next tile)
+    // (the low run takes the staying bits that are needed LAST: gate bits on low tile
+    // positions would make the lanes of a warp stride through shared memory)
     std::vector<int> at(T);
-    for (size_t i = 0; i < staying.size(); ++i) at[i] = staying[i];
+    for (size_t i = 0; i < staying.size(); ++i) at[i] = staying[staying.size() - 1 - i];
     for (size_t i = 0; i < leaving.size(); ++i) at[staying.size() + i] = leaving[i];
     close_pass(at);
     std::vector<int> ntp;

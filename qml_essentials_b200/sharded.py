@@ -44,23 +44,48 @@ from . import compiler, parallel
 from .compiler import OP_DIAG, OP_PERM, Program
 
 _SWAP_PERM = (0.0, 2.0, 1.0, 3.0)  # new[v] = old[perm[v]] exchanges the two bits
+_X_PERM = (1.0, 0.0)
+_CX_CONTROL_FIRST = (0, 1, 3, 2)     # CX with control = bits[0]
+_CX_CONTROL_SECOND = (0, 3, 2, 1)    # CX with control = bits[1]
 
 
-def plan_epochs(prog: Program, g: int):
+def plan_epochs(prog: Program, g: int, rank: int = 0):
     """Cut ``prog.ops`` into epochs of local ops separated by exchanges.
 
     Returns ``(steps, pos, consts)``: ``steps`` is a list of ``("ops", ndarray of
     OP_DTYPE with PHYSICAL local bits)`` and ``("exchange",)`` entries, ``pos`` the final
-    logical -> physical map, ``consts`` the constant pool extended by the SWAP table."""
+    logical -> physical map, ``consts`` the constant pool extended by the SWAP table.
+
+    An op whose GLOBAL bits are all controls needs no exchange: on this rank the control
+    value is a constant (a bit of ``rank``), so CX / controlled 2x2 gates with a global
+    control become a plain X / 2x2 on the target or nothing at all.  The exchange schedule
+    does not depend on ``rank`` (every rank cuts the epochs at the same ops); only the ops
+    emitted for such gates do."""
     n = prog.n_bits
     nl = n - g
     if g < 0 or nl < g:
         raise ValueError(f"cannot shard {n} state bits over 2^{g} ranks")
-    consts = np.concatenate([np.asarray(prog.consts, dtype=np.float64), _SWAP_PERM])
+    consts = np.concatenate([np.asarray(prog.consts, dtype=np.float64), _SWAP_PERM, _X_PERM])
     swap_aux = len(prog.consts)
+    x_aux = swap_aux + len(_SWAP_PERM)
     pos = list(range(n))
     ops = prog.ops
     bits_of = [list(int(b) for b in o["bits"][: o["k"]]) for o in ops]
+
+    def control_target(i):
+        """(control bit, target bit) of a CX / controlled 2x2, else None."""
+        o = ops[i]
+        if int(o["kind"]) == compiler.OP_CTRL1:
+            return bits_of[i][0], bits_of[i][1]
+        if int(o["kind"]) == OP_PERM and int(o["k"]) == 2:
+            perm = tuple(int(v) for v in prog.consts[int(o["aux"]): int(o["aux"]) + 4])
+            if perm == _CX_CONTROL_FIRST:
+                return bits_of[i][0], bits_of[i][1]
+            if perm == _CX_CONTROL_SECOND:
+                return bits_of[i][1], bits_of[i][0]
+        return None
+
+    ct_of = [control_target(i) for i in range(len(ops))]
 
     # next use of every logical bit at or after op index i (for the victim choice)
     INF = len(ops) + 1
@@ -68,7 +93,9 @@ def plan_epochs(prog: Program, g: int):
     for i in range(len(ops) - 1, -1, -1):
         next_use[i] = next_use[i + 1]
         for b in bits_of[i]:
-            next_use[i, b] = i
+            # a control does not have to be local (see above): only targets count as uses
+            if ct_of[i] is None or b != ct_of[i][0]:
+                next_use[i, b] = i
 
     steps: List[tuple] = []
     cur: List[tuple] = []
@@ -86,6 +113,14 @@ def plan_epochs(prog: Program, g: int):
 
     for i, o in enumerate(ops):
         lb = bits_of[i]
+        if g and ct_of[i] is not None and pos[ct_of[i][0]] >= nl and pos[ct_of[i][1]] < nl:
+            ctl, tgt = ct_of[i]
+            if (rank >> (pos[ctl] - nl)) & 1:  # control reads 1 on this rank
+                if int(o["kind"]) == OP_PERM:
+                    emit(OP_PERM, 1, -1, x_aux, [pos[tgt]])
+                else:
+                    emit(compiler.OP_MAT, 1, int(o["src"]), 0, [pos[tgt]])
+            continue
         if g and any(pos[b] >= nl for b in lb):
             if len(lb) > nl - g:
                 raise ValueError("operation too wide for the local register after an exchange")
@@ -314,7 +349,7 @@ class ShardedExecutor:
         key = ("sharded", size, id(eng))
         cached = plan.device.get(key)
         if cached is None:
-            steps, pos, consts = plan_epochs(prog, g)
+            steps, pos, consts = plan_epochs(prog, g, rank)
             compiled = []
             for st in steps:
                 if st[0] == "exchange":
