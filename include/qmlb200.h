@@ -287,11 +287,15 @@ int qmlb_coef_moments(const void* coef, int dtype, const int32_t* rows, int32_t 
 /* One-shot all-reduce (sum, float64) over peer-mapped symmetric buffers: peer_buf[r] is the
  * address, valid in this process, of rank r's buffer of qmlb_allreduce_buffer_bytes(n) bytes
  * (zero-initialised once); `in` and `out` are local, n doubles each.  One launch per rank
- * on n_peers (2..8) GPUs; every rank obtains the same bits (rank-order summation).  If a
- * peer does not arrive within ~2^28 polls the result is NaN instead of a hang. */
+ * on n_peers (2..8) GPUs; every rank obtains the same bits (rank-order summation).
+ * mode 0: synchronous - out = sum over ranks of this call's `in`.  mode 1: pipelined - out =
+ * the reduction of the PREVIOUS call (zeros for the first), so launch skew between GPUs is
+ * not serialised into every step.  mode 2: drain - contributes nothing and returns the
+ * reduction of the last call (closes a pipelined sequence).  If a peer does not arrive
+ * within ~2^28 polls the result is NaN instead of a hang. */
 size_t qmlb_allreduce_buffer_bytes(int64_t n);
 int qmlb_allreduce_peer(const void* const* peer_buf, int32_t n_peers, int32_t rank, int64_t n,
-                        const double* in, double* out, void* stream);
+                        const double* in, double* out, int32_t mode, void* stream);
 
 /* Measurement aid: sustained FMA throughput of this GPU in the given real
  * precision (TFLOP/s), used as the roofline denominator of the register-resident

@@ -108,7 +108,7 @@ def load_library(path: str = LIB_PATH) -> C.CDLL:
     lib.qmlb_allreduce_buffer_bytes.argtypes = [C.c_int64]
     lib.qmlb_allreduce_buffer_bytes.restype = C.c_size_t
     lib.qmlb_allreduce_peer.argtypes = [C.POINTER(C.c_void_p), C.c_int32, C.c_int32, C.c_int64,
-                                        C.c_void_p, C.c_void_p, C.c_void_p]
+                                        C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]
     lib.qmlb_plan_describe.argtypes = [C.POINTER(_Desc), C.c_char_p, C.c_size_t]
     lib.qmlb_zsums.argtypes = [C.c_void_p, C.c_int, C.c_int64, C.c_int32, C.c_void_p,
                                C.c_void_p, C.c_size_t, C.c_void_p]

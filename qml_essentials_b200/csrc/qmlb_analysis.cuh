@@ -109,16 +109,22 @@ __global__ void __launch_bounds__(256) k_coef_moments(const cx<T>* __restrict__ 
   if (lane == 0) out[t] = make_double2(re, im);
 }
 
-// One-shot all-reduce (sum) of n doubles over peer-mapped buffers, ONE CTA per rank.
+// One-shot all-reduce (sum) of n doubles over peer-mapped buffers, ONE CTA per rank, PUSH
+// form: remote stores are fire-and-forget, remote loads are round trips - so a rank writes
+// its contribution into EVERY peer's buffer and each rank then sums from its own memory.
 // Layout of every rank's symmetric buffer: [16 x uint64 arrival flags | 1 x uint64 epoch |
-// pad to 256 B | 2 x n doubles (payload, double-buffered by epoch parity)].  Every rank
-// copies its input into its own payload, publishes the epoch to every peer's flag slot and
-// waits until every peer has published the same epoch, then sums the payloads in rank order
-// (identical on every rank).  A rank can run at most one epoch ahead of the slowest reader,
-// which is what the two payload buffers cover.
+// pad to 256 B | 3 slots (epoch % 3) x 8 source ranks x n doubles].  A call stores its input
+// into slot[epoch % 3][rank] of every peer, fences system-wide and publishes the epoch to
+// every peer's flag.  mode 0 (synchronous): wait until every peer has published the SAME
+// epoch and sum those contributions in rank order (identical bits on every rank).  mode 1
+// (pipelined): wait for / sum the PREVIOUS epoch instead - the result of call k is the
+// reduction of call k - 1, so a rank never stalls on a peer that is less than one call
+// behind (launch skew between GPUs is not serialised into every step).  mode 2 (drain):
+// publish nothing, wait for the current epoch and sum it - closes a pipelined sequence.  A
+// writer can be at most two epochs ahead of the slowest reader: three slots.
 struct PeerReduce {
   void* buf[8];
-  int32_t n_peers, rank;
+  int32_t n_peers, rank, mode, pad;
   int64_t n;
 };
 
@@ -129,37 +135,45 @@ __global__ void __launch_bounds__(256) k_allreduce_oneshot(PeerReduce R,
   __shared__ int s_ok;
   unsigned long long* mine = static_cast<unsigned long long*>(R.buf[R.rank]);
   if (threadIdx.x == 0) {
-    s_epoch = mine[16] + 1ull;
+    s_epoch = mine[16] + (R.mode == 2 ? 0ull : 1ull);
     mine[16] = s_epoch;
     s_ok = 1;
   }
   __syncthreads();
   const unsigned long long epoch = s_epoch;
+  const unsigned long long want = R.mode == 1 ? epoch - 1ull : epoch;
   const int64_t n = R.n;
-  auto payload = [&](int r) {
-    return reinterpret_cast<double*>(static_cast<unsigned char*>(R.buf[r]) + 256) +
-           (epoch & 1ull) * n;
+  auto slot = [&](int owner, unsigned long long e, int src) {
+    return reinterpret_cast<double*>(static_cast<unsigned char*>(R.buf[owner]) + 256) +
+           ((e % 3ull) * 8 + src) * n;
   };
-  double* my = payload(R.rank);
-  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) my[i] = in[i];
-  __threadfence_system();
+  if (R.mode != 2) {
+    for (int r = 0; r < R.n_peers; ++r) {
+      double* dst = slot(r, epoch, R.rank);
+      for (int64_t i = threadIdx.x; i < n; i += blockDim.x) dst[i] = in[i];
+    }
+    __threadfence_system();
+  }
   __syncthreads();
   if (threadIdx.x < R.n_peers) {
-    unsigned long long* flag = static_cast<unsigned long long*>(R.buf[threadIdx.x]) + R.rank;
-    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(flag), "l"(epoch) : "memory");
+    if (R.mode != 2) {
+      unsigned long long* flag = static_cast<unsigned long long*>(R.buf[threadIdx.x]) + R.rank;
+      asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(flag), "l"(epoch) : "memory");
+    }
     const unsigned long long* wait = mine + threadIdx.x;
     unsigned long long seen = 0;
     long long spins = 0;
     do {
       asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(wait) : "memory");
-    } while (seen < epoch && ++spins < (1ll << 28));
-    if (seen < epoch) s_ok = 0;  // a peer never arrived: poison the result instead of hanging
+    } while (seen < want && ++spins < (1ll << 28));
+    if (seen < want) s_ok = 0;  // a peer never arrived: poison the result instead of hanging
   }
   __syncthreads();
   const bool ok = s_ok != 0;
   for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
     double s = 0.0;
-    for (int r = 0; r < R.n_peers; ++r) s += __ldcv(payload(r) + i);  // peer data: bypass L1
+    if (want > 0)
+      for (int r = 0; r < R.n_peers; ++r) s += __ldcv(slot(R.rank, want, r) + i);
     out[i] = ok ? s : __longlong_as_double(0x7ff8000000000000ll);
   }
 }

@@ -1313,14 +1313,14 @@ int qmlb_coef_moments(const void* coef, int dtype, const int32_t* rows, int32_t 
 }
 
 size_t qmlb_allreduce_buffer_bytes(int64_t n) {
-  return 256 + 2 * (size_t)std::max<int64_t>(n, 0) * sizeof(double);
+  return 256 + 3 * 8 * (size_t)std::max<int64_t>(n, 0) * sizeof(double);
 }
 
 int qmlb_allreduce_peer(const void* const* peer_buf, int32_t n_peers, int32_t rank, int64_t n,
-                        const double* in, double* out, void* stream) {
+                        const double* in, double* out, int32_t mode, void* stream) {
   if (!peer_buf || !in || !out) return fail(QMLB_ERR_INVALID, "null argument");
-  if (n_peers < 2 || n_peers > 8 || rank < 0 || rank >= n_peers || n < 1)
-    return fail(QMLB_ERR_INVALID, "peer count must be 2..8, rank inside it, n >= 1");
+  if (n_peers < 2 || n_peers > 8 || rank < 0 || rank >= n_peers || n < 1 || mode < 0 || mode > 2)
+    return fail(QMLB_ERR_INVALID, "peer count must be 2..8, rank inside it, n >= 1, mode 0..2");
   PeerReduce R{};
   for (int i = 0; i < n_peers; ++i) {
     if (!peer_buf[i]) return fail(QMLB_ERR_INVALID, "null peer pointer");
@@ -1328,6 +1328,7 @@ int qmlb_allreduce_peer(const void* const* peer_buf, int32_t n_peers, int32_t ra
   }
   R.n_peers = n_peers;
   R.rank = rank;
+  R.mode = mode;
   R.n = n;
   g_launches.fetch_add(1, std::memory_order_relaxed);
   k_allreduce_oneshot<<<1, 256, 0, static_cast<cudaStream_t>(stream)>>>(R, in, out);

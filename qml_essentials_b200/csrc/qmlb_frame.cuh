@@ -222,6 +222,32 @@ __device__ __noinline__ void frame_items_d2(cx<T>* tile, const cx<T>* mats, cons
   }
 }
 
+// The same for exactly TWO items per thread (256 threads on a 2^13-amplitude tile, up to
+// 255 registers): both items are loaded first, so the shared-memory latency of the second
+// hides under the arithmetic of the first and the stores of the first under the arithmetic
+// of the second - only half of the shared-memory time of the step stays exposed.
+template <typename T, int SA, int SB>
+__device__ __noinline__ void frame_items_d2_x2(cx<T>* tile, const cx<T>* mats,
+                                               const FrameStep& st, unsigned rank, uint32_t tlane,
+                                               uint32_t tsize) {
+  uint32_t piv[FRAME_R];
+#pragma unroll
+  for (int j = 0; j < FRAME_R; ++j) piv[j] = st.pivots[j];
+  const cx<T>* ma = mats + st.foff[0];
+  const cx<T>* mb = mats + st.foff[1];
+  const uint32_t base0 = frame_item_base(st, tlane, piv, rank);
+  const uint32_t base1 = frame_item_base(st, tlane + tsize, piv, rank);
+  RegState<T, FRAME_R> S0, S1;
+  frame_load<T>(S0, tile, base0, st);
+  frame_load<T>(S1, tile, base1, st);
+  if constexpr (SA >= 0) frame_mat2<T, 1, 0, SA>(S0, ma);
+  if constexpr (SB >= 0) frame_mat2<T, 3, 2, SB>(S0, mb);
+  frame_store<T>(S0, tile, base0, st);
+  if constexpr (SA >= 0) frame_mat2<T, 1, 0, SA>(S1, ma);
+  if constexpr (SB >= 0) frame_mat2<T, 3, 2, SB>(S1, mb);
+  frame_store<T>(S1, tile, base1, st);
+}
+
 // fast path: only 2x2 ops, at most one per register bit (MASK)
 template <typename T, int MASK, bool REAL>
 __device__ __noinline__ void frame_items_m1(cx<T>* tile, const cx<T>* mats, const FrameStep& st,
@@ -243,15 +269,20 @@ __device__ __noinline__ void frame_items_m1(cx<T>* tile, const cx<T>* mats, cons
   }
 }
 
-template <typename T, int I = 0>
+template <typename T, bool X2, int I = 0>
 __device__ __forceinline__ void frame_dispatch_d2(int code, cx<T>* tile, const cx<T>* mats,
                                                   const FrameStep& st, unsigned rank,
                                                   uint32_t tlane, uint32_t tsize, uint32_t n) {
   if constexpr (I < 16) {
     if (code == I) {
-      if constexpr (I > 0) frame_items_d2<T, (I >> 2) - 1, (I & 3) - 1>(tile, mats, st, rank, tlane, tsize, n);
+      if constexpr (I > 0) {
+        if (X2 && n == 2 * tsize)
+          frame_items_d2_x2<T, (I >> 2) - 1, (I & 3) - 1>(tile, mats, st, rank, tlane, tsize);
+        else
+          frame_items_d2<T, (I >> 2) - 1, (I & 3) - 1>(tile, mats, st, rank, tlane, tsize, n);
+      }
     } else {
-      frame_dispatch_d2<T, I + 1>(code, tile, mats, st, rank, tlane, tsize, n);
+      frame_dispatch_d2<T, X2, I + 1>(code, tile, mats, st, rank, tlane, tsize, n);
     }
   }
 }
@@ -364,14 +395,14 @@ __device__ __noinline__ void frame_items_generic(cx<T>* tile, const cx<T>* mats,
   }
 }
 
-template <typename T, bool HEAVY>
+template <typename T, bool HEAVY, bool X2 = false>
 __device__ __forceinline__ void frame_subpass(cx<T>* tile, const cx<T>* mats, const FrameStep& st,
                                               unsigned outer, uint32_t tlane, uint32_t tsize,
                                               uint32_t n_items) {
   if (!HEAVY && st.fast >= 64)
     frame_dispatch_m1<T>(st.fast - 64, tile, mats, st, outer, tlane, tsize, n_items);
   else if (!HEAVY && st.fast >= 16)
-    frame_dispatch_d2<T>(st.fast - 16, tile, mats, st, outer, tlane, tsize, n_items);
+    frame_dispatch_d2<T, X2>(st.fast - 16, tile, mats, st, outer, tlane, tsize, n_items);
   else
     frame_items_generic<T, HEAVY>(tile, mats, st, outer, tlane, tsize, n_items);
 }
@@ -519,7 +550,7 @@ __global__ void __launch_bounds__(THREADS, (THREADS == 512 || WIDE) ? 1 : 2)
         __syncthreads();
       }
 
-      if (valid) frame_subpass<T, HEAVY>(tile, mats, st, rank, tlane, tsize, n_items);
+      if (valid) frame_subpass<T, HEAVY, WIDE>(tile, mats, st, rank, tlane, tsize, n_items);
       __syncthreads();
     }
 

@@ -74,8 +74,8 @@ __device__ __forceinline__ void fence_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
 
-template <typename T>
-__global__ void __launch_bounds__(256, sizeof(T) == 4 ? 3 : 2)
+template <typename T, int THREADS>
+__global__ void __launch_bounds__(THREADS, THREADS == 512 ? 2 : (sizeof(T) == 4 ? 3 : 2))
     k_fstream(RunArgs A, const FStreamPass P, cx<T>* __restrict__ gstate,
               const cx<T>* __restrict__ premats) {
   extern __shared__ __align__(128) unsigned char fsm[];
@@ -158,18 +158,22 @@ __global__ void __launch_bounds__(256, sizeof(T) == 4 ? 3 : 2)
         cmine &= tile_n - 1u;
         __syncthreads();
         cg::cluster_group cluster = cg::this_cluster();
-        const int per = (int)(tile_n >> 8);
+        constexpr int TB = THREADS == 512 ? 9 : 8;
+        const int per = (int)(tile_n >> TB);
         if (per == 16)
-          frame_relayout<T, 16>(tile, cluster, false, 0u, Tb, 8, (int)threadIdx.x, cmine, tab_lo,
+          frame_relayout<T, 16>(tile, cluster, false, 0u, Tb, TB, (int)threadIdx.x, cmine, tab_lo,
                                 tab_hi);
-        else if (per == 32)
-          frame_relayout<T, 32>(tile, cluster, false, 0u, Tb, 8, (int)threadIdx.x, cmine, tab_lo,
+        else if (per == 32 && THREADS == 256)
+          frame_relayout<T, 32>(tile, cluster, false, 0u, Tb, TB, (int)threadIdx.x, cmine, tab_lo,
                                 tab_hi);
         else if (per == 8)
-          frame_relayout<T, 8>(tile, cluster, false, 0u, Tb, 8, (int)threadIdx.x, cmine, tab_lo,
+          frame_relayout<T, 8>(tile, cluster, false, 0u, Tb, TB, (int)threadIdx.x, cmine, tab_lo,
                                tab_hi);
         else if (per == 4)
-          frame_relayout<T, 4>(tile, cluster, false, 0u, Tb, 8, (int)threadIdx.x, cmine, tab_lo,
+          frame_relayout<T, 4>(tile, cluster, false, 0u, Tb, TB, (int)threadIdx.x, cmine, tab_lo,
+                               tab_hi);
+        else if (per == 2)
+          frame_relayout<T, 2>(tile, cluster, false, 0u, Tb, TB, (int)threadIdx.x, cmine, tab_lo,
                                tab_hi);
         __syncthreads();
         continue;

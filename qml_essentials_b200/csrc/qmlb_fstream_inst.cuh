@@ -1,12 +1,15 @@
 // Instantiates the streaming frame engine for one precision.
+#include <cstdlib>
+
 #include "qmlb_internal.h"
 #include "qmlb_fstream.cuh"
 
 namespace qmlb {
 
-cudaError_t QMLB_LAUNCH_FSTREAM(const qmlb_program* p, const RunArgs& R, void* state,
-                                const void* premats, int init_mode, cudaStream_t st) {
-  auto kern = k_fstream<QMLB_T>;
+template <int THREADS>
+static cudaError_t launch_fstream_t(const qmlb_program* p, const RunArgs& R, void* state,
+                                    const void* premats, int init_mode, cudaStream_t st) {
+  auto kern = k_fstream<QMLB_T, THREADS>;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -15,7 +18,7 @@ cudaError_t QMLB_LAUNCH_FSTREAM(const qmlb_program* p, const RunArgs& R, void* s
     attr_set = true;
   }
   int per_sm = 0;
-  cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, p->frame_smem);
+  cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, THREADS, p->frame_smem);
   if (e != cudaSuccess) return e;
   if (per_sm < 1) return cudaErrorLaunchOutOfResources;
   const FrameProg& F = p->frame;
@@ -36,13 +39,26 @@ cudaError_t QMLB_LAUNCH_FSTREAM(const qmlb_program* p, const RunArgs& R, void* s
     for (int i = 0; i < F.tile_bits; ++i) P.tp[i] = (uint8_t)ps.tp[i];
     for (int g = 0; g < F.outer_bits; ++g) P.opos[g] = (uint8_t)ps.opos[g];
     g_launches.fetch_add(1, std::memory_order_relaxed);
-    kern<<<grid, 256, p->frame_smem, st>>>(R, P, static_cast<cx<QMLB_T>*>(state),
+    kern<<<grid, THREADS, p->frame_smem, st>>>(R, P, static_cast<cx<QMLB_T>*>(state),
                                           static_cast<const cx<QMLB_T>*>(premats));
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     first = false;
   }
   return cudaSuccess;
+}
+
+cudaError_t QMLB_LAUNCH_FSTREAM(const qmlb_program* p, const RunArgs& R, void* state,
+                                const void* premats, int init_mode, cudaStream_t st) {
+  // one item per thread (512 threads, 64 registers, twice the resident warps) measured
+  // against two items per thread (256 threads): see DESIGN.md 4.1
+  static const int threads = [] {
+    const char* v = std::getenv("QMLB_FSTREAM_THREADS");
+    return v ? std::atoi(v) : 256;
+  }();
+  if (threads == 512 && p->frame.tile_bits >= 13)
+    return launch_fstream_t<512>(p, R, state, premats, init_mode, st);
+  return launch_fstream_t<256>(p, R, state, premats, init_mode, st);
 }
 
 }  // namespace qmlb

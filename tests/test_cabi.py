@@ -154,13 +154,18 @@ def test_stream_scheduler_invariants(lib, n, L, ct, precision, noise):
 
 def test_plan_strategies_by_size(lib):
     """n <= 5 -> registers, up to 2^16 (c128) / 2^17 (c64) amplitudes -> on-chip frame
-    engine (one CTA or a cluster), beyond -> streamed passes; the force flag used by the
-    qubit-sharded path always streams."""
-    for n, want in ((4, 0), (9, 3), (16, 3), (18, 2)):
+    engine (one CTA or a cluster), beyond -> tile passes over HBM (<Z_q> output) or the
+    register-group stream (other outputs); the force flag used by the qubit-sharded path
+    always takes the register-group stream."""
+    for n, want in ((4, 0), (9, 3), (16, 3), (18, 4)):
         plan = _plan_of(n, 1, "Hardware_Efficient", "complex128")
         text = backend.plan_describe(lib, plan.program, plan.out_type, plan.obs_recs,
                                      plan.obs_pool, "complex128")
         assert text.startswith(f"strategy {want}")
+    plan = _plan_of(18, 1, "Hardware_Efficient", "complex128", "probs")
+    text = backend.plan_describe(lib, plan.program, plan.out_type, plan.obs_recs, plan.obs_pool,
+                                 "complex128")
+    assert text.startswith("strategy 2")
     plan = _plan_of(9, 1, "Hardware_Efficient", "complex128")
     text = backend.plan_describe(lib, plan.program, plan.out_type, plan.obs_recs, plan.obs_pool,
                                  "complex128", flags=backend.QMLB_DESC_FORCE_STREAM)
