@@ -335,22 +335,43 @@ class CudaExecutor:
                 return np.concatenate(parts, axis=0)
             return self.torch.cat(parts, dim=0)
 
+    SHOT_MAX_QUBITS = 14  # qmlb_sample keeps one probability vector in shared memory
+
     def execute_shots(self, plan, host_args, batch: int, uniforms: np.ndarray,
                       chunk: Optional[int] = None) -> np.ndarray:
-        """Exact probabilities on the device, then the shot bookkeeping kernel."""
+        """Exact probabilities on the device, then the shot bookkeeping kernel - chunk by
+        chunk: probabilities, the (chunk, shots) uniforms and the int32 counts of one chunk
+        are resident at a time (memory-aware like ``execute``)."""
+        if plan.n_qubits > self.SHOT_MAX_QUBITS:
+            raise BackendError(
+                f"shot sampling is limited to {self.SHOT_MAX_QUBITS} qubits (qmlb_sample holds "
+                f"the cumulative probabilities of one element in shared memory); got "
+                f"{plan.n_qubits}")
         torch = self.torch
+        shots = uniforms.shape[1]
+        # the uniforms and counts of a chunk take part in the device budget
+        per_elem = shots * 8 + (2 ** plan.n_qubits) * 12
+        free = int(torch.cuda.mem_get_info(self.device)[0] * 0.5)
+        chunk = batch if not chunk else min(chunk, batch)
+        chunk = int(max(1, min(chunk, free // max(per_elem, 1))))
         with torch.cuda.device(self.device):
-            call = self.stage(plan, host_args, batch)
-            probs = call.launch()
-            shots = uniforms.shape[1]
-            u = torch.from_numpy(np.ascontiguousarray(uniforms, dtype=np.float64)).to(self.device)
-            counts = torch.empty((batch, probs.shape[1]), dtype=torch.int32, device=self.device)
-            rc = self.lib.qmlb_sample(
-                probs.data_ptr(), call.h.dtype, u.data_ptr(), batch, plan.n_qubits, shots,
-                counts.data_ptr(), torch.cuda.current_stream(self.device).cuda_stream)
-            if rc != 0:
-                raise BackendError(f"qmlb_sample: {self.lib.qmlb_last_error().decode()}")
-            return counts.cpu().numpy()
+            dev_args = self.to_device(host_args)
+            handle = self.handle_for(plan)
+            parts = []
+            for lo in range(0, batch, chunk):
+                n = min(chunk, batch - lo)
+                call = DeviceCall(self, handle, dev_args, n, lo)
+                probs = call.launch()
+                u = torch.from_numpy(np.ascontiguousarray(uniforms[lo:lo + n],
+                                                          dtype=np.float64)).to(self.device)
+                counts = torch.empty((n, probs.shape[1]), dtype=torch.int32, device=self.device)
+                rc = self.lib.qmlb_sample(
+                    probs.data_ptr(), handle.dtype, u.data_ptr(), n, plan.n_qubits, shots,
+                    counts.data_ptr(), torch.cuda.current_stream(self.device).cuda_stream)
+                if rc != 0:
+                    raise BackendError(f"qmlb_sample: {self.lib.qmlb_last_error().decode()}")
+                parts.append(counts.cpu().numpy())
+            return parts[0] if len(parts) == 1 else np.concatenate(parts, axis=0)
 
     # -- fused reductions for the analysis callers -----------------------------------
     def purities(self, states, n_qubits: int, is_density: bool):

@@ -80,7 +80,7 @@ class Coefficients:
 
     @classmethod
     def _device_spectrum(cls, model: Model, mfs: int, mts: int, shift: bool, trim: bool,
-                         **kwargs: Any):
+                         _keep_on_device: bool = False, **kwargs: Any):
         """One input feature, expectation values averaged over the observables: the mean
         over qubits, the DFT along the grid axis AND get_spectrum's trim / shift run on the
         GPU right behind the circuit kernel (``qmlb_grid_dft`` writes coefficient k to the
@@ -111,6 +111,8 @@ class Coefficients:
         kw = {k: v for k, v in kwargs.items() if k != "force_mean"}
         ev = model.device_result(inputs=grid, **kw)
         coef = ex.grid_dft(ev.reshape(n_x, -1, ev.shape[-1]), order)
+        if _keep_on_device:
+            return coef, [freqs]
         coeffs = np.asarray(ex.to_host(coef)).squeeze()
         # the kernel writes coefficient n - k as the conjugate of coefficient k, so the
         # imaginary parts cancel pairwise; only the self-conjugate rows (k = 0, n / 2) can
@@ -269,11 +271,13 @@ class FCC:
         """Fourier coefficient correlation: mean |correlation| over the strict lower
         triangle of the non-negative-frequency block (coefficients.py:968-1037)."""
         if trim_redundant and not weight:
-            _, coeffs, freqs = cls._calculate_coefficients(model, n_samples, random_key, scale,
-                                                           **kwargs)
-            pos = cls._calculate_mask(freqs)
-            sub = coeffs.reshape(-1, coeffs.shape[-1])[pos]
-            fp = cls._correlate(sub.transpose(), method=method)
+            fp = cls._device_fingerprint(model, n_samples, random_key, method, scale, **kwargs)
+            if fp is None:
+                _, coeffs, freqs = cls._calculate_coefficients(model, n_samples, random_key,
+                                                               scale, **kwargs)
+                pos = cls._calculate_mask(freqs)
+                sub = coeffs.reshape(-1, coeffs.shape[-1])[pos]
+                fp = cls._correlate(sub.transpose(), method=method)
             afp = np.abs(fp)
             diag = np.abs(np.diagonal(fp))
             lower_sum = (np.nansum(afp) - np.nansum(diag)) / 2.0
@@ -320,6 +324,49 @@ class FCC:
             pos_freqs = cls._flat_frequencies(freqs)[pos]
             return lower_block(fp[pos][:, pos], pos_freqs)
         return fp, freqs
+
+    @classmethod
+    def _device_fingerprint(cls, model: Model, n_samples: int, random_key, method: str,
+                            scale: bool, **kwargs: Any):
+        """Correlation matrix of the non-negative-frequency coefficients without the
+        coefficients ever leaving the GPU: circuit kernel -> grid DFT -> additive moments
+        over the samples (``qmlb_coef_moments``), K + K + K^2 numbers to the host (and across
+        ranks).  Pearson / complex Pearson / covariance are functions of those moments
+        (coefficients.py:1346-1498); Spearman needs ranks and takes the host route.
+        ``None`` when the device route does not apply."""
+        if method not in ("pearson", "complex_pearson", "covariance"):
+            return None
+        kw = dict(kwargs)
+        kw.setdefault("force_mean", True)
+        kw.setdefault("execution_type", "expval")
+        if n_samples > 0:
+            total = int(2 ** model.n_qubits * n_samples * model.n_input_feat) if scale \
+                else n_samples
+            model.initialize_params(random_key, repeat=total)
+        rank, size = parallel.world()
+        if size > 1 and model.params.shape[0] > 1:
+            lo, hi = parallel.shard_bounds(model.params.shape[0], rank, size)
+            kw["params"] = model.params[lo:hi]
+        dev = Coefficients._device_spectrum(model, 1, 1, True, True, _keep_on_device=True, **kw)
+        if dev is None:
+            return None
+        coef, freqs = dev
+        from .script import get_executor
+
+        ex = model.script.executor or get_executor()
+        pos = cls._calculate_mask(freqs[0])
+        s1, s2, cc = (np.asarray(t.cpu().numpy()) for t in ex.coef_moments(coef, pos))
+        n = int(coef.shape[1])
+        if method == "pearson":  # real and imaginary parts as separate observations
+            st = _Stats.from_moments(2 * n, s1.real + s1.imag, s2, cc.real).allreduce()
+            cov = st.covariance(1)
+            with np.errstate(invalid="ignore", divide="ignore"):
+                std = np.sqrt(np.diagonal(cov))
+                den = std[:, None] * std[None, :]
+                res = np.where(den > 0, cov / den, np.nan)
+            return np.clip(np.real(res), -1.0, 1.0)
+        st = _Stats.from_moments(n, s1, s2, cc).allreduce()
+        return st.covariance(1) if method == "covariance" else st.complex_pearson(1)
 
     @classmethod
     def calculate_fcc(cls, fourier_fingerprint: np.ndarray) -> float:

@@ -320,3 +320,23 @@ def test_two_feature_spectrum_reconstructs_model_output():
     assert np.allclose(got, want, atol=1e-10)
     fcc = FCC.get_fcc(model=m, n_samples=12)
     assert 0 <= fcc <= 1
+
+
+def test_stats_from_device_moments_reproduce_every_estimator():
+    """The K + K + K^2 moments the GPU reduces (qmlb_coef_moments) carry everything the
+    Pearson / complex-Pearson / covariance estimators of coefficients.py:1346-1498 need."""
+    from qml_essentials_b200.coefficients import FCC, _Stats
+
+    g = np.random.default_rng(5)
+    c = g.normal(size=(200, 9)) + 1j * g.normal(size=(200, 9))  # (samples, coefficients)
+    c[:, 3] = 0.5 * c[:, 1] + 0.1 * c[:, 3]
+    s1, s2, cc = c.sum(axis=0), (np.abs(c) ** 2).sum(axis=0), c.conj().T @ c
+    st = _Stats.from_moments(200, s1, s2, cc)
+    assert np.allclose(st.covariance(1), FCC._covariance(c), atol=1e-12)
+    assert np.allclose(st.complex_pearson(1), FCC._complex_pearson(c), atol=1e-12)
+    # Pearson: real and imaginary parts are separate observations (2N of them)
+    sp = _Stats.from_moments(400, s1.real + s1.imag, s2, cc.real)
+    cov = sp.covariance(1)
+    std = np.sqrt(np.diagonal(cov))
+    assert np.allclose(np.clip(np.real(cov / (std[:, None] * std[None, :])), -1, 1),
+                       FCC._pearson(c), atol=1e-12)

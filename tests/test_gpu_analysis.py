@@ -66,3 +66,20 @@ def test_get_spectrum_device_path_equals_host_path(monkeypatch):
         monkeypatch.delenv("QMLB_HOST_FFT")
         assert np.array_equal(np.asarray(dev_f), np.asarray(host_f))
         assert dev_c.shape == host_c.shape and np.abs(dev_c - host_c).max() < 1e-12
+
+
+@pytest.mark.parametrize("method", ["pearson", "complex_pearson", "covariance"])
+def test_fcc_device_moments_equal_host_route(monkeypatch, method):
+    """FCC through circuit kernel -> grid DFT -> moments on the GPU (only K + K + K^2 numbers
+    leave the device) against the reference's host route over the full coefficient array."""
+    from qml_essentials_b200 import rng
+    from qml_essentials_b200.coefficients import FCC
+    from qml_essentials_b200.model import Model
+
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        m = Model(3, 2, "Circuit_19")
+        a = FCC.get_fcc(m, n_samples=300, random_key=rng.key(3), method=method)
+        monkeypatch.setenv("QMLB_HOST_FFT", "1")
+        b = FCC.get_fcc(m, n_samples=300, random_key=rng.key(3), method=method)
+    assert np.isfinite(a) and abs(a - b) < 1e-9

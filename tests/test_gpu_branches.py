@@ -206,3 +206,32 @@ def test_memory_model_bounds_the_library_workspace(typ):
         ws = ex.lib.qmlb_workspace_bytes(h.ptr, args, 4, batch)
         est = memory.estimate_peak_bytes(n, batch, typ, False, n_obs=n, n_ops=plan.n_ops)
         assert est >= ws, (n, typ, est, ws)
+
+
+def test_shots_run_chunked_and_reject_large_registers(monkeypatch):
+    """execute_shots follows the memory-aware chunking (identical counts with
+    and without chunks, same uniform stream) and refuses n > 14 with a clear error instead
+    of QMLB_ERR_UNSUPPORTED from the kernel."""
+    from qml_essentials_b200 import backend, memory, rng as qrng
+
+    def circ(t):
+        op.RX(t, wires=0)
+        op.CX(wires=[0, 1])
+        op.RY(0.3 * t, wires=2)
+
+    th = np.linspace(0.1, 3.0, 23)
+    full = Script(circ, 3).execute("probs", args=(th,), in_axes=(0,), shots=500,
+                                   key=qrng.key(11))
+    monkeypatch.setattr(memory, "available_memory_bytes", lambda: 3_000)
+    s2 = Script(circ, 3)
+    part = s2.execute("probs", args=(th,), in_axes=(0,), shots=500, key=qrng.key(11))
+    assert np.array_equal(full, part)
+    chunks = [v for k, v in s2._jit_cache.items() if k[0] == "_mem"]
+    assert chunks and chunks[0] < 23
+
+    def wide():
+        for q in range(15):
+            op.H(wires=q)
+
+    with pytest.raises(backend.BackendError, match="limited to 14 qubits"):
+        Script(wide, 15).execute("probs", shots=10, key=qrng.key(1))
