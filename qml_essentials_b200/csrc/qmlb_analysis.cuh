@@ -9,15 +9,17 @@
 
 namespace qmlb {
 
-constexpr int DFT_PCOLS = 8;  // parameter samples per CTA
+constexpr int DFT_PCOLS = 4;  // parameter samples per CTA
 
 // out[row_of[k]][p] = (1 / n_x) * sum_x s[x][p] * exp(-2 pi i k x / n_x),
 // s[x][p] = mean over the n_obs observables of ev[x][p][:]   (ev: (n_x, n_p, n_obs) real)
 // One CTA = DFT_PCOLS samples x all frequencies; the signal tile and the twiddle table sit
-// in shared memory (double precision throughout), x is summed in index order.  The signal
-// is real, so only k <= n_x / 2 is summed and coefficient n_x - k is written as the
-// conjugate.  row_of (optional) places frequency k on an output row of the caller's choice
-// (-1 = not wanted): get_spectrum's shift / trim cost nothing.
+// in shared memory (double precision throughout).  The signal is real: only k <= n_x / 2
+// is summed (coefficient n_x - k is written as the conjugate), and grid points x and
+// n_x - x are folded first (E = s[x] + s[n-x] meets the cosine, O = s[x] - s[n-x] the sine),
+// which halves the inner loop; x is summed in index order.  row_of (optional) places
+// frequency k on an output row of the caller's choice (-1 = not wanted): get_spectrum's
+// shift / trim cost nothing.
 template <typename T>
 __global__ void __launch_bounds__(256) k_grid_dft(const T* __restrict__ ev, int n_x, int64_t n_p,
                                                   int n_obs, const int32_t* __restrict__ row_of,
@@ -42,18 +44,26 @@ __global__ void __launch_bounds__(256) k_grid_dft(const T* __restrict__ ev, int 
     tw[j] = make_double2(c, s);
   }
   __syncthreads();
+  const int half = (n_x - 1) / 2;  // pairs (x, n_x - x), x = 1 .. half
+  for (int i = threadIdx.x; i < half * DFT_PCOLS; i += blockDim.x) {
+    const int x = 1 + i / DFT_PCOLS, c = i % DFT_PCOLS;
+    const double a = sig[x * DFT_PCOLS + c], b = sig[(n_x - x) * DFT_PCOLS + c];
+    sig[x * DFT_PCOLS + c] = a + b;
+    sig[(n_x - x) * DFT_PCOLS + c] = a - b;
+  }
+  __syncthreads();
   const int c = threadIdx.x % DFT_PCOLS;
   const double inv = 1.0 / (double)n_x;
   for (int k = threadIdx.x / DFT_PCOLS; k <= n_x / 2; k += blockDim.x / DFT_PCOLS) {
-    double re = 0.0, im = 0.0;
+    double re = sig[c], im = 0.0;
+    if ((n_x & 1) == 0) re += (k & 1) ? -sig[(n_x / 2) * DFT_PCOLS + c] : sig[(n_x / 2) * DFT_PCOLS + c];
     int idx = 0;  // (k * x) mod n_x
-    for (int x = 0; x < n_x; ++x) {
-      const double v = sig[x * DFT_PCOLS + c];
-      const double2 w = tw[idx];
-      re = fma(v, w.x, re);
-      im = fma(v, w.y, im);
+    for (int x = 1; x <= half; ++x) {
       idx += k;
       if (idx >= n_x) idx -= n_x;
+      const double2 w = tw[idx];
+      re = fma(sig[x * DFT_PCOLS + c], w.x, re);
+      im = fma(sig[(n_x - x) * DFT_PCOLS + c], w.y, im);
     }
     if (p0 + c < n_p) {
       const int r0 = row_of ? row_of[k] : k;

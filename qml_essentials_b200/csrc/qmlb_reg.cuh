@@ -246,9 +246,12 @@ constexpr int reg_min_ctas() {
   return (2 * (1 << N) * (int)sizeof(T) / 4 <= 64) ? (sizeof(T) == 8 ? 2 : QMLB_REG_MIN_CTAS) : 1;
 }
 
-template <typename T, int N>
-__global__ void __launch_bounds__(128, reg_min_ctas<T, N>()) k_reg(DevProg P, RunArgs R, int mode, int n_args,
-                                             void* __restrict__ out) {
+// MINB: resident CTAs per SM the variant is compiled for (0 = reg_min_ctas default).  The
+// complex128 n = 4 kernel exists at 2 (210 registers, no spills) and 3 (168 registers, 124
+// bytes of spills, 12 instead of 8 warps per SM).
+template <typename T, int N, int MINB = 0>
+__global__ void __launch_bounds__(128, MINB ? MINB : reg_min_ctas<T, N>())
+    k_reg(DevProg P, RunArgs R, int mode, int n_args, void* __restrict__ out) {
   constexpr int D = 1 << N;
   // op stream -> shared memory (all threads take part before anyone leaves)
   extern __shared__ __align__(16) unsigned char reg_smem[];

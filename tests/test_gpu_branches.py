@@ -222,7 +222,7 @@ def test_shots_run_chunked_and_reject_large_registers(monkeypatch):
     th = np.linspace(0.1, 3.0, 23)
     full = Script(circ, 3).execute("probs", args=(th,), in_axes=(0,), shots=500,
                                    key=qrng.key(11))
-    monkeypatch.setattr(memory, "available_memory_bytes", lambda: 3_000)
+    monkeypatch.setattr(memory, "available_memory_bytes", lambda: 1_000)
     s2 = Script(circ, 3)
     part = s2.execute("probs", args=(th,), in_axes=(0,), shots=500, key=qrng.key(11))
     assert np.array_equal(full, part)
