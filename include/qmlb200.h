@@ -297,6 +297,16 @@ size_t qmlb_allreduce_buffer_bytes(int64_t n);
 int qmlb_allreduce_peer(const void* const* peer_buf, int32_t n_peers, int32_t rank, int64_t n,
                         const double* in, double* out, int32_t mode, void* stream);
 
+/* Sub-register outputs (jaqsi.py:79-146, applied by Model._forward, model.py:1711-1724):
+ * qmlb_partial_trace keeps the qubits `keep[0..k)` (wire numbers, ascending) of `batch`
+ * density matrices (batch, 2^n, 2^n) -> (batch, 2^k, 2^k); qmlb_marginal_probs the same for
+ * probability vectors (batch, 2^n) -> (batch, 2^k).  Output index bits follow the ascending
+ * wire order, wire keep[0] most significant, like the reference.  n <= 16. */
+int qmlb_partial_trace(const void* rho, int dtype, int64_t batch, int32_t n_qubits,
+                       const int32_t* keep, int32_t k, void* out, void* stream);
+int qmlb_marginal_probs(const void* probs, int dtype, int64_t batch, int32_t n_qubits,
+                        const int32_t* keep, int32_t k, void* out, void* stream);
+
 /* Measurement aid: sustained FMA throughput of this GPU in the given real
  * precision (TFLOP/s), used as the roofline denominator of the register-resident
  * regime.  Blocks until done. */

@@ -33,7 +33,7 @@ EXPORTED_SYMBOLS = (
     "qmlb_sample", "qmlb_purity", "qmlb_overlap_fidelity", "qmlb_fma_peak",
     "qmlb_evolve", "qmlb_zsums", "qmlb_zsums_workspace_bytes", "qmlb_plan_describe",
     "qmlb_evolve_peer", "qmlb_grid_dft", "qmlb_coef_moments", "qmlb_allreduce_buffer_bytes",
-    "qmlb_allreduce_peer",
+    "qmlb_allreduce_peer", "qmlb_partial_trace", "qmlb_marginal_probs",
 )
 QMLB_DESC_FORCE_STREAM = 1
 
@@ -109,6 +109,10 @@ def load_library(path: str = LIB_PATH) -> C.CDLL:
     lib.qmlb_allreduce_buffer_bytes.restype = C.c_size_t
     lib.qmlb_allreduce_peer.argtypes = [C.POINTER(C.c_void_p), C.c_int32, C.c_int32, C.c_int64,
                                         C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]
+    lib.qmlb_partial_trace.argtypes = [C.c_void_p, C.c_int, C.c_int64, C.c_int32, C.c_void_p,
+                                       C.c_int32, C.c_void_p, C.c_void_p]
+    lib.qmlb_marginal_probs.argtypes = [C.c_void_p, C.c_int, C.c_int64, C.c_int32, C.c_void_p,
+                                        C.c_int32, C.c_void_p, C.c_void_p]
     lib.qmlb_plan_describe.argtypes = [C.POINTER(_Desc), C.c_char_p, C.c_size_t]
     lib.qmlb_zsums.argtypes = [C.c_void_p, C.c_int, C.c_int64, C.c_int32, C.c_void_p,
                                C.c_void_p, C.c_size_t, C.c_void_p]
@@ -428,6 +432,35 @@ class CudaExecutor:
                                     torch.cuda.current_stream(ev.device).cuda_stream)
         if rc != 0:
             raise BackendError(f"qmlb_grid_dft: {self.lib.qmlb_last_error().decode()}")
+        return out
+
+    def partial_trace(self, rho, n_qubits: int, keep):
+        """(B, 2^n, 2^n) device density matrices -> (B, 2^k, 2^k) over the wires ``keep``."""
+        torch = self.torch
+        keep = sorted(int(q) for q in keep)
+        k, B = len(keep), rho.shape[0]
+        dt = QMLB_C128 if rho.dtype == torch.complex128 else QMLB_C64
+        out = torch.empty((B, 2**k, 2**k), dtype=rho.dtype, device=rho.device)
+        arr = (C.c_int32 * k)(*keep)
+        rc = self.lib.qmlb_partial_trace(rho.data_ptr(), dt, B, n_qubits, arr, k, out.data_ptr(),
+                                         torch.cuda.current_stream(rho.device).cuda_stream)
+        if rc != 0:
+            raise BackendError(f"qmlb_partial_trace: {self.lib.qmlb_last_error().decode()}")
+        return out
+
+    def marginal_probs(self, probs, n_qubits: int, keep):
+        """(B, 2^n) device probabilities -> (B, 2^k) marginal over the wires ``keep``."""
+        torch = self.torch
+        keep = sorted(int(q) for q in keep)
+        k, B = len(keep), probs.shape[0]
+        dt = QMLB_C128 if probs.dtype == torch.float64 else QMLB_C64
+        out = torch.empty((B, 2**k), dtype=probs.dtype, device=probs.device)
+        arr = (C.c_int32 * k)(*keep)
+        rc = self.lib.qmlb_marginal_probs(probs.data_ptr(), dt, B, n_qubits, arr, k,
+                                          out.data_ptr(),
+                                          torch.cuda.current_stream(probs.device).cuda_stream)
+        if rc != 0:
+            raise BackendError(f"qmlb_marginal_probs: {self.lib.qmlb_last_error().decode()}")
         return out
 
     def to_host(self, t) -> np.ndarray:

@@ -119,6 +119,58 @@ __global__ void __launch_bounds__(256) k_coef_moments(const cx<T>* __restrict__ 
   if (lane == 0) out[t] = make_double2(re, im);
 }
 
+// Sub-register outputs (jaqsi.py:79-146): partial trace of density matrices and marginal
+// probabilities, reduced on the device so that only the 2^k x 2^k / 2^k result leaves it.
+// keep[j]: bit position (in the n-bit basis index) of output bit j, MSB first; gone[t]: the
+// traced positions.  One thread per output entry, traced configurations in index order.
+struct BitSel {
+  int8_t keep[16], gone[16];
+  int32_t k, g;
+};
+
+__device__ __forceinline__ uint32_t bits_deposit(uint32_t v, const int8_t* pos, int count,
+                                                 bool msb_first) {
+  uint32_t o = 0;
+  for (int j = 0; j < count; ++j)
+    o |= ((v >> (msb_first ? count - 1 - j : j)) & 1u) << pos[j];
+  return o;
+}
+
+template <typename T>
+__global__ void k_partial_trace(const cx<T>* __restrict__ rho, int64_t batch, int n,
+                                const BitSel sel, cx<T>* __restrict__ out) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t per = (int64_t)1 << (2 * sel.k);
+  if (t >= batch * per) return;
+  const int64_t b = t / per;
+  const uint32_t io = (uint32_t)((t % per) >> sel.k), jo = (uint32_t)((t % per) & ((1u << sel.k) - 1u));
+  const uint32_t ik = bits_deposit(io, sel.keep, sel.k, true);
+  const uint32_t jk = bits_deposit(jo, sel.keep, sel.k, true);
+  const cx<T>* r = rho + ((size_t)b << (2 * n));
+  T re = (T)0, im = (T)0;
+  for (uint32_t c = 0; c < (1u << sel.g); ++c) {
+    const uint32_t tr = bits_deposit(c, sel.gone, sel.g, false);
+    const cx<T> v = r[((size_t)(ik | tr) << n) | (jk | tr)];
+    re += v.x;
+    im += v.y;
+  }
+  out[t] = mk<T>(re, im);
+}
+
+template <typename T>
+__global__ void k_marginal_probs(const T* __restrict__ probs, int64_t batch, int n,
+                                 const BitSel sel, T* __restrict__ out) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t per = (int64_t)1 << sel.k;
+  if (t >= batch * per) return;
+  const int64_t b = t / per;
+  const uint32_t vk = bits_deposit((uint32_t)(t % per), sel.keep, sel.k, true);
+  const T* p = probs + ((size_t)b << n);
+  T acc = (T)0;
+  for (uint32_t c = 0; c < (1u << sel.g); ++c) acc += p[vk | bits_deposit(c, sel.gone, sel.g, false)];
+  out[t] = acc;
+}
+
 // One-shot all-reduce (sum) of n doubles over peer-mapped buffers, ONE CTA per rank, PUSH
 // form: remote stores are fire-and-forget, remote loads are round trips - so a rank writes
 // its contribution into EVERY peer's buffer and each rank then sums from its own memory.

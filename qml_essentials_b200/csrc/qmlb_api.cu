@@ -1312,6 +1312,64 @@ int qmlb_coef_moments(const void* coef, int dtype, const int32_t* rows, int32_t 
   return QMLB_OK;
 }
 
+static int make_bitsel(int32_t n, const int32_t* keep, int32_t k, BitSel* sel) {
+  if (!keep || n < 1 || n > 16 || k < 1 || k > n) return fail(QMLB_ERR_INVALID, "bad qubit subset");
+  std::memset(sel, 0, sizeof(*sel));
+  uint32_t seen = 0;
+  for (int j = 0; j < k; ++j) {
+    if (keep[j] < 0 || keep[j] >= n || (seen >> keep[j] & 1u) || (j && keep[j] <= keep[j - 1]))
+      return fail(QMLB_ERR_INVALID, "kept wires must be distinct, ascending and inside the register");
+    seen |= 1u << keep[j];
+    sel->keep[j] = (int8_t)(n - 1 - keep[j]);  // wire q is bit n-1-q
+  }
+  int g = 0;
+  for (int q = n - 1; q >= 0; --q)
+    if (!(seen >> q & 1u)) sel->gone[g++] = (int8_t)(n - 1 - q);
+  sel->k = k;
+  sel->g = g;
+  return QMLB_OK;
+}
+
+int qmlb_partial_trace(const void* rho, int dtype, int64_t batch, int32_t n, const int32_t* keep,
+                       int32_t k, void* out, void* stream) {
+  if (!rho || !out) return fail(QMLB_ERR_INVALID, "null argument");
+  BitSel sel;
+  int rc = make_bitsel(n, keep, k, &sel);
+  if (rc != QMLB_OK) return rc;
+  if (batch <= 0) return QMLB_OK;
+  const int64_t total = batch << (2 * k);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  if (dtype == QMLB_C128)
+    k_partial_trace<double><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
+        static_cast<const cx<double>*>(rho), batch, n, sel, static_cast<cx<double>*>(out));
+  else
+    k_partial_trace<float><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
+        static_cast<const cx<float>*>(rho), batch, n, sel, static_cast<cx<float>*>(out));
+  CUDA_TRY(cudaGetLastError());
+  return QMLB_OK;
+}
+
+int qmlb_marginal_probs(const void* probs, int dtype, int64_t batch, int32_t n,
+                        const int32_t* keep, int32_t k, void* out, void* stream) {
+  if (!probs || !out) return fail(QMLB_ERR_INVALID, "null argument");
+  BitSel sel;
+  int rc = make_bitsel(n, keep, k, &sel);
+  if (rc != QMLB_OK) return rc;
+  if (batch <= 0) return QMLB_OK;
+  const int64_t total = batch << k;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  if (dtype == QMLB_C128)
+    k_marginal_probs<double><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
+        static_cast<const double*>(probs), batch, n, sel, static_cast<double*>(out));
+  else
+    k_marginal_probs<float><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
+        static_cast<const float*>(probs), batch, n, sel, static_cast<float*>(out));
+  CUDA_TRY(cudaGetLastError());
+  return QMLB_OK;
+}
+
 size_t qmlb_allreduce_buffer_bytes(int64_t n) {
   return 256 + 3 * 8 * (size_t)std::max<int64_t>(n, 0) * sizeof(double);
 }

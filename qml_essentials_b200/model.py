@@ -712,6 +712,21 @@ class Model:
         if self.shots is not None:
             sub_key, shot_key = safe_random_split(sub_key)
 
+        # sub-register density / probability outputs: trace / marginalise on the GPU so that
+        # only the reduced result is copied back (jaqsi.py:79-146 on the device)
+        reduce_dev = None
+        if (not _device and not self.all_qubit_measurement and self.shots is None
+                and self.execution_type in ("density", "probs")):
+            from .script import get_executor
+
+            try:
+                ex = self.script.executor or get_executor()
+            except Exception:  # no device: Script.execute raises the proper error below
+                ex = None
+            if ex is not None and hasattr(ex, "partial_trace"):
+                reduce_dev = ex
+        on_device = _device or reduce_dev is not None
+
         if B > 1:
             ax_params, ax_inputs, ax_pulse = self._batch_axes(B)
             keys = LazyKeys(sub_key, B)
@@ -720,15 +735,30 @@ class Model:
                 type=meas_type, obs=obs,
                 args=(params, inputs, pulse_params, keys, enc_params),
                 kwargs=exec_kwargs, in_axes=in_axes, shots=self.shots, key=shot_key,
-                device_result=_device)
+                device_result=on_device)
         else:
             result = self.script.execute(
                 type=meas_type, obs=obs,
                 args=(params, inputs, pulse_params, sub_key, enc_params),
-                kwargs=exec_kwargs, shots=self.shots, key=shot_key, device_result=_device)
-            if _device:
+                kwargs=exec_kwargs, shots=self.shots, key=shot_key, device_result=on_device)
+            if on_device:
                 result = result[None]
         if _device:
+            return result
+        if reduce_dev is not None:
+            ex = reduce_dev
+            if self.execution_type == "density":
+                result = ex.to_host(ex.partial_trace(result, self.n_qubits, self.output_qubit))
+            elif isinstance(self.output_qubit[0], (list, tuple)):
+                result = np.stack([ex.to_host(ex.marginal_probs(result, self.n_qubits, list(g)))
+                                   for g in self.output_qubit])
+            else:
+                result = ex.to_host(ex.marginal_probs(result, self.n_qubits, self.output_qubit))
+            result = np.asarray(result)
+            result = result.reshape((*self.eff_batch_shape, *self._result_shape)).squeeze()
+            if (self.execution_type == "probs" and force_mean
+                    and len(result.shape) > 0 and self._result_shape[0] > 1):
+                result = result.mean(axis=-1)
             return result
 
         result = self._postprocess_res(result)

@@ -235,3 +235,29 @@ def test_shots_run_chunked_and_reject_large_registers(monkeypatch):
 
     with pytest.raises(backend.BackendError, match="limited to 14 qubits"):
         Script(wide, 15).execute("probs", shots=10, key=qrng.key(1))
+
+
+@pytest.mark.parametrize("precision", ["complex128", "complex64"])
+def test_device_partial_trace_and_marginals_equal_host_helpers(precision):
+    """qmlb_partial_trace / qmlb_marginal_probs (what Model uses for output_qubit subsets on
+    the GPU) against jaqsi.partial_trace / marginalize_probs applied to the full outputs."""
+    from qml_essentials_b200 import jaqsi as js
+
+    tol = 1e-12 if precision == "complex128" else 2e-6
+    noise = {"Depolarizing": 0.03, "AmplitudeDamping": 0.05}
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        x = np.linspace(-1, 1, 5).reshape(-1, 1)
+        full = Model(6, 1, "Hardware_Efficient", precision=precision)
+        for keep in ([1, 4], [0], [2, 3, 5], [5, 0]):
+            sub = Model(6, 1, "Hardware_Efficient", output_qubit=keep, precision=precision)
+            sub.params = full.params
+            for nz in (None, noise):
+                rho = full(inputs=x, execution_type="density", noise_params=nz)
+                got = sub(inputs=x, execution_type="density", noise_params=nz)
+                want = js.partial_trace(rho, 6, keep)
+                assert got.shape == want.shape and np.abs(got - want).max() < tol, (keep, nz)
+                pr = full(inputs=x, execution_type="probs", noise_params=nz)
+                got = sub(inputs=x, execution_type="probs", noise_params=nz)
+                want = js.marginalize_probs(pr.reshape(5, -1), 6, keep)
+                assert np.abs(got.reshape(5, -1) - want).max() < tol, (keep, nz)
