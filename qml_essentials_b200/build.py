@@ -21,7 +21,8 @@ LIB = os.path.join(HERE, "libqmlb200.so")
 UNITS = ["qmlb_api.cu", "qmlb_reg_f32.cu", "qmlb_reg_f64.cu", "qmlb_tile_f32.cu",
          "qmlb_tile_f64.cu", "qmlb_stream_f32_lean.cu", "qmlb_stream_f32_heavy.cu", "qmlb_stream_f64_lean.cu",
          "qmlb_stream_f64_heavy.cu", "qmlb_frame_plan.cu", "qmlb_frame_f32.cu", "qmlb_frame_f64.cu",
-         "qmlb_fstream_f32.cu", "qmlb_fstream_f64.cu"]
+         "qmlb_fstream_f32.cu", "qmlb_fstream_f64.cu", "qmlb_frame_ptm_f32.cu",
+         "qmlb_frame_ptm_f64.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xptxas", "-v",

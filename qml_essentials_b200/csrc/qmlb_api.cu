@@ -619,6 +619,17 @@ int plan(qmlb_program* p) {
     return QMLB_OK;
   }
 
+  // ---- strategy 5: Pauli-basis frame engine for noisy density programs ----------------
+  if ((force < 0 || force == 5) && !p->force_stream && p->density && env_int("QMLB_PTM", 1)) {
+    if (plan_frame_ptm(p) == QMLB_OK) {
+      p->strategy = 5;
+      p->direct_out = true;
+      p->frame_out_mode = p->out_type == QMLB_OUT_PROBS ? 1 : 2;
+      return QMLB_OK;
+    }
+    if (force == 5) return fail(QMLB_ERR_UNSUPPORTED, "program outside the Pauli-basis engine");
+  }
+
   // ---- strategy 3: on-chip frame engine (state in shared memory / cluster DSMEM) -----
   if ((force < 0 || force == 3) && !p->force_stream && env_int("QMLB_FRAME", 1)) {
     if (plan_frame(p) == QMLB_OK) {
@@ -829,7 +840,9 @@ size_t pre_layout(const qmlb_program* p, const qmlb_arg* a, int64_t batch, bool 
 
 // batched streaming runs keep a table of every (element, op) matrix
 size_t premats_bytes(const qmlb_program* p, int64_t batch) {
-  if (!(p->strategy == 3 || p->strategy == 4 || (p->strategy == 2 && batch > 1))) return 0;
+  if (!(p->strategy == 3 || p->strategy == 4 || p->strategy == 5 ||
+        (p->strategy == 2 && batch > 1)))
+    return 0;
   return ((size_t)batch * p->stream_mat_row * cs_of(p->dtype) + 255) & ~size_t(255);
 }
 
@@ -939,6 +952,13 @@ int run_typed(const qmlb_program* p, RunArgs& R, void* out, void* workspace, siz
     const bool f64 = std::is_same<T, double>::value;
     CUDA_TRY((f64 ? launch_stream_mats_f64 : launch_stream_mats_f32)(p, R, premats, st));
     CUDA_TRY((f64 ? launch_fstream_f64 : launch_fstream_f32)(p, R, state, premats, 1, st));
+  } else if (p->strategy == 5) {
+    unsigned char* premats = static_cast<unsigned char*>(workspace) + tab_bytes +
+                             (state_layout(p, R.batch, &part_off) - premats_bytes(p, R.batch));
+    const bool f64 = std::is_same<T, double>::value;
+    CUDA_TRY((f64 ? launch_stream_mats_f64 : launch_stream_mats_f32)(p, R, premats, st));
+    CUDA_TRY((f64 ? launch_frame_ptm_f64 : launch_frame_ptm_f32)(p, R, premats, out,
+                                                                   p->frame_out_mode, st));
   } else if (p->strategy == 3) {
     // [tables | state + partials | evaluated matrices]: one launch evaluates every matrix
     // of every element, one launch runs the whole tape on chip
@@ -1001,7 +1021,7 @@ int qmlb_plan_describe(const qmlb_program_desc* d, char* buf, size_t buflen) {
       }
       s += "\n";
     }
-  } else if (prog.strategy == 3 || prog.strategy == 4) {
+  } else if (prog.strategy == 3 || prog.strategy == 4 || prog.strategy == 5) {
     s += describe_frame(&prog);
   } else if (prog.strategy == 1) {
     s += "smem_bytes " + std::to_string(prog.smem) + " teams " + std::to_string(prog.teams) + "\n";
@@ -1063,7 +1083,7 @@ int qmlb_program_info(const qmlb_program* p, int32_t* strategy, int32_t* n_passe
   if (n_passes)
     *n_passes = p->strategy == 0   ? 1
                 : p->strategy == 2 ? (int32_t)p->stream_passes.size()
-                : p->strategy == 3 ? (int32_t)p->frame_steps.size()
+                : (p->strategy == 3 || p->strategy == 5) ? (int32_t)p->frame_steps.size()
                 : p->strategy == 4 ? (int32_t)p->fstream_passes.size()
                                    : (int32_t)p->passes.size();
   if (n_device_ops) *n_device_ops = (int32_t)p->ops.size();

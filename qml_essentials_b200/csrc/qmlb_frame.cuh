@@ -409,19 +409,17 @@ __device__ __forceinline__ void frame_subpass(cx<T>* tile, const cx<T>* mats, co
 
 // RELAYOUT gather: destination d of this thread <- source (rank, index) through the GF(2)
 // map; PER amplitudes per thread held in registers across the cluster barrier
-template <typename T, int PER, typename Cluster>
-__device__ __forceinline__ void frame_relayout(cx<T>* tile, Cluster& cluster, bool clustered,
-                                               unsigned rank, int Tb, int team_bits, int tlane,
-                                               uint32_t cmine, const uint32_t* tab_lo,
-                                               const uint32_t* tab_hi) {
-  using V = typename std::conditional<sizeof(T) == 8, double2, float2>::type;  // one access
+template <typename V, int PER, typename Cluster>
+__device__ __forceinline__ void frame_relayout_v(V* tv, Cluster& cluster, bool clustered,
+                                                 unsigned rank, int Tb, int team_bits, int tlane,
+                                                 uint32_t cmine, const uint32_t* tab_lo,
+                                                 const uint32_t* tab_hi, int hi_shift = 8) {
   const uint32_t tile_mask = (1u << Tb) - 1u;
-  V* tv = reinterpret_cast<V*>(tile);
   V hold[PER];
 #pragma unroll
   for (int k = 0; k < PER; ++k) {
     const uint32_t d = (uint32_t)tlane + ((uint32_t)k << team_bits);
-    const uint32_t src = cmine ^ tab_lo[d & 255u] ^ tab_hi[d >> 8];
+    const uint32_t src = cmine ^ tab_lo[d & 255u] ^ tab_hi[d >> hi_shift];
     const uint32_t r = src >> Tb, loc = src & tile_mask;
     const V* from = tv;
     if (clustered && r != rank) from = cluster.map_shared_rank(tv, r);
@@ -433,6 +431,16 @@ __device__ __forceinline__ void frame_relayout(cx<T>* tile, Cluster& cluster, bo
     __syncthreads();
 #pragma unroll
   for (int k = 0; k < PER; ++k) tv[(uint32_t)tlane + ((uint32_t)k << team_bits)] = hold[k];
+}
+
+template <typename T, int PER, typename Cluster>
+__device__ __forceinline__ void frame_relayout(cx<T>* tile, Cluster& cluster, bool clustered,
+                                               unsigned rank, int Tb, int team_bits, int tlane,
+                                               uint32_t cmine, const uint32_t* tab_lo,
+                                               const uint32_t* tab_hi) {
+  using V = typename std::conditional<sizeof(T) == 8, double2, float2>::type;  // one access
+  frame_relayout_v<V, PER>(reinterpret_cast<V*>(tile), cluster, clustered, rank, Tb, team_bits,
+                           tlane, cmine, tab_lo, tab_hi);
 }
 
 // HEAVY = the program holds a dense op on 3 or 4 bits (rare: 2-qubit channels, CCX as a

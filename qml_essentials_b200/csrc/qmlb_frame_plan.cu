@@ -2,6 +2,7 @@
 // SUBPASS / RELAYOUT steps (qmlb_frame_types.h).  Pure host code - no CUDA call - so the
 // CPU test-suite can check every schedule through qmlb_plan_describe.
 #include <algorithm>
+#include <cmath>
 #include <cstdlib>
 #include <cstring>
 #include <string>
@@ -38,7 +39,7 @@ struct OpInfo {
 };
 
 int base_entries(const qmlb_program* p, const qmlb_op& o) {
-  if (o.kind == QMLB_OP_PERM) return 0;
+  if (o.kind == QMLB_OP_PERM || o.kind == QMLB_OP_SIGN) return 0;
   const qmlb_source& s = p->sources[o.src];
   return source_entries(s.kind, s.k, s.flags);
 }
@@ -62,6 +63,7 @@ bool analyse(const qmlb_program* p, std::vector<OpInfo>& info) {
         f.need = 1ull << o.bits[1];
         break;
       case QMLB_OP_DIAG:
+      case QMLB_OP_SIGN:
         break;
       case QMLB_OP_PERM: {
         const int D = 1 << o.k;
@@ -200,6 +202,9 @@ struct Builder {
   int N, T, G;
   int mat_cap;
   bool resident = false;   // matrices of the whole element stay in shared memory
+  bool ptm = false;        // Pauli-basis engine: real state, 4x4 transfer matrices
+  std::vector<char> ptm_diag;  // per op: its transfer matrix is provably diagonal
+  uint64_t init_xmask = 0;     // physical positions that hold x bits in the initial frame
   std::vector<FrameStep> steps;
   std::vector<std::vector<int>> step_ops;  // program-op indices per step (describe)
 
@@ -391,15 +396,15 @@ bool Builder::build_step() {
         ok = want.size() <= pin_try.size() && std::equal(want.begin(), want.end(), pin_try.begin());
     }
     std::vector<int> par_try = par_bits;
-    if (ok && (o.kind == QMLB_OP_CTRL1 || o.kind == QMLB_OP_DIAG)) {
-      const int first = o.kind == QMLB_OP_CTRL1 ? 0 : 0;
+    if (ok && (o.kind == QMLB_OP_CTRL1 || o.kind == QMLB_OP_DIAG || o.kind == QMLB_OP_SIGN)) {
+      const int first = 0;
       const int last = o.kind == QMLB_OP_CTRL1 ? 1 : o.k;
       for (int a = first; a < last; ++a)
         if (std::find(par_try.begin(), par_try.end(), o.bits[a]) == par_try.end())
           par_try.push_back(o.bits[a]);
       ok = FRAME_R + (int)par_try.size() <= FRAME_MAX_PAR;
     }
-    const int need_slots = o.kind == QMLB_OP_DIAG ? 2 : 1;
+    const int need_slots = (o.kind == QMLB_OP_DIAG || o.kind == QMLB_OP_SIGN) ? 2 : 1;
     const int e = resident ? 0 : f.entries;
     if (ok) ok = slots + need_slots <= FRAME_MAX_OPS && entries + e <= mat_cap;
     if (!ok) {
@@ -516,7 +521,7 @@ bool Builder::build_step() {
       fo.k = (uint8_t)o.k;
       fo.premat_off = premat_off[i];
       fo.smem_off = resident ? premat_off[i] : used;
-      if (o.kind != QMLB_OP_DIAG) {
+      if (o.kind != QMLB_OP_DIAG && o.kind != QMLB_OP_SIGN) {
         const Shape sh = shape_of(p, o.src);
         fo.shape = sh.xshape && o.kind == QMLB_OP_MAT && o.k == 2
                        ? QMLB_FSHAPE_XREAL
@@ -534,7 +539,8 @@ bool Builder::build_step() {
         fo.flags = p0 < p1 ? 1 : 0;
         fo.has_c = has_c(fo.j0) || has_c(fo.j1);
         // the evaluated matrix is stored with the roles of its two bits already swapped
-        p->stream_matlist[matlist_index[i]].swap2 = fo.flags & 1;
+        p->stream_matlist[matlist_index[i]].swap2 = (ptm ? 2 : 0) | (fo.flags & 1);
+        if (ptm) fo.shape = ptm_diag[i] ? QMLB_FSHAPE_PDIAG : QMLB_FSHAPE_REAL;
       } else if (o.kind == QMLB_OP_MAT) {
         fo.code = QMLB_FOP_MATK;
       } else if (o.kind == QMLB_OP_CTRL1) {
@@ -542,12 +548,15 @@ bool Builder::build_step() {
         fo.j0 = (uint8_t)regpos[o.bits[1]];
         fo.j1 = (uint8_t)par_index(o.bits[0]);
         fo.has_c = has_c(fo.j0);
+      } else if (o.kind == QMLB_OP_SIGN) {
+        fo.code = QMLB_FOP_SIGN;
+        fo.premat_off = o.aux;  // the sign mask
       } else {
         fo.code = QMLB_FOP_DIAG;
       }
       used += info[i].entries;
       s.ops[slot++] = fo;
-      if (o.kind == QMLB_OP_DIAG) {
+      if (o.kind == QMLB_OP_DIAG || o.kind == QMLB_OP_SIGN) {
         FrameOp aux;
         std::memset(&aux, 0, sizeof(aux));
         uint8_t* idx = reinterpret_cast<uint8_t*>(&aux);
@@ -581,7 +590,9 @@ bool Builder::build_step() {
           m1 = false;
         }
       }
-      if (d2 && slot > 0) {
+      if (ptm) {
+        s.fast = 0;  // the Pauli-basis kernel has its own item loop
+      } else if (d2 && slot > 0) {
         s.fast = 16 + 4 * (sA + 1) + (sB + 1);
       } else if (m1 && slot > 0) {
         s.fast = 64 + 16 * (all_real ? 1 : 0) + mask;
@@ -606,6 +617,8 @@ int Builder::run() {
   F.N = N;
   F.T = T;
   F.set_permutation(choose_positions());
+  init_xmask = 0;
+  for (int j = N / 2; j < N; ++j) init_xmask |= F.col[j];  // ket (= x) bits of a density program
   size_t remaining = p->ops.size();
   auto count_left = [&]() {
     size_t n = 0;
@@ -904,6 +917,242 @@ int plan_frame(qmlb_program* p) {
   return QMLB_OK;
 }
 
+
+// ---------------------------------------------------------------------------------------
+// Pauli-basis (transfer-matrix) form of a density program.  rho = 2^-n sum_P r_P P with REAL
+// coefficients r_P = Tr(P rho): half the memory of the complex 4^n vector (config 4: 512 KiB
+// instead of 1 MiB -> a cluster of 4 CTAs instead of 8) and a quarter of the arithmetic (a
+// 1-qubit superoperator is a real 4x4 on four real numbers instead of a complex 4x4 on four
+// complex ones).  Qubit w keeps its two index bits: the ket bit now holds x_w, the bra bit
+// z_w, Pauli = X^x Z^z up to phase (I = 00, Z = 01, X = 10, Y = 11), so the fused (ket, bra)
+// superoperator ops become 4x4 transfer matrices R = T S T^-1 on the SAME bits (evaluated by
+// k_stream_mats, swap2 = 2).  A CX is a Clifford: it permutes Paulis by the GF(2)-linear map
+// x_t ^= x_c, z_c ^= z_t - folded into the frame like every linear permutation - times the
+// sign (-1)^(x_c z_t (x_t ^ z_c ^ 1)) (Aaronson-Gottesman), applied as a +-1 diagonal over
+// four parity rows.  Eligible: density programs made of 1-qubit (ket, bra) ops and CX / SWAP
+// pairs with <Z-string> or probability output; everything else keeps the complex form.
+static const int kCxFirst[4] = {0, 1, 3, 2}, kCxSecond[4] = {0, 3, 2, 1}, kSwap[4] = {0, 2, 1, 3};
+
+static int perm_kind(const qmlb_program* p, const qmlb_op& o) {
+  if (o.kind != QMLB_OP_PERM || o.k != 2) return -1;
+  int t[4];
+  for (int v = 0; v < 4; ++v) t[v] = (int)p->consts[o.aux + v];
+  if (std::equal(t, t + 4, kCxFirst)) return 0;
+  if (std::equal(t, t + 4, kCxSecond)) return 1;
+  if (std::equal(t, t + 4, kSwap)) return 2;
+  return -1;
+}
+
+// host value of a superoperator source made of constants only (else false)
+static bool const_super(const qmlb_program* p, int sid, double out[32]) {
+  const qmlb_source& s = p->sources[sid];
+  auto load = [&](int off, int n, double* dst) {
+    for (int i = 0; i < 2 * n; ++i) dst[i] = p->consts[2 * (size_t)off + i];
+  };
+  if (s.kind == QMLB_SRC_CONST && s.k == 2 && !(s.flags & QMLB_FLAG_DIAGVEC)) {
+    load(s.a0, 16, out);
+    return true;
+  }
+  if (s.kind != QMLB_SRC_SUPER) return false;
+  double acc[32] = {0};
+  for (int i = 0; i < 4; ++i) acc[2 * (i * 5)] = 1.0;
+  for (int t = 0; t < s.a1; ++t) {
+    const qmlb_source& it = p->sources[p->items[s.a0 + t]];
+    if (!(it.kind == QMLB_SRC_CONST && it.k == 2 && !(it.flags & QMLB_FLAG_DIAGVEC))) return false;
+    double f[32], r[32];
+    load(it.a0, 16, f);
+    for (int i = 0; i < 4; ++i)
+      for (int j = 0; j < 4; ++j) {
+        double re = 0, im = 0;
+        for (int l = 0; l < 4; ++l) {
+          const double ar = f[2 * (i * 4 + l)], ai = f[2 * (i * 4 + l) + 1];
+          const double br = acc[2 * (l * 4 + j)], bi = acc[2 * (l * 4 + j) + 1];
+          re += ar * br - ai * bi;
+          im += ar * bi + ai * br;
+        }
+        r[2 * (i * 4 + j)] = re;
+        r[2 * (i * 4 + j) + 1] = im;
+      }
+    std::memcpy(acc, r, sizeof(acc));
+  }
+  std::memcpy(out, acc, sizeof(acc));
+  return true;
+}
+
+// R = T S T^-1 for S in (ket, bra) order [rho00, rho01, rho10, rho11] and Pauli order
+// (I, Z, X, Y); is it diagonal?
+static bool ptm_is_diagonal(const double S[32]) {
+  // T rows: I = (1,0,0,1), Z = (1,0,0,-1), X = (0,1,1,0), Y = (0,i,-i,0); T^-1 = T^dagger / 2
+  const double Tr[4][4] = {{1, 0, 0, 1}, {1, 0, 0, -1}, {0, 1, 1, 0}, {0, 0, 0, 0}};
+  const double Ti[4][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}, {0, 0, 0, 0}, {0, 1, -1, 0}};
+  for (int a = 0; a < 4; ++a)
+    for (int b = 0; b < 4; ++b) {
+      double re = 0, im = 0;
+      for (int i = 0; i < 4; ++i)
+        for (int j = 0; j < 4; ++j) {
+          // T[a][i] * S[i][j] * conj(T[b][j]) / 2
+          const double tr = Tr[a][i], ti = Ti[a][i], sr = S[2 * (i * 4 + j)],
+                       si = S[2 * (i * 4 + j) + 1], ur = Tr[b][j], ui = -Ti[b][j];
+          const double xr = tr * sr - ti * si, xi = tr * si + ti * sr;
+          re += 0.5 * (xr * ur - xi * ui);
+          im += 0.5 * (xr * ui + xi * ur);
+        }
+      if (a != b && (std::abs(re) > 1e-15 || std::abs(im) > 1e-15)) return false;
+    }
+  return true;
+}
+
+int plan_frame_ptm(qmlb_program* p) {
+  if (!p->density) return QMLB_ERR_UNSUPPORTED;
+  const int n = p->n_qubits, N = p->n_bits;
+  if (!(p->out_type == QMLB_OUT_PROBS ||
+        (p->out_type == QMLB_OUT_EXPVAL &&
+         std::all_of(p->obs.begin(), p->obs.end(),
+                     [](const qmlb_obs& o) { return o.kind == QMLB_OBS_ZSTRING; }))))
+    return QMLB_ERR_UNSUPPORTED;
+  if (p->out_type == QMLB_OUT_PROBS && n > 10) return QMLB_ERR_UNSUPPORTED;
+  // ---- rewrite the op list ----------------------------------------------------------
+  qmlb_program q = *p;  // shares sources / items / angles / terms; ops and consts change
+  q.blob = nullptr;
+  q.ops.clear();
+  std::vector<char> diag_flag;
+  std::vector<int> origin;  // rewritten op -> index of the original op (describe / tests)
+  for (size_t i = 0; i < p->ops.size(); ++i) {
+    const qmlb_op& o = p->ops[i];
+    if (o.kind == QMLB_OP_MAT && o.k == 2 && o.bits[0] - o.bits[1] == n && o.bits[1] < n) {
+      q.ops.push_back(o);
+      origin.push_back((int)i);
+      double S[32];
+      diag_flag.push_back(const_super(p, o.src, S) && ptm_is_diagonal(S) ? 1 : 0);
+      continue;
+    }
+    const int kind = perm_kind(p, o);
+    if (kind < 0 || i + 1 >= p->ops.size()) return QMLB_ERR_UNSUPPORTED;
+    const qmlb_op& o2 = p->ops[i + 1];
+    if (perm_kind(p, o2) != kind || o.bits[0] < n || o.bits[1] < n ||
+        o2.bits[0] != o.bits[0] - n || o2.bits[1] != o.bits[1] - n)
+      return QMLB_ERR_UNSUPPORTED;
+    ++i;
+    // bit roles: ket bit of wire w = x_w, bra bit = z_w
+    const int a = kind == 1 ? 1 : 0;  // index (in o.bits) of the control / first wire
+    const int xc = o.bits[a], zc = o2.bits[a], xt = o.bits[1 - a], zt = o2.bits[1 - a];
+    qmlb_op perm{};
+    perm.kind = QMLB_OP_PERM;
+    perm.k = 4;
+    perm.src = -1;
+    perm.aux = (int32_t)q.consts.size();
+    perm.bits[0] = xc;
+    perm.bits[1] = zc;
+    perm.bits[2] = xt;
+    perm.bits[3] = zt;
+    int sign_mask = 0;
+    for (int v = 0; v < 16; ++v) {  // v = x_c z_c x_t z_t
+      const int vxc = v >> 3 & 1, vzc = v >> 2 & 1, vxt = v >> 1 & 1, vzt = v & 1;
+      int img;
+      if (kind == 2) {
+        img = (vxt << 3) | (vzt << 2) | (vxc << 1) | vzc;
+      } else {
+        img = (vxc << 3) | ((vzc ^ vzt) << 2) | ((vxt ^ vxc) << 1) | vzt;
+        if (vxc & vzt & (vxt ^ vzc ^ 1)) sign_mask |= 1 << v;
+      }
+      q.consts.push_back((double)img);
+    }
+    q.ops.push_back(perm);
+    diag_flag.push_back(0);
+    origin.push_back((int)i - 1);
+    if (sign_mask) {
+      qmlb_op sg{};
+      sg.kind = QMLB_OP_SIGN;
+      sg.k = 4;
+      sg.src = -1;
+      sg.aux = sign_mask;
+      sg.bits[0] = xc;
+      sg.bits[1] = zc;
+      sg.bits[2] = xt;
+      sg.bits[3] = zt;
+      q.ops.push_back(sg);
+      diag_flag.push_back(0);
+      origin.push_back((int)i - 1);
+    }
+  }
+  // ---- geometry: real elements -----------------------------------------------------
+  const size_t rs = p->dtype == QMLB_C128 ? 8 : 4, cs = 2 * rs;
+  const int maxT = p->dtype == QMLB_C128 ? 14 : 15;
+  if (N < 6 || N > maxT + 3) return QMLB_ERR_UNSUPPORTED;
+  Builder B;
+  B.p = &q;
+  B.ptm = true;
+  B.ptm_diag = diag_flag;
+  if (!analyse(&q, B.info)) return QMLB_ERR_UNSUPPORTED;
+  B.N = N;
+  B.G = std::max(0, N - maxT);
+  B.T = N - B.G;
+  int threads, team_bits, teams;
+  if (B.T - FRAME_R >= 8) {
+    team_bits = std::min(10, B.T - FRAME_R);
+    threads = 1 << team_bits;
+    teams = 1;
+  } else {
+    threads = 256;
+    team_bits = B.T - FRAME_R;
+    teams = threads >> team_bits;
+  }
+  int row = 0;
+  B.premat_off.assign(q.ops.size(), 0);
+  B.matlist_index.assign(q.ops.size(), -1);
+  q.stream_matlist.clear();
+  for (size_t i = 0; i < q.ops.size(); ++i) {
+    if (q.ops[i].kind != QMLB_OP_MAT) continue;
+    B.premat_off[i] = row;
+    B.matlist_index[i] = (int)q.stream_matlist.size();
+    StreamMatOp mo{};
+    mo.src = q.ops[i].src;
+    mo.off = row;
+    mo.swap2 = 2;
+    q.stream_matlist.push_back(mo);
+    row += B.info[i].entries;  // 16 complex slots; the 16 reals of R use the first half
+  }
+  q.stream_mat_row = row;
+  const size_t budget = 216 * 1024;
+  const size_t fixed = 2 * sizeof(FrameStep) + (256 + 128) * sizeof(uint32_t) + 2048 * sizeof(double);
+  const size_t tile_bytes = (size_t(1) << B.T) * rs;
+  while (teams > 1 && (size_t)teams * (tile_bytes + (size_t)row * cs) + fixed > budget) teams >>= 1;
+  if ((size_t)teams * (tile_bytes + (size_t)row * cs) + fixed > budget) return QMLB_ERR_UNSUPPORTED;
+  if (teams > 1 || team_bits < 8) threads = teams << team_bits;
+  if (threads < 32) return QMLB_ERR_UNSUPPORTED;
+  B.mat_cap = std::max(row, 1);
+  B.resident = true;
+  const int rc = B.run();
+  if (rc != QMLB_OK) return rc;
+  // the physical positions that hold x bits at the start (initial frame = permutation)
+  p->stream_matlist = q.stream_matlist;
+  p->stream_mat_row = row;
+  p->frame_steps = std::move(B.steps);
+  p->frame_step_ops = std::move(B.step_ops);
+  for (auto& v : p->frame_step_ops)
+    for (int& idx : v) idx = origin[idx];
+  FrameProg& fp = p->frame;
+  std::memset(&fp, 0, sizeof(fp));
+  fp.n_steps = (int)p->frame_steps.size();
+  fp.n_bits = N;
+  fp.tile_bits = B.T;
+  fp.outer_bits = B.G;
+  fp.team_bits = team_bits;
+  fp.teams = teams;
+  fp.mat_cap = B.mat_cap;
+  fp.mat_resident = 1;
+  fp.premat_row = row;
+  fp.density = 1;
+  fp.n_qubits = n;
+  fp.n_obs = (int)p->obs.size();
+  fp.ptm = 1;
+  p->frame_ptm_xmask = B.init_xmask;
+  p->frame_threads = threads;
+  p->frame_heavy = false;
+  p->frame_smem = (size_t)teams * (tile_bytes + (size_t)row * cs) + fixed;
+  return QMLB_OK;
+}
+
 std::string describe_frame(const qmlb_program* p) {
   std::string s;
   const FrameProg& fp = p->frame;
@@ -924,7 +1173,8 @@ std::string describe_frame(const qmlb_program* p) {
        std::to_string(fp.outer_bits) + " team_bits " + std::to_string(fp.team_bits) +
        " teams " + std::to_string(fp.teams) + " threads " + std::to_string(p->frame_threads) +
        " mat_cap " + std::to_string(fp.mat_cap) + " resident " + std::to_string(fp.mat_resident) +
-       " premat_row " + std::to_string(fp.premat_row) +
+       " premat_row " + std::to_string(fp.premat_row) + " ptm " + std::to_string(fp.ptm) +
+       " xmask " + std::to_string((unsigned long long)p->frame_ptm_xmask) +
        " smem " + std::to_string(p->frame_smem) + "\n";
   for (size_t i = 0; i < p->frame_steps.size(); ++i) {
     const FrameStep& st = p->frame_steps[i];
@@ -951,7 +1201,7 @@ std::string describe_frame(const qmlb_program* p) {
            std::to_string(fo.has_c) + ":" + std::to_string(fo.flags) + ":" +
            std::to_string(fo.premat_off) + ":" + std::to_string(fo.smem_off) + ":" +
            std::to_string(fo.shape);
-      if (fo.code == QMLB_FOP_DIAG) {
+      if (fo.code == QMLB_FOP_DIAG || fo.code == QMLB_FOP_SIGN) {
         const uint8_t* idx = reinterpret_cast<const uint8_t*>(&st.ops[o + 1]);
         s += ":";
         for (int a = 0; a < fo.k; ++a) s += (a ? "," : "") + std::to_string(idx[a]);

@@ -1,0 +1,233 @@
+// Pauli-basis form of the on-chip frame engine (strategy 5): a noisy density-matrix program
+// evolved as the REAL vector r_P = Tr(P rho) of 4^n Pauli coefficients (see plan_frame_ptm in
+// qmlb_frame_plan.cu).  Same step program, frame algebra and relayouts as qmlb_frame.cuh;
+// what changes is the element (one real number instead of a complex one: config 4 fits a
+// cluster of 4 CTAs instead of 8), the gate (a real 4x4 transfer matrix on four reals: 16
+// FMA instead of 64; diagonal for depolarizing / flip / phase-damping channels) and the
+// Clifford sign op.  <Z_S> is ONE coefficient (r at index S on the z bits), probabilities
+// are a Walsh-Hadamard transform of the 2^n coefficients with x = 0.
+#pragma once
+
+#include "qmlb_frame.cuh"
+
+namespace qmlb {
+
+// real 4x4 on register bits JA > JB of a group of 16 reals; m = 16 reals, row-major
+template <typename T, int JA, int JB, bool DIAG>
+__device__ __forceinline__ void ptm_mat2(T (&S)[FRAME_D], const T* __restrict__ m) {
+  static_assert(JA > JB, "canonical order");
+  if constexpr (DIAG) {
+    const T d0 = m[0], d1 = m[5], d2 = m[10], d3 = m[15];
+#pragma unroll
+    for (int g = 0; g < (1 << (FRAME_R - 2)); ++g) {
+      const int t = ((g >> JB) << (JB + 1)) | (g & ((1 << JB) - 1));
+      const int i00 = ((t >> JA) << (JA + 1)) | (t & ((1 << JA) - 1));
+      S[i00] *= d0;
+      S[i00 | (1 << JB)] *= d1;
+      S[i00 | (1 << JA)] *= d2;
+      S[i00 | (1 << JA) | (1 << JB)] *= d3;
+    }
+  } else {
+    T mm[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) mm[i] = m[i];
+#pragma unroll
+    for (int g = 0; g < (1 << (FRAME_R - 2)); ++g) {
+      const int t = ((g >> JB) << (JB + 1)) | (g & ((1 << JB) - 1));
+      const int i00 = ((t >> JA) << (JA + 1)) | (t & ((1 << JA) - 1));
+      const int idx[4] = {i00, i00 | (1 << JB), i00 | (1 << JA), i00 | (1 << JA) | (1 << JB)};
+      const T a0 = S[idx[0]], a1 = S[idx[1]], a2 = S[idx[2]], a3 = S[idx[3]];
+#pragma unroll
+      for (int v = 0; v < 4; ++v)
+        S[idx[v]] = fma(mm[v * 4 + 3], a3, fma(mm[v * 4 + 2], a2, fma(mm[v * 4 + 1], a1, mm[v * 4] * a0)));
+    }
+  }
+}
+
+template <typename T, int THREADS>
+__global__ void __launch_bounds__(THREADS, THREADS >= 512 ? 1 : 2)
+    k_frame_ptm(DevProg P, RunArgs A, const FrameProg F, const uint64_t xmask,
+                const cx<T>* __restrict__ premats, void* __restrict__ out) {
+  extern __shared__ __align__(16) unsigned char fsm[];
+  const int Tb = F.tile_bits;
+  const uint32_t tile_n = 1u << Tb;
+  const int teams = F.teams;
+  const int tsize = 1 << F.team_bits;
+  const int team = threadIdx.x >> F.team_bits;
+  const int tlane = threadIdx.x & (tsize - 1);
+  // [tiles (real) | matrices | 2 step records | relayout tables | scratch]
+  T* tiles = reinterpret_cast<T*>(fsm);
+  cx<T>* mats_all = reinterpret_cast<cx<T>*>(tiles + (size_t)teams * tile_n);
+  FrameStep* sstep = reinterpret_cast<FrameStep*>(mats_all + (size_t)teams * F.mat_cap);
+  uint32_t* tab_lo = reinterpret_cast<uint32_t*>(sstep + 2);
+  uint32_t* tab_hi = tab_lo + 256;
+  double* scratch_all = reinterpret_cast<double*>(tab_hi + 128);
+  T* tile = tiles + (size_t)team * tile_n;
+  const T* mats = reinterpret_cast<const T*>(mats_all + (size_t)team * F.mat_cap);  // reals
+
+  const bool clustered = F.outer_bits > 0;
+  cg::cluster_group cluster = cg::this_cluster();
+  const unsigned rank = clustered ? cluster.block_rank() : 0u;
+  const int64_t cluster_id = blockIdx.x >> F.outer_bits;
+  const int64_t n_clusters = gridDim.x >> F.outer_bits;
+  auto sync_all = [&]() {
+    if (clustered)
+      cluster.sync();
+    else
+      __syncthreads();
+  };
+  const int64_t per_round = n_clusters * teams;
+  const int64_t rounds = (A.batch + per_round - 1) / per_round;
+  const uint32_t n_items = 1u << (Tb - FRAME_R);
+  const int nq = F.n_qubits;
+
+  for (int64_t rd = 0; rd < rounds; ++rd) {
+    const int64_t bl = rd * per_round + cluster_id * teams + team;
+    const bool valid = bl < A.batch;
+    const cx<T>* prow = premats + (size_t)(valid ? bl : 0) * F.premat_row;
+
+    // |0..0><0..0| = 2^-n prod_q (I + Z_q): coefficient 1 wherever every x bit is 0
+    for (uint32_t i = tlane; i < tile_n; i += tsize) {
+      const uint64_t full = ((uint64_t)rank << Tb) | i;
+      tile[i] = (full & xmask) ? (T)0 : (T)1;
+    }
+    {
+      cx<T>* mdst = mats_all + (size_t)team * F.mat_cap;
+      for (int i = tlane; i < F.premat_row; i += tsize) mdst[i] = prow[i];
+    }
+    for (int i = threadIdx.x; i < 256; i += THREADS)
+      reinterpret_cast<uint32_t*>(&sstep[0])[i] = reinterpret_cast<const uint32_t*>(&F.steps[0])[i];
+    sync_all();
+
+    for (int si = 0; si < F.n_steps; ++si) {
+      const FrameStep& st = sstep[si & 1];
+      if (si + 1 < F.n_steps)
+        for (int i = threadIdx.x; i < 256; i += THREADS)
+          reinterpret_cast<uint32_t*>(&sstep[(si + 1) & 1])[i] =
+              reinterpret_cast<const uint32_t*>(&F.steps[si + 1])[i];
+
+      if (st.kind == QMLB_FSTEP_RELAYOUT) {
+        for (int i = threadIdx.x; i < 256 + 128; i += THREADS) {
+          uint32_t acc = 0;
+          if (i < 256) {
+            for (int b = 0; b < 8; ++b)
+              if (i >> b & 1) acc ^= (uint32_t)st.qcol[b];
+            tab_lo[i] = acc;
+          } else {
+            const int h = i - 256;
+            for (int b = 0; b < 7; ++b)
+              if ((h >> b & 1) && 8 + b < Tb) acc ^= (uint32_t)st.qcol[8 + b];
+            tab_hi[h] = acc;
+          }
+        }
+        uint32_t cmine = 0;
+        for (int g = 0; g < F.outer_bits; ++g)
+          if (rank >> g & 1) cmine ^= (uint32_t)st.qcol[Tb + g];
+        const bool across = clustered && st.mat_entries == 0;
+        if (across)
+          cluster.sync();
+        else
+          __syncthreads();
+        const int per = (int)(tile_n >> F.team_bits);
+        if (per == 16)
+          frame_relayout_v<T, 16>(tile, cluster, across, rank, Tb, F.team_bits, tlane, cmine,
+                                  tab_lo, tab_hi);
+        else if (per == 32)
+          frame_relayout_v<T, 32>(tile, cluster, across, rank, Tb, F.team_bits, tlane, cmine,
+                                  tab_lo, tab_hi);
+        __syncthreads();
+        continue;
+      }
+
+      if (valid) {
+        uint32_t piv[FRAME_R];
+#pragma unroll
+        for (int j = 0; j < FRAME_R; ++j) piv[j] = st.pivots[j];
+        for (uint32_t it = tlane; it < n_items; it += tsize) {
+          const uint32_t base = frame_item_base(st, it, piv, rank);
+          T S[FRAME_D];
+#pragma unroll
+          for (int v = 0; v < FRAME_D; ++v) S[v] = tile[base ^ st.eoff[v]];
+#pragma unroll 1
+          for (int o = 0; o < st.n_ops; ++o) {
+            const FrameOp fo = st.ops[o];
+            if (fo.code == QMLB_FOP_MAT2) {
+              const T* m = mats + 2 * fo.smem_off;  // smem_off counts complex slots
+              const bool dg = fo.shape == QMLB_FSHAPE_PDIAG;
+              auto on_pair = [&](auto JA, auto JB) {
+                constexpr int A_ = decltype(JA)::value, B_ = decltype(JB)::value;
+                if constexpr (A_ > B_) {
+                  if (dg)
+                    ptm_mat2<T, A_, B_, true>(S, m);
+                  else
+                    ptm_mat2<T, A_, B_, false>(S, m);
+                }
+              };
+              if (fo.j0 == 3 && fo.j1 == 2)
+                on_pair(std::integral_constant<int, 3>{}, std::integral_constant<int, 2>{});
+              else if (fo.j0 == 1 && fo.j1 == 0)
+                on_pair(std::integral_constant<int, 1>{}, std::integral_constant<int, 0>{});
+              else
+                dispatch2<T, FRAME_R>(fo.j0, fo.j1, on_pair);
+            } else if (fo.code == QMLB_FOP_SIGN) {
+              const uint8_t* idx = reinterpret_cast<const uint8_t*>(&st.ops[o + 1]);
+              const unsigned mask = (unsigned)fo.premat_off;
+              int lb = 0;
+              unsigned flip[4];
+#pragma unroll
+              for (int a = 0; a < 4; ++a) {
+                const FramePar pr = st.par[idx[a]];
+                lb |= ((__popc(base & pr.rloc) ^ __popc(rank & pr.rout)) & 1) << (3 - a);
+                flip[a] = pr.smask;
+              }
+#pragma unroll
+              for (int v = 0; v < FRAME_D; ++v) {
+                int loc = lb;
+#pragma unroll
+                for (int a = 0; a < 4; ++a) loc ^= (int)((flip[a] >> v) & 1u) << (3 - a);
+                if ((mask >> loc) & 1u) S[v] = -S[v];
+              }
+              ++o;
+            }
+          }
+#pragma unroll
+          for (int v = 0; v < FRAME_D; ++v) tile[base ^ st.eoff[v]] = S[v];
+        }
+      }
+      __syncthreads();
+    }
+
+    // ---- result: coefficient of Pauli (x, z) at index x << n | z (wire q = bit n-1-q) -------
+    if (F.out_mode == 2) {
+      // <Z_S> = r at x = 0, z = S: index zmask < 2^n sits in the tile of cluster rank 0
+      if (valid && rank == 0)
+        for (int j = tlane; j < F.n_obs; j += tsize)
+          reinterpret_cast<T*>(out)[(size_t)bl * F.n_obs + j] = tile[(uint32_t)P.obs[j].zmask];
+    } else if (F.out_mode == 1) {
+      // p(b) = 2^-n sum_S (-1)^(b.S) r[S]: Walsh-Hadamard transform of the x = 0 coefficients
+      // (the first 2^n entries of rank 0's tile), done in that CTA's scratch (teams == 1)
+      if (rank == 0) {
+        const uint32_t dim = 1u << nq;
+        double* scratch = scratch_all + (size_t)team * dim;  // teams * 2^n <= 2048
+        for (uint32_t i = tlane; i < dim; i += tsize) scratch[i] = (double)tile[i];
+        __syncthreads();
+        for (int b = 0; b < nq; ++b) {
+          for (uint32_t i = tlane; i < dim / 2; i += tsize) {
+            const uint32_t lo = ((i >> b) << (b + 1)) | (i & ((1u << b) - 1u)), hi = lo | (1u << b);
+            const double u = scratch[lo], w = scratch[hi];
+            scratch[lo] = u + w;
+            scratch[hi] = u - w;
+          }
+          __syncthreads();
+        }
+        const double inv = 1.0 / (double)dim;
+        if (valid)
+          for (uint32_t i = tlane; i < dim; i += tsize)
+            reinterpret_cast<T*>(out)[((size_t)bl << nq) + i] = (T)(scratch[i] * inv);
+      }
+    }
+    sync_all();
+  }
+}
+
+}  // namespace qmlb

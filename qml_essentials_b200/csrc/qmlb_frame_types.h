@@ -41,10 +41,15 @@ constexpr int FRAME_MAX_BITS = 40;
 #define QMLB_FOP_MATK 2   // dense 2^k x 2^k on register bits k-1..0 (k = 3, 4)
 #define QMLB_FOP_CTRL1 3  // 2x2 on register bit j0 where parity row j1 reads 1
 #define QMLB_FOP_DIAG 4   // diagonal over k parity rows (their indices sit in the next slot)
+#define QMLB_FOP_SIGN 5   // +-1 over k parity rows: negate where bit (local value) of the mask in
+                          // premat_off is set (Pauli-basis engine: the sign part of a Clifford)
+
+#define QMLB_OP_SIGN 4    // planner-internal op kind behind QMLB_FOP_SIGN (never in a user program)
 
 #define QMLB_FSHAPE_FULL 0   // general complex matrix
 #define QMLB_FSHAPE_REAL 1   // every entry real (RY chains, Pauli channels): half the FMAs
 #define QMLB_FSHAPE_XREAL 2  // 4x4, real, only v == u and v == u ^ 3 (depolarizing, flips, damping)
+#define QMLB_FSHAPE_PDIAG 3  // Pauli-basis engine: the 4x4 transfer matrix is diagonal
 
 struct FrameOp {           // 16 bytes
   uint8_t code, k, j0, j1;
@@ -97,6 +102,7 @@ struct FrameProg {
   int32_t premat_row;  // evaluated-matrix entries per element
   int32_t out_mode;    // 0: complex state in index order, 1: probabilities, 2: Z-string expvals
   int32_t density, n_qubits, n_obs;
+  int32_t ptm;         // 1: the state is the REAL Pauli-coefficient vector of a density matrix
 };
 
 }  // namespace qmlb

@@ -78,6 +78,7 @@ struct qmlb_program {
   int frame_threads = 0;
   int frame_out_mode = 0;
   bool frame_heavy = false;  // a dense op on 3-4 bits
+  uint64_t frame_ptm_xmask = 0;  // strategy 5: physical positions of the x bits at the start
   size_t frame_smem = 0;
 
   // strategy 4: streaming frame engine (tiles of an HBM-resident state)
@@ -142,6 +143,11 @@ cudaError_t launch_fstream_f64(const qmlb_program* p, const RunArgs& R, void* st
                                const void* premats, int init_mode, cudaStream_t st);
 int plan_frame(qmlb_program* p);                 // QMLB_OK or QMLB_ERR_UNSUPPORTED (fall back)
 int plan_frame_stream(qmlb_program* p);
+int plan_frame_ptm(qmlb_program* p);
+cudaError_t launch_frame_ptm_f32(const qmlb_program* p, const RunArgs& R, const void* premats,
+                                 void* out, int out_mode, cudaStream_t st);
+cudaError_t launch_frame_ptm_f64(const qmlb_program* p, const RunArgs& R, const void* premats,
+                                 void* out, int out_mode, cudaStream_t st);
 std::string describe_frame(const qmlb_program* p);
 cudaError_t tile_set_smem_f32(size_t bytes);
 cudaError_t tile_set_smem_f64(size_t bytes);

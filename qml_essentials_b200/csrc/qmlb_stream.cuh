@@ -227,7 +227,46 @@ __global__ void k_stream_mats(DevProg P, RunArgs A, const StreamMatOp* __restric
   const StreamMatOp mo = list[t % n_list];
   cx<T>* dst = out + (size_t)bl * mat_row + mo.off;
   const RowsDirect rows{A, bl + A.batch_offset};
-  if (mo.swap2) {
+  if (mo.swap2 >= 2) {
+    // Pauli transfer matrix of a 1-qubit superoperator: R = T S T^-1 with S in (ket, bra)
+    // order [rho00, rho01, rho10, rho11], Pauli order (I, Z, X, Y) and T^-1 = T^dagger / 2,
+    //   T = [[1,0,0,1],[1,0,0,-1],[0,1,1,0],[0,i,-i,0]].
+    // R is real for every completely positive map; its 16 reals go to the first half of
+    // the op's 16 complex slots (row-major; swap2 == 3: roles of the two bits exchanged).
+    cx<T> S[16];
+    eval_source_mem<T>(P, A, rows, mo.src, S);
+    T* rdst = reinterpret_cast<T*>(dst);
+    // X = T S: rows I, Z, X, Y
+    cx<T> X[16];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      X[0 * 4 + j] = cadd(S[0 * 4 + j], S[3 * 4 + j]);
+      X[1 * 4 + j] = mk<T>(S[0 * 4 + j].x - S[3 * 4 + j].x, S[0 * 4 + j].y - S[3 * 4 + j].y);
+      X[2 * 4 + j] = cadd(S[1 * 4 + j], S[2 * 4 + j]);
+      // i * (S1 - S2)
+      X[3 * 4 + j] = mk<T>(-(S[1 * 4 + j].y - S[2 * 4 + j].y), S[1 * 4 + j].x - S[2 * 4 + j].x);
+    }
+    // R = X T^dagger / 2: columns I: (x0 + x3)/2, Z: (x0 - x3)/2, X: (x1 + x2)/2,
+    // Y: (conj(i) x1 + conj(-i) x2)/2 = (-i x1 + i x2)/2 -> real part = (x1.y - x2.y)/2
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+      const cx<T> x0 = X[a * 4 + 0], x1 = X[a * 4 + 1], x2 = X[a * 4 + 2], x3 = X[a * 4 + 3];
+      T r[4];
+      r[0] = (T)0.5 * (x0.x + x3.x);
+      r[1] = (T)0.5 * (x0.x - x3.x);
+      r[2] = (T)0.5 * (x1.x + x2.x);
+      r[3] = (T)0.5 * (x1.y - x2.y);
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        int ra = a, rb = b;
+        if (mo.swap2 == 3) {
+          ra = ((a & 1) << 1) | (a >> 1);
+          rb = ((b & 1) << 1) | (b >> 1);
+        }
+        rdst[ra * 4 + rb] = r[b];
+      }
+    }
+  } else if (mo.swap2) {
     cx<T> tmp[16];
     eval_source_mem<T>(P, A, rows, mo.src, tmp);
 #pragma unroll

@@ -14,13 +14,17 @@ import numpy as np
 
 from oracle import program_interp as pi
 
-FOP_MAT1, FOP_MAT2, FOP_MATK, FOP_CTRL1, FOP_DIAG = 0, 1, 2, 3, 4
+FOP_MAT1, FOP_MAT2, FOP_MATK, FOP_CTRL1, FOP_DIAG, FOP_SIGN = 0, 1, 2, 3, 4, 5
+
+# Pauli transfer matrices: rows (I, Z, X, Y), columns (rho00, rho01, rho10, rho11)
+_T = np.array([[1, 0, 0, 1], [1, 0, 0, -1], [0, 1, 1, 0], [0, 1j, -1j, 0]], dtype=np.complex128)
+_TINV = _T.conj().T / 2
 R, D = 4, 16
 
 
 def parse(text):
     lines = text.strip().split("\n")
-    assert lines[0] in ("strategy 3", "strategy 4"), lines[0]
+    assert lines[0] in ("strategy 3", "strategy 4", "strategy 5"), lines[0]
     geo = {"passes": []}
     steps = []
     for line in lines[1:]:
@@ -99,14 +103,33 @@ def emulate(prog, text, args, batch):
     interp = pi.Interp(prog, args, batch)
     mats = {}
 
+    ptm = bool(geo.get("ptm", 0))
+
     def matrix(index):
         if index not in mats:
             m = interp.source(prog.ops[index]["src"])
-            mats[index] = np.ascontiguousarray(np.broadcast_to(m, (batch,) + m.shape[1:]))
+            m = np.ascontiguousarray(np.broadcast_to(m, (batch,) + m.shape[1:]))
+            if ptm:  # transfer matrix of the (ket, bra) superoperator: real
+                m = _T @ m @ _TINV
+                assert np.abs(m.imag).max() < 1e-12
+                m = m.real.astype(np.complex128)
+            mats[index] = m
         return mats[index]
 
     st = np.zeros((batch, 1 << N), dtype=np.complex128)
     st[:, 0] = 1.0
+    if ptm:  # |0..0><0..0|: coefficient 1 wherever every x bit is 0 (initial frame)
+        idx = np.arange(1 << N, dtype=np.int64)
+        st[:, :] = ((idx & geo["xmask"]) == 0).astype(np.float64)[None, :]
+        r = _run_steps(st, steps, T, G, N, matrix, batch)
+        assert np.abs(r.imag).max() == 0.0
+        n = N // 2
+        arr = r.reshape((batch,) + (2,) * N)
+        tin = _TINV.reshape(2, 2, 2, 2)  # [k, b, x, z]
+        for w in range(n):
+            ax, az = 1 + w, 1 + n + w
+            arr = np.moveaxis(np.tensordot(tin, arr, axes=([2, 3], [ax, az])), [0, 1], [ax, az])
+        return arr.reshape(batch, 1 << N)
     if geo["passes"]:  # streamed tiles: HBM layout <-> (tile number, tile index) per pass
         idx = np.arange(1 << N, dtype=np.int64)
         for ps in geo["passes"]:
@@ -175,11 +198,14 @@ def _run_steps(st, steps, T, G, N, matrix, batch, local_only=False):
             cj = [par_at(j) for j in range(R)]
             assert not any(c.any() for c in cj), "shifted items must see unflipped values"
             for o in ops:
-                M = matrix(o["index"])
                 code, k = o["code"], o["k"]
-                if o["shape"] >= 1:  # the planner's structural claims about the matrix
+                M = matrix(o["index"]) if code != FOP_SIGN else None
+                if code == FOP_MAT2 and o["shape"] == 3:  # Pauli basis: diagonal transfer matrix
+                    off = M - np.einsum("bii->bi", M)[:, :, None] * np.eye(4)[None]
+                    assert np.abs(off).max() < 1e-14, "transfer matrix claimed diagonal"
+                elif o["shape"] >= 1 and code != FOP_SIGN:  # structural claims about the matrix
                     assert np.abs(M.imag).max() == 0.0, "matrix claimed real"
-                if o["shape"] == 2:
+                if o["shape"] == 2 and code != FOP_SIGN:
                     for v in range(4):
                         for u in range(4):
                             if v != u and v != (u ^ 3):
@@ -241,6 +267,17 @@ def _run_steps(st, steps, T, G, N, matrix, batch, local_only=False):
                             acc = acc + M[:, lv, u ^ c] * S[:, :, (v & ~(1 << j)) | (u << j)]
                         out[:, :, v] = np.where(on[None, :], acc, S[:, :, v])
                     S = out
+                elif code == FOP_SIGN:
+                    out = S.copy()
+                    mask = o["premat_off"]
+                    for v in range(D):
+                        loc = np.zeros_like(base)
+                        for a, pidx in enumerate(o["idx"]):
+                            bit = par_at(pidx) ^ ((par[pidx][2] >> v) & 1)
+                            loc |= bit << (k - 1 - a)
+                        out[:, :, v] = np.where(((mask >> loc) & 1).astype(bool)[None, :],
+                                                -S[:, :, v], S[:, :, v])
+                    S = out
                 elif code == FOP_DIAG:
                     out = S.copy()
                     for v in range(D):
@@ -276,7 +313,7 @@ class FrameEmuExecutor:
         args = [(a[0], a[1], a[2]) if a is not None else (None, 1, 1) for a in host_args]
         text = backend.plan_describe(self.lib, plan.program, plan.out_type, plan.obs_recs,
                                      plan.obs_pool, plan.precision)
-        if text.startswith(("strategy 3", "strategy 4")):
+        if text.startswith(("strategy 3", "strategy 4", "strategy 5")):
             st = emulate(plan.program, text, args, batch)
             self.frame_runs += 1
             self.steps.append(text)

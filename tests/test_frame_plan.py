@@ -49,7 +49,8 @@ NOISE = {"Depolarizing": 0.01, "AmplitudeDamping": 0.02}
     (4, 1, "Circuit_6", "probs", {"BitFlip": 0.1, "MultiQubitDepolarizing": 0.05}),  # 16x16
     (6, 1, "Circuit_9", "expval", None),              # H + CZ: diagonal ops on parity rows
 ])
-def test_single_cta_schedules(lib, n, L, ct, typ, noise):
+def test_single_cta_schedules(lib, monkeypatch, n, L, ct, typ, noise):
+    monkeypatch.setenv("QMLB_PTM", "0")  # the complex engine; strategy 5 has its own tests
     ex, err = _both(lib, n, L, ct, typ, noise)
     assert ex.frame_runs == 1, "planner did not choose the frame engine"
     assert err < 1e-12
@@ -61,9 +62,10 @@ def test_single_cta_schedules(lib, n, L, ct, typ, noise):
     (14, 1, "Hardware_Efficient", "expval", None, "complex128"),
     (15, 1, "Circuit_19", "probs", None, "complex64"),
 ])
-def test_cluster_schedules(lib, n, L, ct, typ, noise, precision):
+def test_cluster_schedules(lib, monkeypatch, n, L, ct, typ, noise, precision):
     """States beyond one CTA's shared memory: outer (cluster-rank) bits, relayouts through
     distributed shared memory, CX folded with an outer control."""
+    monkeypatch.setenv("QMLB_PTM", "0")
     ex, err = _both(lib, n, L, ct, typ, noise, precision, B_I=1, B_P=1)
     assert ex.frame_runs == 1
     geo, steps = fe.parse(ex.steps[0])
@@ -72,10 +74,12 @@ def test_cluster_schedules(lib, n, L, ct, typ, noise, precision):
     assert err < (1e-12 if precision == "complex128" else 1e-9)
 
 
-def test_config4_schedule_shape(lib):
-    """BASELINE config 4 (8 qubits, 4 layers, depolarizing + amplitude damping): 472 tape
+def test_config4_schedule_shape(lib, monkeypatch):
+    """BASELINE config 4 (8 qubits, 4 layers, depolarizing + amplitude damping) in the COMPLEX
+    engine (density output; <Z> / probs go through strategy 5): 472 tape
     ops -> at most 100 sub-passes and 12 coalesced cluster exchanges (each preceded by a
     tile-local shuffle); every CX is folded (no permutation op reaches the kernel)."""
+    monkeypatch.setenv("QMLB_PTM", "0")
     ex, err = _both(lib, 8, 4, "Strongly_Entangling", "expval", NOISE, B_I=1, B_P=1)
     geo, steps = fe.parse(ex.steps[0])
     assert (geo["tile_bits"], geo["outer_bits"], geo["threads"]) == (13, 3, 256)
@@ -127,3 +131,38 @@ def test_config5_pass_count(lib):
     assert len(geo["passes"]) <= 20
     assert all(s[5] >= 64 for s in steps if s[0] == "subpass")
     assert all(s[2] for s in steps if s[0] == "relayout")
+
+
+@pytest.mark.parametrize("n,L,ct,typ,noise", [
+    (3, 2, "Strongly_Entangling", "expval", NOISE),
+    (4, 2, "Hardware_Efficient", "probs", NOISE),
+    (5, 1, "Circuit_15", "expval", {"BitFlip": 0.05, "PhaseDamping": 0.1}),
+    (4, 1, "Circuit_6", "expval", {"PhaseFlip": 0.1, "ThermalRelaxation": None}),
+    (8, 1, "Strongly_Entangling", "probs", NOISE),
+])
+def test_pauli_basis_schedules(lib, n, L, ct, typ, noise):
+    """Strategy 5: noisy density programs made of 1-qubit (ket, bra) ops and CX pairs evolve
+    as the REAL Pauli-coefficient vector - transfer matrices T S T^-1, the CX as a folded
+    linear map on the (x, z) bits times the Aaronson-Gottesman sign.  The emulation converts
+    the final coefficients back to rho and compares with the interpreter's complex
+    evolution."""
+    noise = {k: v for k, v in noise.items() if v is not None}
+    ex, err = _both(lib, n, L, ct, typ, noise, B_I=2 if n < 8 else 1, B_P=2 if n < 8 else 1)
+    assert ex.frame_runs == 1
+    geo, steps = fe.parse(ex.steps[0])
+    if ct == "Circuit_6":  # controlled rotations: not a Clifford + 1-qubit program
+        assert not geo.get("ptm")
+    else:
+        assert ex.steps[0].startswith("strategy 5") and geo["ptm"] == 1
+        assert any(o["code"] == fe.FOP_SIGN for s in steps if s[0] == "subpass" for o in s[4])
+    assert err < 1e-12
+
+
+def test_config4_pauli_basis_shape(lib):
+    """BASELINE config 4 with <Z> output: 512 KiB of real coefficients per evaluation -> a
+    cluster of 4 CTAs (the complex form needs 8), 1024 threads with one item each."""
+    ex, err = _both(lib, 8, 4, "Strongly_Entangling", "expval", NOISE, B_I=1, B_P=1)
+    geo, steps = fe.parse(ex.steps[0])
+    assert (geo["ptm"], geo["tile_bits"], geo["outer_bits"], geo["threads"]) == (1, 14, 2, 1024)
+    assert sum(1 for s in steps if s[0] == "relayout" and not s[2]) <= 10
+    assert err < 1e-12

@@ -79,22 +79,51 @@ def test_frame_equals_streamed_strategy(monkeypatch):
         a, _ = run(n, L, ct, typ, noise, 2)
         rng.bit_generator.state = state
         monkeypatch.setenv("QMLB_FRAME", "0")
+        monkeypatch.setenv("QMLB_PTM", "0")
         b, _ = run(n, L, ct, typ, noise, 2)
         monkeypatch.delenv("QMLB_FRAME")
+        monkeypatch.delenv("QMLB_PTM")
         assert np.abs(a - b).max() < 1e-10, (n, ct)
 
 
 def test_frame_engine_is_selected():
-    """Config 3 / config 4 programs are planned as strategy 3 on the device."""
+    """Config 3 is planned as strategy 3 on the device; config 4 as strategy 5 (Pauli basis)
+    for <Z> / probabilities and as strategy 3 when the density matrix itself is asked for."""
     ex = get_executor()
     from qml_essentials_b200 import backend
     import test_cabi
 
-    for n, L, ct, noise in ((6, 3, "Circuit_15", None), (8, 4, "Strongly_Entangling", NOISE)):
-        plan = test_cabi._plan_of(n, L, ct, "complex128", "expval", noise)
+    for n, L, ct, typ, noise, want in ((6, 3, "Circuit_15", "expval", None, 3),
+                                       (8, 4, "Strongly_Entangling", "expval", NOISE, 5),
+                                       (8, 4, "Strongly_Entangling", "probs", NOISE, 5),
+                                       (8, 4, "Strongly_Entangling", "density", NOISE, 3)):
+        plan = test_cabi._plan_of(n, L, ct, "complex128", typ, noise)
         h = backend.ProgramHandle(ex.lib, plan.program, plan.out_type, plan.obs_recs,
                                   plan.obs_pool, "complex128")
-        assert h.strategy == 3
+        assert h.strategy == want, (ct, typ)
+
+
+@pytest.mark.parametrize("precision", ["complex128", "complex64"])
+@pytest.mark.parametrize("n,L,typ,B_I,B_P", [
+    (8, 4, "expval", 3, 2), (8, 2, "probs", 2, 2), (7, 2, "expval", 5, 3), (5, 3, "probs", 9, 4),
+    (3, 2, "expval", 17, 5), (2, 2, "probs", 4, 4),
+])
+def test_pauli_basis_equals_complex_engine(monkeypatch, precision, n, L, typ, B_I, B_P):
+    """Strategy 5 (real Pauli coefficients, CX folded + sign op) against the complex (ket,
+    bra) evolution of strategy 3 on the same noisy circuits - two independent algorithms."""
+    rng = np.random.default_rng(11)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        m = Model(n, L, "Strongly_Entangling", precision=precision)
+        params = rng.uniform(0, 2 * np.pi, (B_P, *m._params_shape))
+        inputs = rng.uniform(-1, 1, (B_I, 1))
+        noise = {"Depolarizing": 0.01, "AmplitudeDamping": 0.02, "PhaseFlip": 0.03}
+        call = lambda: np.asarray(m(params=params, inputs=inputs, execution_type=typ,
+                                    noise_params=dict(noise)))
+        a = call()
+        monkeypatch.setenv("QMLB_PTM", "0")
+        b = call()
+    assert np.abs(a - b).max() < (1e-11 if precision == "complex128" else 2e-6)
 
 
 @pytest.mark.parametrize("precision", ["complex128", "complex64"])
