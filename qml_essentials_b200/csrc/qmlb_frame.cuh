@@ -409,7 +409,9 @@ __device__ __forceinline__ void frame_subpass(cx<T>* tile, const cx<T>* mats, co
 
 // RELAYOUT gather: destination d of this thread <- source (rank, index) through the GF(2)
 // map; PER amplitudes per thread held in registers across the cluster barrier
-template <typename V, int PER, typename Cluster>
+// NB > 0: the tile is swizzled (qmlb_frame_ptm.cuh) - the tables then hold swizzled source
+// indices and the destination index is swizzled here
+template <typename V, int PER, int NB = 0, typename Cluster>
 __device__ __forceinline__ void frame_relayout_v(V* tv, Cluster& cluster, bool clustered,
                                                  unsigned rank, int Tb, int team_bits, int tlane,
                                                  uint32_t cmine, const uint32_t* tab_lo,
@@ -430,7 +432,12 @@ __device__ __forceinline__ void frame_relayout_v(V* tv, Cluster& cluster, bool c
   else
     __syncthreads();
 #pragma unroll
-  for (int k = 0; k < PER; ++k) tv[(uint32_t)tlane + ((uint32_t)k << team_bits)] = hold[k];
+  for (int k = 0; k < PER; ++k) {
+    uint32_t d = (uint32_t)tlane + ((uint32_t)k << team_bits);
+    if constexpr (NB > 0)
+      d ^= ((d >> NB) ^ (d >> (2 * NB)) ^ (d >> (3 * NB))) & ((1u << NB) - 1u);
+    tv[d] = hold[k];
+  }
 }
 
 template <typename T, int PER, typename Cluster>

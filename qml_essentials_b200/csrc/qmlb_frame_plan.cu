@@ -203,6 +203,8 @@ struct Builder {
   int mat_cap;
   bool resident = false;   // matrices of the whole element stay in shared memory
   bool ptm = false;        // Pauli-basis engine: real state, 4x4 transfer matrices
+  int swz_bits = 0;        // log2(elements per shared-memory wavefront) of the swizzled tile
+  int team_bits = 0;       // log2(threads per tile): item bits above belong to one thread
   std::vector<char> ptm_diag;  // per op: its transfer matrix is provably diagonal
   uint64_t init_xmask = 0;     // physical positions that hold x bits in the initial frame
   std::vector<FrameStep> steps;
@@ -404,7 +406,7 @@ bool Builder::build_step() {
           par_try.push_back(o.bits[a]);
       ok = FRAME_R + (int)par_try.size() <= FRAME_MAX_PAR;
     }
-    const int need_slots = (o.kind == QMLB_OP_DIAG || o.kind == QMLB_OP_SIGN) ? 2 : 1;
+    const int need_slots = o.kind == QMLB_OP_SIGN ? 4 : (o.kind == QMLB_OP_DIAG ? 2 : 1);
     const int e = resident ? 0 : f.entries;
     if (ok) ok = slots + need_slots <= FRAME_MAX_OPS && entries + e <= mat_cap;
     if (!ok) {
@@ -551,23 +553,94 @@ bool Builder::build_step() {
       } else if (o.kind == QMLB_OP_SIGN) {
         fo.code = QMLB_FOP_SIGN;
         fo.premat_off = o.aux;  // the sign mask
+        uint8_t pi4[4];
+        uint32_t ro = 0;
+        for (int a = 0; a < 4; ++a) {
+          pi4[a] = (uint8_t)par_index(o.bits[a]);
+          ro |= (s.par[pi4[a]].rout & 255u) << (8 * a);
+        }
+        fo.j0 = pi4[0], fo.j1 = pi4[1], fo.shape = pi4[2], fo.has_c = pi4[3];
+        fo.smem_off = (int32_t)ro;
       } else {
         fo.code = QMLB_FOP_DIAG;
       }
       used += info[i].entries;
       s.ops[slot++] = fo;
-      if (o.kind == QMLB_OP_DIAG || o.kind == QMLB_OP_SIGN) {
+      if (o.kind == QMLB_OP_DIAG) {
         FrameOp aux;
         std::memset(&aux, 0, sizeof(aux));
         uint8_t* idx = reinterpret_cast<uint8_t*>(&aux);
         for (int a = 0; a < o.k; ++a) idx[a] = (uint8_t)par_index(o.bits[a]);
         s.ops[slot++] = aux;
       }
+      if (o.kind == QMLB_OP_SIGN) {
+        {
+          const uint8_t idx[4] = {fo.j0, fo.j1, fo.shape, fo.has_c};
+          uint32_t rl4[4];
+          for (int a = 0; a < 4; ++a) rl4[a] = s.par[idx[a]].rloc;
+          std::memcpy(&s.ops[slot++], rl4, sizeof(rl4));
+          // sign words: entry lb = local value (first op bit most significant) read at slot
+          // 0 of an item; bit v = sign of slot v, whose local value is lb ^ flip(v)
+          uint16_t tab[16];
+          for (int lb = 0; lb < 16; ++lb) {
+            unsigned w = 0;
+            for (int v = 0; v < FRAME_D; ++v) {
+              int loc = lb;
+              for (int a = 0; a < o.k; ++a)
+                loc ^= (int)((s.par[idx[a]].smask >> v) & 1u) << (o.k - 1 - a);
+              w |= (((unsigned)o.aux >> loc) & 1u) << v;
+            }
+            tab[lb] = (uint16_t)w;
+          }
+          std::memcpy(&s.ops[slot], tab, sizeof(tab));
+          slot += 2;
+        }
+      }
       ops_of_step.push_back(i);
       done[i] = 1;
     }
     s.n_ops = slot;
     s.mat_entries = used;
+    // item bit -> tile position (FrameSubX).  The address of item `it` is linear in its
+    // bits: position q contributes Lq = (1 << q) ^ eoff[c_q] (c_q = the item shift its
+    // parities cause).  In the swizzled tile the bank of an address is the XOR of its
+    // swz_bits-wide digits, so the lanes of one wavefront hit distinct banks iff the bank
+    // vectors of the lowest swz_bits item bits are independent: pick them greedily.
+    {
+      FrameSubX* sx = reinterpret_cast<FrameSubX*>(s.qcol);
+      auto addr_of = [&](int q) {
+        int c = 0;
+        for (int j = 0; j < FRAME_R; ++j) c |= (int)((s.par[j].rloc >> q) & 1u) << j;
+        return (uint32_t)(1u << q) ^ s.eoff[c];
+      };
+      std::vector<int> free_pos;
+      for (int q = 0; q < T; ++q)
+        if (!(pivmask >> q & 1)) free_pos.push_back(q);
+      std::vector<int> lanes;
+      if (swz_bits > 0) {
+        const uint32_t dm = (1u << swz_bits) - 1u;
+        std::vector<uint32_t> basis;
+        for (int q : free_pos) {
+          if ((int)lanes.size() == swz_bits) break;
+          uint32_t w = 0;
+          for (uint32_t h = addr_of(q); h; h >>= swz_bits) w ^= h & dm;
+          for (uint32_t b : basis)
+            if ((w ^ b) < w) w ^= b;
+          if (!w) continue;
+          basis.push_back(w);
+          std::sort(basis.rbegin(), basis.rend());
+          lanes.push_back(q);
+        }
+        sx->lanes_ok = (int)lanes.size() == std::min(swz_bits, (int)free_pos.size()) ? 1u : 0u;
+      }
+      std::vector<int> order(lanes);
+      for (int q : free_pos)
+        if (std::find(lanes.begin(), lanes.end(), q) == lanes.end()) order.push_back(q);
+      for (size_t b = 0; b < order.size() && b < 16; ++b) sx->ipos[b] = (uint8_t)order[b];
+      for (int b = 0; b < 4; ++b)
+        if (team_bits > 0 && team_bits + b < (int)order.size())
+          sx->kd[b] = addr_of(order[team_bits + b]);
+    }
     // fast-path classification (see FrameStep::fast)
     {
       bool d2 = true, m1 = true, all_real = true;
@@ -1089,7 +1162,13 @@ int plan_frame_ptm(qmlb_program* p) {
   B.T = N - B.G;
   int threads, team_bits, teams;
   if (B.T - FRAME_R >= 8) {
-    team_bits = std::min(10, B.T - FRAME_R);
+    // 512 threads with two (complex128) or four (complex64) items each: 128 registers per
+    // thread hold an item, its addresses and a transfer matrix without spills
+    const char* tb = std::getenv("QMLB_PTM_TEAM_BITS");
+    const int cap = tb ? std::max(8, std::min(10, std::atoi(tb))) : 9;
+    team_bits = std::min(cap, B.T - FRAME_R);
+    // a relayout holds 2^(T - team_bits) elements per thread in registers: at most 32 doubles
+    if (p->dtype == QMLB_C128) team_bits = std::max(team_bits, B.T - 5);
     threads = 1 << team_bits;
     teams = 1;
   } else {
@@ -1097,6 +1176,8 @@ int plan_frame_ptm(qmlb_program* p) {
     team_bits = B.T - FRAME_R;
     teams = threads >> team_bits;
   }
+  B.swz_bits = p->dtype == QMLB_C128 ? 4 : 5;  // 128-byte wavefront / element size
+  B.team_bits = team_bits;
   int row = 0;
   B.premat_off.assign(q.ops.size(), 0);
   B.matlist_index.assign(q.ops.size(), -1);
@@ -1184,7 +1265,15 @@ std::string describe_frame(const qmlb_program* p) {
       s += "\n";
       continue;
     }
-    s += "subpass fast " + std::to_string(st.fast) + " pivots";
+    s += "subpass fast " + std::to_string(st.fast);
+    {
+      const FrameSubX* sx = reinterpret_cast<const FrameSubX*>(st.qcol);
+      s += " lanes_ok " + std::to_string(sx->lanes_ok) + " ipos";
+      for (int b = 0; b < fp.tile_bits - FRAME_R && b < 16; ++b) s += " " + std::to_string(sx->ipos[b]);
+      s += " kd";
+      for (int b = 0; b < 4; ++b) s += " " + std::to_string(sx->kd[b]);
+    }
+    s += " pivots";
     for (int j = 0; j < FRAME_R; ++j) s += " " + std::to_string(st.pivots[j]);
     s += " eoff";
     for (int v = 0; v < FRAME_D; ++v) s += " " + std::to_string(st.eoff[v]);
@@ -1201,11 +1290,19 @@ std::string describe_frame(const qmlb_program* p) {
            std::to_string(fo.has_c) + ":" + std::to_string(fo.flags) + ":" +
            std::to_string(fo.premat_off) + ":" + std::to_string(fo.smem_off) + ":" +
            std::to_string(fo.shape);
-      if (fo.code == QMLB_FOP_DIAG || fo.code == QMLB_FOP_SIGN) {
+      if (fo.code == QMLB_FOP_DIAG) {
         const uint8_t* idx = reinterpret_cast<const uint8_t*>(&st.ops[o + 1]);
         s += ":";
         for (int a = 0; a < fo.k; ++a) s += (a ? "," : "") + std::to_string(idx[a]);
         ++o;
+      } else if (fo.code == QMLB_FOP_SIGN) {
+        const uint8_t idx[4] = {fo.j0, fo.j1, fo.shape, fo.has_c};
+        s += ":";
+        for (int a = 0; a < 4; ++a) s += (a ? "," : "") + std::to_string(idx[a]);
+        const uint16_t* tab = reinterpret_cast<const uint16_t*>(&st.ops[o + 2]);
+        s += ":";
+        for (int a = 0; a < 16; ++a) s += (a ? "," : "") + std::to_string(tab[a]);
+        o += 3;
       }
     }
     s += "\n";

@@ -44,8 +44,31 @@ __device__ __forceinline__ void ptm_mat2(T (&S)[FRAME_D], const T* __restrict__ 
   }
 }
 
-template <typename T, int THREADS>
-__global__ void __launch_bounds__(THREADS, THREADS >= 512 ? 1 : 2)
+// Swizzled tile: element i of a tile lives at i ^ (XOR of the higher NB-bit digits of i, taken
+// on its lowest digit) - a GF(2)-linear involution, so swz(a ^ b) = swz(a) ^ swz(b) and the
+// bank of an address is the XOR of ALL its digits.  NB = log2(elements per 128-byte
+// wavefront): 4 for doubles, 5 for floats.  Aligned runs of 2^NB elements stay runs.
+template <int NB>
+__device__ __forceinline__ uint32_t ptm_swz(uint32_t i) {
+  return i ^ (((i >> NB) ^ (i >> (2 * NB)) ^ (i >> (3 * NB))) & ((1u << NB) - 1u));
+}
+
+// negate the slots whose bit is set in w (a flip of the IEEE sign bit, no FP pipe)
+template <typename T>
+__device__ __forceinline__ void ptm_sign(T (&S)[FRAME_D], unsigned w) {
+#pragma unroll
+  for (int v = 0; v < FRAME_D; ++v) {
+    const unsigned sb = (w << (31 - v)) & 0x80000000u;
+    if constexpr (sizeof(T) == 8)
+      S[v] = __hiloint2double(__double2hiint(S[v]) ^ (int)sb, __double2loint(S[v]));
+    else
+      S[v] = __int_as_float(__float_as_int(S[v]) ^ (int)sb);
+  }
+}
+
+// MINB = 1: one CTA per SM (the tile fills its shared memory anyway), up to 255 registers
+template <typename T, int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB)
     k_frame_ptm(DevProg P, RunArgs A, const FrameProg F, const uint64_t xmask,
                 const cx<T>* __restrict__ premats, void* __restrict__ out) {
   extern __shared__ __align__(16) unsigned char fsm[];
@@ -78,8 +101,10 @@ __global__ void __launch_bounds__(THREADS, THREADS >= 512 ? 1 : 2)
   };
   const int64_t per_round = n_clusters * teams;
   const int64_t rounds = (A.batch + per_round - 1) / per_round;
-  const uint32_t n_items = 1u << (Tb - FRAME_R);
+  const int per_thread = 1 << (Tb - FRAME_R - F.team_bits);  // items of one thread
   const int nq = F.n_qubits;
+  constexpr int NB = sizeof(T) == 8 ? 4 : 5;
+  const uint32_t tile_mask = tile_n - 1u;
 
   for (int64_t rd = 0; rd < rounds; ++rd) {
     const int64_t bl = rd * per_round + cluster_id * teams + team;
@@ -88,7 +113,7 @@ __global__ void __launch_bounds__(THREADS, THREADS >= 512 ? 1 : 2)
 
     // |0..0><0..0| = 2^-n prod_q (I + Z_q): coefficient 1 wherever every x bit is 0
     for (uint32_t i = tlane; i < tile_n; i += tsize) {
-      const uint64_t full = ((uint64_t)rank << Tb) | i;
+      const uint64_t full = ((uint64_t)rank << Tb) | ptm_swz<NB>(i);
       tile[i] = (full & xmask) ? (T)0 : (T)1;
     }
     {
@@ -112,17 +137,18 @@ __global__ void __launch_bounds__(THREADS, THREADS >= 512 ? 1 : 2)
           if (i < 256) {
             for (int b = 0; b < 8; ++b)
               if (i >> b & 1) acc ^= (uint32_t)st.qcol[b];
-            tab_lo[i] = acc;
+            tab_lo[i] = (acc & ~tile_mask) | ptm_swz<NB>(acc & tile_mask);
           } else {
             const int h = i - 256;
             for (int b = 0; b < 7; ++b)
               if ((h >> b & 1) && 8 + b < Tb) acc ^= (uint32_t)st.qcol[8 + b];
-            tab_hi[h] = acc;
+            tab_hi[h] = (acc & ~tile_mask) | ptm_swz<NB>(acc & tile_mask);
           }
         }
         uint32_t cmine = 0;
         for (int g = 0; g < F.outer_bits; ++g)
           if (rank >> g & 1) cmine ^= (uint32_t)st.qcol[Tb + g];
+        cmine = (cmine & ~tile_mask) | ptm_swz<NB>(cmine & tile_mask);
         const bool across = clustered && st.mat_entries == 0;
         if (across)
           cluster.sync();
@@ -130,68 +156,100 @@ __global__ void __launch_bounds__(THREADS, THREADS >= 512 ? 1 : 2)
           __syncthreads();
         const int per = (int)(tile_n >> F.team_bits);
         if (per == 16)
-          frame_relayout_v<T, 16>(tile, cluster, across, rank, Tb, F.team_bits, tlane, cmine,
-                                  tab_lo, tab_hi);
+          frame_relayout_v<T, 16, NB>(tile, cluster, across, rank, Tb, F.team_bits, tlane,
+                                      cmine, tab_lo, tab_hi);
         else if (per == 32)
-          frame_relayout_v<T, 32>(tile, cluster, across, rank, Tb, F.team_bits, tlane, cmine,
-                                  tab_lo, tab_hi);
+          frame_relayout_v<T, 32, NB>(tile, cluster, across, rank, Tb, F.team_bits, tlane,
+                                      cmine, tab_lo, tab_hi);
+        else if (sizeof(T) == 4 && per == 64)  // floats only: 64 doubles do not fit the registers
+          frame_relayout_v<T, sizeof(T) == 4 ? 64 : 16, NB>(tile, cluster, across, rank, Tb, F.team_bits, tlane,
+                                      cmine, tab_lo, tab_hi);
         __syncthreads();
         continue;
       }
 
       if (valid) {
-        uint32_t piv[FRAME_R];
+        // per-step constants in registers: the parity rows of the register bits, the four
+        // basis offsets of the group (swizzled), the thread's first item
+        const FrameSubX* sx = reinterpret_cast<const FrameSubX*>(st.qcol);
+        uint32_t eb[FRAME_R], seb[FRAME_R];
+        uint32_t base0 = 0;
+        for (int b = 0; b < F.team_bits; ++b) base0 |= (((uint32_t)tlane >> b) & 1u) << sx->ipos[b];
+        {
+          int c = 0;
 #pragma unroll
-        for (int j = 0; j < FRAME_R; ++j) piv[j] = st.pivots[j];
-        for (uint32_t it = tlane; it < n_items; it += tsize) {
-          const uint32_t base = frame_item_base(st, it, piv, rank);
+          for (int j = 0; j < FRAME_R; ++j) {
+            const FramePar pr = st.par[j];
+            eb[j] = st.eoff[1 << j];
+            seb[j] = ptm_swz<NB>(eb[j]);
+            c |= ((__popc(base0 & pr.rloc) ^ __popc(rank & pr.rout)) & 1) << j;
+          }
+#pragma unroll
+          for (int j = 0; j < FRAME_R; ++j)
+            if (c >> j & 1) base0 ^= eb[j];  // slot v then holds logical value v
+        }
+        const int n_ops = st.n_ops;
+#pragma unroll 1
+        for (int k = 0; k < per_thread; ++k) {
+          uint32_t base = base0;  // item k of this thread: address linear in the item bits
+          for (int b = 0; (k >> b) != 0; ++b)
+            if (k >> b & 1) base ^= sx->kd[b];
+          uint32_t ad[FRAME_D];
+          ad[0] = ptm_swz<NB>(base);
+#pragma unroll
+          for (int v = 1; v < FRAME_D; ++v) {
+            const int j = 31 - __builtin_clz(v);
+            ad[v] = ad[v ^ (1 << j)] ^ seb[j];
+          }
           T S[FRAME_D];
 #pragma unroll
-          for (int v = 0; v < FRAME_D; ++v) S[v] = tile[base ^ st.eoff[v]];
+          for (int v = 0; v < FRAME_D; ++v) S[v] = tile[ad[v]];
 #pragma unroll 1
-          for (int o = 0; o < st.n_ops; ++o) {
+          for (int o = 0; o < n_ops; ++o) {
             const FrameOp fo = st.ops[o];
-            if (fo.code == QMLB_FOP_MAT2) {
-              const T* m = mats + 2 * fo.smem_off;  // smem_off counts complex slots
-              const bool dg = fo.shape == QMLB_FSHAPE_PDIAG;
-              auto on_pair = [&](auto JA, auto JB) {
-                constexpr int A_ = decltype(JA)::value, B_ = decltype(JB)::value;
-                if constexpr (A_ > B_) {
-                  if (dg)
-                    ptm_mat2<T, A_, B_, true>(S, m);
-                  else
-                    ptm_mat2<T, A_, B_, false>(S, m);
-                }
-              };
-              if (fo.j0 == 3 && fo.j1 == 2)
-                on_pair(std::integral_constant<int, 3>{}, std::integral_constant<int, 2>{});
-              else if (fo.j0 == 1 && fo.j1 == 0)
-                on_pair(std::integral_constant<int, 1>{}, std::integral_constant<int, 0>{});
-              else
-                dispatch2<T, FRAME_R>(fo.j0, fo.j1, on_pair);
-            } else if (fo.code == QMLB_FOP_SIGN) {
-              const uint8_t* idx = reinterpret_cast<const uint8_t*>(&st.ops[o + 1]);
-              const unsigned mask = (unsigned)fo.premat_off;
-              int lb = 0;
-              unsigned flip[4];
-#pragma unroll
-              for (int a = 0; a < 4; ++a) {
-                const FramePar pr = st.par[idx[a]];
-                lb |= ((__popc(base & pr.rloc) ^ __popc(rank & pr.rout)) & 1) << (3 - a);
-                flip[a] = pr.smask;
+            const T* m = mats + 2 * fo.smem_off;  // smem_off counts complex slots
+            int key = 5;
+            if (fo.code == QMLB_FOP_SIGN)
+              key = 4;
+            else if (fo.j0 == 1 && fo.j1 == 0)
+              key = fo.shape == QMLB_FSHAPE_PDIAG ? 1 : 0;
+            else if (fo.j0 == 3 && fo.j1 == 2)
+              key = fo.shape == QMLB_FSHAPE_PDIAG ? 3 : 2;
+            switch (key) {
+              case 0: ptm_mat2<T, 1, 0, false>(S, m); break;
+              case 1: ptm_mat2<T, 1, 0, true>(S, m); break;
+              case 2: ptm_mat2<T, 3, 2, false>(S, m); break;
+              case 3: ptm_mat2<T, 3, 2, true>(S, m); break;
+              case 4: {
+                // slot o+1: rloc of the four parity rows (their rout bytes in smem_off),
+                // o+2 / o+3: sign words by local value of slot 0 (bit v = sign of slot v)
+                const uint4 rl4 = *reinterpret_cast<const uint4*>(&st.ops[o + 1]);
+                const unsigned ro = (unsigned)fo.smem_off;
+                const int lb = ((__popc(base & rl4.x) ^ __popc(rank & (ro & 255u))) & 1) << 3 |
+                               ((__popc(base & rl4.y) ^ __popc(rank & ((ro >> 8) & 255u))) & 1) << 2 |
+                               ((__popc(base & rl4.z) ^ __popc(rank & ((ro >> 16) & 255u))) & 1) << 1 |
+                               ((__popc(base & rl4.w) ^ __popc(rank & (ro >> 24))) & 1);
+                const unsigned w = reinterpret_cast<const uint16_t*>(&st.ops[o + 2])[lb];
+                ptm_sign<T>(S, w);
+                o += 3;
+                break;
               }
-#pragma unroll
-              for (int v = 0; v < FRAME_D; ++v) {
-                int loc = lb;
-#pragma unroll
-                for (int a = 0; a < 4; ++a) loc ^= (int)((flip[a] >> v) & 1u) << (3 - a);
-                if ((mask >> loc) & 1u) S[v] = -S[v];
+              default: {
+                const bool dg = fo.shape == QMLB_FSHAPE_PDIAG;
+                dispatch2<T, FRAME_R>(fo.j0, fo.j1, [&](auto JA, auto JB) {
+                  constexpr int A_ = decltype(JA)::value, B_ = decltype(JB)::value;
+                  if constexpr (A_ > B_) {
+                    if (dg)
+                      ptm_mat2<T, A_, B_, true>(S, m);
+                    else
+                      ptm_mat2<T, A_, B_, false>(S, m);
+                  }
+                });
               }
-              ++o;
             }
           }
 #pragma unroll
-          for (int v = 0; v < FRAME_D; ++v) tile[base ^ st.eoff[v]] = S[v];
+          for (int v = 0; v < FRAME_D; ++v) tile[ad[v]] = S[v];
         }
       }
       __syncthreads();
@@ -202,14 +260,15 @@ __global__ void __launch_bounds__(THREADS, THREADS >= 512 ? 1 : 2)
       // <Z_S> = r at x = 0, z = S: index zmask < 2^n sits in the tile of cluster rank 0
       if (valid && rank == 0)
         for (int j = tlane; j < F.n_obs; j += tsize)
-          reinterpret_cast<T*>(out)[(size_t)bl * F.n_obs + j] = tile[(uint32_t)P.obs[j].zmask];
+          reinterpret_cast<T*>(out)[(size_t)bl * F.n_obs + j] =
+              tile[ptm_swz<NB>((uint32_t)P.obs[j].zmask)];
     } else if (F.out_mode == 1) {
       // p(b) = 2^-n sum_S (-1)^(b.S) r[S]: Walsh-Hadamard transform of the x = 0 coefficients
       // (the first 2^n entries of rank 0's tile), done in that CTA's scratch (teams == 1)
       if (rank == 0) {
         const uint32_t dim = 1u << nq;
         double* scratch = scratch_all + (size_t)team * dim;  // teams * 2^n <= 2048
-        for (uint32_t i = tlane; i < dim; i += tsize) scratch[i] = (double)tile[i];
+        for (uint32_t i = tlane; i < dim; i += tsize) scratch[i] = (double)tile[ptm_swz<NB>(i)];
         __syncthreads();
         for (int b = 0; b < nq; ++b) {
           for (uint32_t i = tlane; i < dim / 2; i += tsize) {

@@ -4,10 +4,10 @@
 
 namespace qmlb {
 
-template <int THREADS>
+template <int THREADS, int MINB>
 static cudaError_t launch_ptm_t(const qmlb_program* p, const RunArgs& R, const FrameProg& F,
                                 const cx<QMLB_T>* premats, void* out, cudaStream_t st) {
-  auto kern = k_frame_ptm<QMLB_T, THREADS>;
+  auto kern = k_frame_ptm<QMLB_T, THREADS, MINB>;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -56,12 +56,13 @@ cudaError_t QMLB_LAUNCH_FRAME_PTM(const qmlb_program* p, const RunArgs& R, const
   F.steps = p->frame_steps_dev;
   F.out_mode = out_mode;
   const cx<QMLB_T>* pm = static_cast<const cx<QMLB_T>*>(premats);
-  if (p->frame_threads == 1024) return launch_ptm_t<1024>(p, R, F, pm, out, st);
-  if (p->frame_threads == 512) return launch_ptm_t<512>(p, R, F, pm, out, st);
-  if (p->frame_threads == 256) return launch_ptm_t<256>(p, R, F, pm, out, st);
-  if (p->frame_threads == 128) return launch_ptm_t<128>(p, R, F, pm, out, st);
-  if (p->frame_threads == 64) return launch_ptm_t<64>(p, R, F, pm, out, st);
-  if (p->frame_threads == 32) return launch_ptm_t<32>(p, R, F, pm, out, st);
+  if (p->frame_threads == 1024) return launch_ptm_t<1024, 1>(p, R, F, pm, out, st);
+  if (p->frame_threads == 512) return launch_ptm_t<512, 1>(p, R, F, pm, out, st);
+  if (p->frame_threads == 256 && F.teams == 1) return launch_ptm_t<256, 1>(p, R, F, pm, out, st);
+  if (p->frame_threads == 256) return launch_ptm_t<256, 2>(p, R, F, pm, out, st);
+  if (p->frame_threads == 128) return launch_ptm_t<128, 2>(p, R, F, pm, out, st);
+  if (p->frame_threads == 64) return launch_ptm_t<64, 2>(p, R, F, pm, out, st);
+  if (p->frame_threads == 32) return launch_ptm_t<32, 2>(p, R, F, pm, out, st);
   return cudaErrorInvalidConfiguration;
 }
 

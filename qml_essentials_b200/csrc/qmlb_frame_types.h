@@ -41,8 +41,11 @@ constexpr int FRAME_MAX_BITS = 40;
 #define QMLB_FOP_MATK 2   // dense 2^k x 2^k on register bits k-1..0 (k = 3, 4)
 #define QMLB_FOP_CTRL1 3  // 2x2 on register bit j0 where parity row j1 reads 1
 #define QMLB_FOP_DIAG 4   // diagonal over k parity rows (their indices sit in the next slot)
-#define QMLB_FOP_SIGN 5   // +-1 over k parity rows: negate where bit (local value) of the mask in
-                          // premat_off is set (Pauli-basis engine: the sign part of a Clifford)
+#define QMLB_FOP_SIGN 5   // +-1 over 4 parity rows: negate where bit (local value) of the mask in
+                          // premat_off is set (Pauli-basis engine: the sign part of a Clifford).
+                          // Four slots: the op (j0, j1, shape, has_c = the parity-row indices,
+                          // smem_off = their four rout bytes), the four rloc words, and 16 sign
+                          // words (entry = local value at slot 0, bit v = sign of slot v)
 
 #define QMLB_OP_SIGN 4    // planner-internal op kind behind QMLB_FOP_SIGN (never in a user program)
 
@@ -88,6 +91,18 @@ struct FrameStep {  // 1024 bytes, loaded into shared memory by the CTA that run
   uint32_t eoffb_unused[3];
 };
 static_assert(sizeof(FrameStep) == 1024, "FrameStep is loaded as 256 words");
+
+// SUBPASS extras, stored over the qcol area (which only a RELAYOUT reads).  Item number ->
+// tile index: item bit b sits at tile position ipos[b].  The planner picks the lowest item
+// bits (the lanes of one shared-memory wavefront) so that the lanes land in distinct banks
+// of the SWIZZLED tile (qmlb_frame_ptm.cuh); kd[b] = address delta of item bit team_bits + b
+// (a thread's further items), the item shift eoff[c] included.
+struct FrameSubX {
+  uint8_t ipos[16];
+  uint32_t kd[4];
+  uint32_t lanes_ok;  // 1: the lane bits are conflict-free
+};
+static_assert(sizeof(FrameSubX) <= sizeof(uint64_t) * FRAME_MAX_BITS, "fits the qcol area");
 
 struct FrameProg {
   const FrameStep* steps;

@@ -27,6 +27,7 @@ def parse(text):
     assert lines[0] in ("strategy 3", "strategy 4", "strategy 5"), lines[0]
     geo = {"passes": []}
     steps = []
+    lanes = []
     for line in lines[1:]:
         tok = line.split()
         if tok[0] == "frame":
@@ -57,9 +58,66 @@ def parse(text):
             rec = dict(zip(("index", "code", "k", "j0", "j1", "has_c", "flags", "premat_off",
                             "smem_off", "shape"), (int(x) for x in f[:10])))
             rec["idx"] = [int(x) for x in f[10].split(",")] if len(f) > 10 else []
+            rec["table"] = [int(x) for x in f[11].split(",")] if len(f) > 11 else []
             ops.append(rec)
         steps.append(("subpass", piv, eoff, par, ops, int(tok[tok.index("fast") + 1])))
+        if "ipos" in tok:
+            ii, ik = tok.index("ipos"), tok.index("kd")
+            lanes.append(dict(ok=int(tok[tok.index("lanes_ok") + 1]),
+                              ipos=[int(x) for x in tok[ii + 1:ik]],
+                              kd=[int(x) for x in tok[ik + 1:ip]], piv=piv, eoff=eoff, par=par))
+    geo["lanes"] = lanes
     return geo, steps
+
+
+def check_item_maps(geo):
+    """FrameSubX of every sub-pass: ipos is a bijection of the item bits onto the non-pivot
+    tile positions and kd[b] is the address delta of item bit team_bits + b."""
+    T, tb = geo["tile_bits"], geo["team_bits"]
+    for ln in geo["lanes"]:
+        free = [q for q in range(T) if q not in ln["piv"]]
+        assert sorted(ln["ipos"]) == free
+        for b in range(4):
+            want = 0
+            if tb + b < len(free):
+                want = item_address(ln, 1 << (tb + b))
+            assert ln["kd"][b] == want
+
+
+def item_address(ln, it):
+    """Tile index of slot 0 of item `it` (cluster rank 0): scatter of the item bits to ipos,
+    then the shift eoff[c] that makes slot v hold logical value v."""
+    base = 0
+    for b, q in enumerate(ln["ipos"]):
+        base |= ((it >> b) & 1) << q
+    c = 0
+    for j in range(R):
+        c |= (bin(base & ln["par"][j][0]).count("1") & 1) << j
+    return base ^ ln["eoff"][c]
+
+
+def smem_wavefronts(geo, elem_bytes):
+    """Shared-memory wavefronts of the tile loads of every sub-pass relative to the ideal,
+    in the swizzled tile of the Pauli-basis kernel (bank = XOR of the address digits)."""
+    nb = {8: 4, 4: 5}[elem_bytes]
+    lanes_per = 1 << nb
+    got = ideal = 0
+    for ln in geo["lanes"]:
+        for warp in range(2):
+            ads = [item_address(ln, warp * 32 + l) for l in range(32)]
+            for v in range(D):
+                for h in range(0, 32, lanes_per):
+                    banks = {}
+                    for a in ads[h:h + lanes_per]:
+                        a ^= ln["eoff"][v]
+                        bank, x = 0, a
+                        while x:
+                            bank ^= x & (lanes_per - 1)
+                            x >>= nb
+                        banks.setdefault(bank, set()).add(a)
+                    got += max(len(x) for x in banks.values())
+                    ideal += 1
+    return got / max(ideal, 1)
 
 
 def _check_fast(fast, ops):
@@ -270,13 +328,18 @@ def _run_steps(st, steps, T, G, N, matrix, batch, local_only=False):
                 elif code == FOP_SIGN:
                     out = S.copy()
                     mask = o["premat_off"]
+                    lb = np.zeros_like(base)  # local value at slot 0: indexes the sign words
+                    for a, pidx in enumerate(o["idx"]):
+                        lb |= par_at(pidx) << (k - 1 - a)
+                    words = np.asarray(o["table"])[lb]
                     for v in range(D):
                         loc = np.zeros_like(base)
                         for a, pidx in enumerate(o["idx"]):
                             bit = par_at(pidx) ^ ((par[pidx][2] >> v) & 1)
                             loc |= bit << (k - 1 - a)
-                        out[:, :, v] = np.where(((mask >> loc) & 1).astype(bool)[None, :],
-                                                -S[:, :, v], S[:, :, v])
+                        neg = (mask >> loc) & 1
+                        assert np.array_equal(neg, (words >> v) & 1), "planner's sign words"
+                        out[:, :, v] = np.where(neg.astype(bool)[None, :], -S[:, :, v], S[:, :, v])
                     S = out
                 elif code == FOP_DIAG:
                     out = S.copy()

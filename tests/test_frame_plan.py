@@ -160,9 +160,12 @@ def test_pauli_basis_schedules(lib, n, L, ct, typ, noise):
 
 def test_config4_pauli_basis_shape(lib):
     """BASELINE config 4 with <Z> output: 512 KiB of real coefficients per evaluation -> a
-    cluster of 4 CTAs (the complex form needs 8), 1024 threads with one item each."""
+    cluster of 4 CTAs (the complex form needs 8), 512 threads with two items each."""
     ex, err = _both(lib, 8, 4, "Strongly_Entangling", "expval", NOISE, B_I=1, B_P=1)
     geo, steps = fe.parse(ex.steps[0])
-    assert (geo["ptm"], geo["tile_bits"], geo["outer_bits"], geo["threads"]) == (1, 14, 2, 1024)
+    assert (geo["ptm"], geo["tile_bits"], geo["outer_bits"], geo["threads"]) == (1, 14, 2, 512)
+    # item maps of the swizzled tile: bijections, and (nearly) conflict-free wavefronts
+    fe.check_item_maps(geo)
+    assert fe.smem_wavefronts(geo, 8) < 1.05
     assert sum(1 for s in steps if s[0] == "relayout" and not s[2]) <= 10
     assert err < 1e-12
