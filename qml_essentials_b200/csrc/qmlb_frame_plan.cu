@@ -664,7 +664,40 @@ bool Builder::build_step() {
         }
       }
       if (ptm) {
-        s.fast = 0;  // the Pauli-basis kernel has its own item loop
+        // [<= 2 signs] A on (1,0) [<= 2 signs] B on (3,2); anything else -> op interpreter
+        FrameSubX* sx = reinterpret_cast<FrameSubX*>(s.qcol);
+        std::memset(sx->sg, 0xff, sizeof(sx->sg));
+        int a = 0, b = 0, stage = 0, ns[2] = {0, 0};
+        bool ok = true;
+        for (int o = 0; o < slot && ok; ++o) {
+          const FrameOp& fo = s.ops[o];
+          const int shp = fo.shape == QMLB_FSHAPE_PDIAG ? 2 : 1;
+          if (fo.code == QMLB_FOP_SIGN) {
+            if (stage < 2 && ns[stage] < 2)
+              sx->sg[2 * stage + ns[stage]++] = (uint8_t)o;
+            else
+              ok = false;
+            o += 3;
+          } else if (fo.code == QMLB_FOP_MAT2 && fo.j0 == 1 && fo.j1 == 0 && stage == 0) {
+            a = shp;
+            s.foff[0] = fo.smem_off;
+            stage = 1;
+          } else if (fo.code == QMLB_FOP_MAT2 && fo.j0 == 3 && fo.j1 == 2 && stage <= 1) {
+            b = shp;
+            s.foff[1] = fo.smem_off;
+            stage = 2;
+          } else {
+            ok = false;
+          }
+        }
+        // signs met before any matrix while A is absent belong in front of B
+        if (ok && a == 0 && ns[1] == 0) {
+          sx->sg[2] = sx->sg[0], sx->sg[3] = sx->sg[1];
+          sx->sg[0] = sx->sg[1] = 0xff;
+        } else if (ok && a == 0) {
+          ok = false;
+        }
+        s.fast = ok && (a || b) ? 128 + 3 * a + b : 0;
       } else if (d2 && slot > 0) {
         s.fast = 16 + 4 * (sA + 1) + (sB + 1);
       } else if (m1 && slot > 0) {
@@ -1272,6 +1305,8 @@ std::string describe_frame(const qmlb_program* p) {
       for (int b = 0; b < fp.tile_bits - FRAME_R && b < 16; ++b) s += " " + std::to_string(sx->ipos[b]);
       s += " kd";
       for (int b = 0; b < 4; ++b) s += " " + std::to_string(sx->kd[b]);
+      s += " sg";
+      for (int b = 0; b < 4; ++b) s += " " + std::to_string(sx->sg[b]);
     }
     s += " pivots";
     for (int j = 0; j < FRAME_R; ++j) s += " " + std::to_string(st.pivots[j]);

@@ -66,6 +66,67 @@ __device__ __forceinline__ void ptm_sign(T (&S)[FRAME_D], unsigned w) {
   }
 }
 
+// sign word of the SIGN op in slot o for the item that starts at tile index `base`: the
+// local value of the op's four parity rows at slot 0 selects one of 16 planner-made words
+__device__ __forceinline__ unsigned ptm_sign_word(const FrameStep& st, int o, uint32_t base,
+                                                  unsigned rank) {
+  const uint4 rl4 = *reinterpret_cast<const uint4*>(&st.ops[o + 1]);
+  const unsigned ro = (unsigned)st.ops[o].smem_off;
+  const int lb = ((__popc(base & rl4.x) ^ __popc(rank & (ro & 255u))) & 1) << 3 |
+                 ((__popc(base & rl4.y) ^ __popc(rank & ((ro >> 8) & 255u))) & 1) << 2 |
+                 ((__popc(base & rl4.z) ^ __popc(rank & ((ro >> 16) & 255u))) & 1) << 1 |
+                 ((__popc(base & rl4.w) ^ __popc(rank & (ro >> 24))) & 1);
+  return reinterpret_cast<const uint16_t*>(&st.ops[o + 2])[lb];
+}
+
+template <typename T, int NB>
+__device__ __forceinline__ void ptm_item_addresses(uint32_t base, const uint32_t (&seb)[FRAME_R],
+                                                   uint32_t (&ad)[FRAME_D]) {
+  ad[0] = ptm_swz<NB>(base);
+#pragma unroll
+  for (int v = 1; v < FRAME_D; ++v) {
+    const int j = 31 - __builtin_clz(v);
+    ad[v] = ad[v ^ (1 << j)] ^ seb[j];
+  }
+}
+
+// Straight-line item body of the common step shape (FrameStep::fast >= 128):
+// [signs] A on register pair (1,0) [signs] B on pair (3,2); SA, SB = 0 absent, 1 full, 2 diagonal
+template <typename T, int NB, int SA, int SB>
+__device__ __forceinline__ void ptm_items_fast(T* tile, const T* mats, const FrameStep& st,
+                                               const FrameSubX* sx, uint32_t base0,
+                                               const uint32_t (&seb)[FRAME_R], int per_thread,
+                                               unsigned rank) {
+  const T* ma = mats + 2 * st.foff[0];
+  const T* mb = mats + 2 * st.foff[1];
+  const int s0 = sx->sg[0], s1 = sx->sg[1], s2 = sx->sg[2], s3 = sx->sg[3];
+#pragma unroll 1
+  for (int k = 0; k < per_thread; ++k) {
+    uint32_t base = base0;
+    for (int b = 0; (k >> b) != 0; ++b)
+      if (k >> b & 1) base ^= sx->kd[b];
+    uint32_t ad[FRAME_D];
+    ptm_item_addresses<T, NB>(base, seb, ad);
+    T S[FRAME_D];
+#pragma unroll
+    for (int v = 0; v < FRAME_D; ++v) S[v] = tile[ad[v]];
+    if (s0 != 0xff) {
+      unsigned w = ptm_sign_word(st, s0, base, rank);
+      if (s1 != 0xff) w ^= ptm_sign_word(st, s1, base, rank);
+      ptm_sign<T>(S, w);
+    }
+    if constexpr (SA != 0) ptm_mat2<T, 1, 0, SA == 2>(S, ma);
+    if (s2 != 0xff) {
+      unsigned w = ptm_sign_word(st, s2, base, rank);
+      if (s3 != 0xff) w ^= ptm_sign_word(st, s3, base, rank);
+      ptm_sign<T>(S, w);
+    }
+    if constexpr (SB != 0) ptm_mat2<T, 3, 2, SB == 2>(S, mb);
+#pragma unroll
+    for (int v = 0; v < FRAME_D; ++v) tile[ad[v]] = S[v];
+  }
+}
+
 // MINB = 1: one CTA per SM (the tile fills its shared memory anyway), up to 255 registers
 template <typename T, int THREADS, int MINB>
 __global__ void __launch_bounds__(THREADS, MINB)
@@ -174,7 +235,14 @@ __global__ void __launch_bounds__(THREADS, MINB)
         const FrameSubX* sx = reinterpret_cast<const FrameSubX*>(st.qcol);
         uint32_t eb[FRAME_R], seb[FRAME_R];
         uint32_t base0 = 0;
-        for (int b = 0; b < F.team_bits; ++b) base0 |= (((uint32_t)tlane >> b) & 1u) << sx->ipos[b];
+        {
+          const uint4 ip4 = *reinterpret_cast<const uint4*>(sx->ipos);
+          const uint32_t ipw[4] = {ip4.x, ip4.y, ip4.z, ip4.w};
+#pragma unroll
+          for (int b = 0; b < 12; ++b)
+            if (b < F.team_bits)
+              base0 |= (((uint32_t)tlane >> b) & 1u) << ((ipw[b >> 2] >> (8 * (b & 3))) & 31u);
+        }
         {
           int c = 0;
 #pragma unroll
@@ -189,18 +257,24 @@ __global__ void __launch_bounds__(THREADS, MINB)
             if (c >> j & 1) base0 ^= eb[j];  // slot v then holds logical value v
         }
         const int n_ops = st.n_ops;
+        bool fast_done = true;
+        switch (st.fast) {
+#define QMLB_PTM_FAST(a, b)                                                                  \
+  case 128 + 3 * a + b:                                                                      \
+    ptm_items_fast<T, NB, a, b>(tile, mats, st, sx, base0, seb, per_thread, rank);           \
+    break;
+          QMLB_PTM_FAST(0, 1) QMLB_PTM_FAST(0, 2) QMLB_PTM_FAST(1, 0) QMLB_PTM_FAST(1, 1)
+          QMLB_PTM_FAST(1, 2) QMLB_PTM_FAST(2, 0) QMLB_PTM_FAST(2, 1) QMLB_PTM_FAST(2, 2)
+#undef QMLB_PTM_FAST
+          default: fast_done = false;
+        }
 #pragma unroll 1
-        for (int k = 0; k < per_thread; ++k) {
+        for (int k = 0; k < (fast_done ? 0 : per_thread); ++k) {
           uint32_t base = base0;  // item k of this thread: address linear in the item bits
           for (int b = 0; (k >> b) != 0; ++b)
             if (k >> b & 1) base ^= sx->kd[b];
           uint32_t ad[FRAME_D];
-          ad[0] = ptm_swz<NB>(base);
-#pragma unroll
-          for (int v = 1; v < FRAME_D; ++v) {
-            const int j = 31 - __builtin_clz(v);
-            ad[v] = ad[v ^ (1 << j)] ^ seb[j];
-          }
+          ptm_item_addresses<T, NB>(base, seb, ad);
           T S[FRAME_D];
 #pragma unroll
           for (int v = 0; v < FRAME_D; ++v) S[v] = tile[ad[v]];
@@ -221,15 +295,7 @@ __global__ void __launch_bounds__(THREADS, MINB)
               case 2: ptm_mat2<T, 3, 2, false>(S, m); break;
               case 3: ptm_mat2<T, 3, 2, true>(S, m); break;
               case 4: {
-                // slot o+1: rloc of the four parity rows (their rout bytes in smem_off),
-                // o+2 / o+3: sign words by local value of slot 0 (bit v = sign of slot v)
-                const uint4 rl4 = *reinterpret_cast<const uint4*>(&st.ops[o + 1]);
-                const unsigned ro = (unsigned)fo.smem_off;
-                const int lb = ((__popc(base & rl4.x) ^ __popc(rank & (ro & 255u))) & 1) << 3 |
-                               ((__popc(base & rl4.y) ^ __popc(rank & ((ro >> 8) & 255u))) & 1) << 2 |
-                               ((__popc(base & rl4.z) ^ __popc(rank & ((ro >> 16) & 255u))) & 1) << 1 |
-                               ((__popc(base & rl4.w) ^ __popc(rank & (ro >> 24))) & 1);
-                const unsigned w = reinterpret_cast<const uint16_t*>(&st.ops[o + 2])[lb];
+                const unsigned w = ptm_sign_word(st, o, base, rank);
                 ptm_sign<T>(S, w);
                 o += 3;
                 break;

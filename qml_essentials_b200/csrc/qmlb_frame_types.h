@@ -85,6 +85,9 @@ struct FrameStep {  // 1024 bytes, loaded into shared memory by the CTA that run
   //          matrix offsets
   //   fast = 64 + 16 * real + mask: only 2x2 ops, at most one per register bit (mask), all
   //          real (1) or treated as full (0); foff[j] = matrix offset of the op on bit j
+  //   fast = 128 + 3 * a + b (Pauli-basis engine): [signs] A [signs] B with A the transfer
+  //          matrix on pair (1,0), B the one on (3,2); a, b = 0 absent, 1 full, 2 diagonal;
+  //          foff[0] / foff[1] = their offsets, FrameSubX::sg = the sign slots
   //   fast = 0: generic interpreter
   int32_t fast;
   int32_t foff[4];
@@ -101,6 +104,10 @@ struct FrameSubX {
   uint8_t ipos[16];
   uint32_t kd[4];
   uint32_t lanes_ok;  // 1: the lane bits are conflict-free
+  // Pauli-basis fast path (FrameStep::fast >= 128): slots of the sign ops that run before the
+  // transfer matrix on register pair (1,0) (sg[0], sg[1]) and between it and the one on pair
+  // (3,2) (sg[2], sg[3]); 0xff = none
+  uint8_t sg[4];
 };
 static_assert(sizeof(FrameSubX) <= sizeof(uint64_t) * FRAME_MAX_BITS, "fits the qcol area");
 

@@ -62,10 +62,13 @@ def parse(text):
             ops.append(rec)
         steps.append(("subpass", piv, eoff, par, ops, int(tok[tok.index("fast") + 1])))
         if "ipos" in tok:
-            ii, ik = tok.index("ipos"), tok.index("kd")
+            ii, ik, isg = tok.index("ipos"), tok.index("kd"), tok.index("sg")
             lanes.append(dict(ok=int(tok[tok.index("lanes_ok") + 1]),
                               ipos=[int(x) for x in tok[ii + 1:ik]],
-                              kd=[int(x) for x in tok[ik + 1:ip]], piv=piv, eoff=eoff, par=par))
+                              kd=[int(x) for x in tok[ik + 1:isg]],
+                              sg=[int(x) for x in tok[isg + 1:ip]], piv=piv, eoff=eoff, par=par))
+            if steps[-1][5] >= 128:
+                _check_ptm_fast(steps[-1][5], ops, lanes[-1]["sg"])
     geo["lanes"] = lanes
     return geo, steps
 
@@ -120,8 +123,39 @@ def smem_wavefronts(geo, elem_bytes):
     return got / max(ideal, 1)
 
 
+def _check_ptm_fast(fast, ops, sg):
+    """Pauli-basis straight-line body: [signs sg[0:2]] A on (1,0) [signs sg[2:4]] B on (3,2)
+    must replay the ops of the step in their order."""
+    a, b = (fast - 128) // 3, (fast - 128) % 3
+    slot, seq = 0, []
+    for o in ops:
+        seq.append((slot, o))
+        slot += {FOP_SIGN: 4, FOP_DIAG: 2}.get(o["code"], 1)
+    want = []
+    by_slot = dict(seq)
+    for s_ in sg[:2]:
+        if s_ != 255:
+            want.append(by_slot[s_])
+    mats = [o for _, o in seq if o["code"] == FOP_MAT2]
+    A = [o for o in mats if (o["j0"], o["j1"]) == (1, 0)]
+    B = [o for o in mats if (o["j0"], o["j1"]) == (3, 2)]
+    assert len(A) == (a != 0) and len(B) == (b != 0) and len(mats) == len(A) + len(B)
+    want += A
+    for s_ in sg[2:]:
+        if s_ != 255:
+            want.append(by_slot[s_])
+    want += B
+    assert [id(o) for o in want] == [id(o) for _, o in seq], "fast body replays another order"
+    for o, code in ((A, a), (B, b)):
+        if o:
+            assert (o[0]["shape"] == 3) == (code == 2)
+    assert all(by_slot[s_]["code"] == FOP_SIGN for s_ in sg if s_ != 255)
+
+
 def _check_fast(fast, ops):
     """The kernel's straight-line item bodies must describe exactly the ops of the step."""
+    if fast >= 128:
+        return  # Pauli-basis body: _check_ptm_fast at parse time
     if fast >= 64:
         real, mask = (fast - 64) >> 4, (fast - 64) & 15
         assert all(o["code"] == FOP_MAT1 for o in ops)
@@ -134,7 +168,7 @@ def _check_fast(fast, ops):
         got = {(o["j0"], o["j1"]): o["shape"] for o in ops}
         assert got == {k: v for k, v in want.items() if v >= 0}
     else:
-        assert fast == 0
+        assert fast == 0 or fast >= 128  # the latter: _check_ptm_fast at parse time
 
 
 def _deposit(w, piv):
