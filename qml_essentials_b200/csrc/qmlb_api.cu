@@ -624,7 +624,8 @@ int plan(qmlb_program* p) {
     if (plan_frame_ptm(p) == QMLB_OK) {
       p->strategy = 5;
       p->direct_out = true;
-      p->frame_out_mode = p->out_type == QMLB_OUT_PROBS ? 1 : 2;
+      p->frame_out_mode =
+          p->out_type == QMLB_OUT_PROBS ? 1 : (p->out_type == QMLB_OUT_DENSITY ? 0 : 2);
       return QMLB_OK;
     }
     if (force == 5) return fail(QMLB_ERR_UNSUPPORTED, "program outside the Pauli-basis engine");

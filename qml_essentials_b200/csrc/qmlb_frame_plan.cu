@@ -1111,7 +1111,7 @@ static bool ptm_is_diagonal(const double S[32]) {
 int plan_frame_ptm(qmlb_program* p) {
   if (!p->density) return QMLB_ERR_UNSUPPORTED;
   const int n = p->n_qubits, N = p->n_bits;
-  if (!(p->out_type == QMLB_OUT_PROBS ||
+  if (!(p->out_type == QMLB_OUT_PROBS || p->out_type == QMLB_OUT_DENSITY ||
         (p->out_type == QMLB_OUT_EXPVAL &&
          std::all_of(p->obs.begin(), p->obs.end(),
                      [](const qmlb_obs& o) { return o.kind == QMLB_OBS_ZSTRING; }))))

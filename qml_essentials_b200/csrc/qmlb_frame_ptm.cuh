@@ -127,6 +127,58 @@ __device__ __forceinline__ void ptm_items_fast(T* tile, const T* mats, const Fra
   }
 }
 
+// Density matrix from the Pauli coefficients, one warp per row x (= ket ^ bra):
+//   rho[k' ^ x][k'] = 2^-n sum_z i^|x & z| (-1)^(z . k') r[x << n | z]
+// (<k|P|k'> of a Pauli string: X / Y move k' to k' ^ x, Z / Y give (-1)^k', Y an extra i).
+// The phase goes onto the loaded coefficient, then a Walsh-Hadamard transform over the n
+// bits of z: bits >= 5 inside a lane (2^NVL values each), bits < 5 with shuffles.
+template <typename T, int NB, int NVL>
+__device__ __forceinline__ void ptm_rho_rows(const T* tile, cx<T>* rho, int nq, int Tb,
+                                             unsigned rank, int tlane, int tsize, bool valid) {
+  constexpr int NV = 1 << NVL;
+  const int lane = tlane & 31, warp = tlane >> 5, nwarps = tsize >> 5;
+  const int xl_bits = Tb - nq, lb = nq - NVL;  // local x bits; z bits spread over the lanes
+  const uint32_t dim = 1u << nq;
+  const T inv = (T)1 / (T)dim;
+  for (uint32_t xl = warp; xl < (1u << xl_bits); xl += nwarps) {
+    const uint32_t x = (rank << xl_bits) | xl;
+    T re[NV], im[NV];
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      const uint32_t z = ((uint32_t)j << 5) | (uint32_t)lane;
+      const T v = z < dim ? tile[ptm_swz<NB>((xl << nq) | z)] : (T)0;
+      const int m = __popc(x & z) & 3;
+      re[j] = m == 0 ? v : (m == 2 ? -v : (T)0);
+      im[j] = m == 1 ? v : (m == 3 ? -v : (T)0);
+    }
+#pragma unroll
+    for (int b = 0; b < NVL; ++b)
+#pragma unroll
+      for (int j = 0; j < NV; ++j)
+        if (!(j >> b & 1)) {
+          const T ar = re[j], ai = im[j], br = re[j | (1 << b)], bi = im[j | (1 << b)];
+          re[j] = ar + br, im[j] = ai + bi;
+          re[j | (1 << b)] = ar - br, im[j | (1 << b)] = ai - bi;
+        }
+    for (int b = 0; b < lb; ++b) {
+      const bool up = lane >> b & 1;
+#pragma unroll
+      for (int j = 0; j < NV; ++j) {
+        const T pr = __shfl_xor_sync(0xffffffffu, re[j], 1 << b);
+        const T pi = __shfl_xor_sync(0xffffffffu, im[j], 1 << b);
+        re[j] = up ? pr - re[j] : re[j] + pr;
+        im[j] = up ? pi - im[j] : im[j] + pi;
+      }
+    }
+    if (valid)
+#pragma unroll
+      for (int j = 0; j < NV; ++j) {
+        const uint32_t kp = ((uint32_t)j << 5) | (uint32_t)lane;
+        if (kp < dim) rho[((size_t)(kp ^ x) << nq) | kp] = mk<T>(re[j] * inv, im[j] * inv);
+      }
+  }
+}
+
 // MINB = 1: one CTA per SM (the tile fills its shared memory anyway), up to 255 registers
 template <typename T, int THREADS, int MINB>
 __global__ void __launch_bounds__(THREADS, MINB)
@@ -328,6 +380,34 @@ __global__ void __launch_bounds__(THREADS, MINB)
         for (int j = tlane; j < F.n_obs; j += tsize)
           reinterpret_cast<T*>(out)[(size_t)bl * F.n_obs + j] =
               tile[ptm_swz<NB>((uint32_t)P.obs[j].zmask)];
+    } else if (F.out_mode == 0) {
+      cx<T>* rho = reinterpret_cast<cx<T>*>(out) + ((size_t)(valid ? bl : 0) << (2 * nq));
+      if (tsize >= 32) {
+        switch (nq > 5 ? nq - 5 : 0) {
+          case 0: ptm_rho_rows<T, NB, 0>(tile, rho, nq, Tb, rank, tlane, tsize, valid); break;
+          case 1: ptm_rho_rows<T, NB, 1>(tile, rho, nq, Tb, rank, tlane, tsize, valid); break;
+          case 2: ptm_rho_rows<T, NB, 2>(tile, rho, nq, Tb, rank, tlane, tsize, valid); break;
+          case 3: ptm_rho_rows<T, NB, 3>(tile, rho, nq, Tb, rank, tlane, tsize, valid); break;
+          default:  // n = 9: complex64 only (a complex128 tile holds at most 2 * 8 bits)
+            ptm_rho_rows<T, NB, sizeof(T) == 4 ? 4 : 3>(tile, rho, nq, Tb, rank, tlane, tsize, valid);
+        }
+      } else if (valid) {
+        // a tile smaller than a warp's row scheme (n <= 4): direct sums
+        const uint32_t dim = 1u << nq;
+        const T inv = (T)1 / (T)dim;
+        for (uint32_t e = tlane; e < tile_n; e += tsize) {
+          const uint32_t x = e >> nq, kp = e & (dim - 1u);
+          T re = 0, im = 0;
+          for (uint32_t z = 0; z < dim; ++z) {
+            T v = tile[ptm_swz<NB>((x << nq) | z)];
+            if (__popc(z & kp) & 1) v = -v;
+            const int m = __popc(x & z) & 3;
+            re += m == 0 ? v : (m == 2 ? -v : (T)0);
+            im += m == 1 ? v : (m == 3 ? -v : (T)0);
+          }
+          rho[((size_t)(kp ^ x) << nq) | kp] = mk<T>(re * inv, im * inv);
+        }
+      }
     } else if (F.out_mode == 1) {
       // p(b) = 2^-n sum_S (-1)^(b.S) r[S]: Walsh-Hadamard transform of the x = 0 coefficients
       // (the first 2^n entries of rank 0's tile), done in that CTA's scratch (teams == 1)

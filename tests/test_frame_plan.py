@@ -139,6 +139,7 @@ def test_config5_pass_count(lib):
     (5, 1, "Circuit_15", "expval", {"BitFlip": 0.05, "PhaseDamping": 0.1}),
     (4, 1, "Circuit_6", "expval", {"PhaseFlip": 0.1, "ThermalRelaxation": None}),
     (8, 1, "Strongly_Entangling", "probs", NOISE),
+    (4, 2, "Strongly_Entangling", "density", NOISE),
 ])
 def test_pauli_basis_schedules(lib, n, L, ct, typ, noise):
     """Strategy 5: noisy density programs made of 1-qubit (ket, bra) ops and CX pairs evolve

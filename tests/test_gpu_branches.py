@@ -248,10 +248,13 @@ def test_device_partial_trace_and_marginals_equal_host_helpers(precision):
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
         x = np.linspace(-1, 1, 5).reshape(-1, 1)
-        full = Model(6, 1, "Hardware_Efficient", precision=precision)
+        first = Model(6, 1, "Hardware_Efficient", precision=precision)
         for keep in ([1, 4], [0], [2, 3, 5], [5, 0]):
+            # fresh models per subset: a call without noise_params reuses the last ones
+            # (model.py:403, as the reference does), so the noiseless case must come first
+            full = Model(6, 1, "Hardware_Efficient", precision=precision)
             sub = Model(6, 1, "Hardware_Efficient", output_qubit=keep, precision=precision)
-            sub.params = full.params
+            full.params = sub.params = first.params
             for nz in (None, noise):
                 rho = full(inputs=x, execution_type="density", noise_params=nz)
                 got = sub(inputs=x, execution_type="density", noise_params=nz)

@@ -88,7 +88,7 @@ def test_frame_equals_streamed_strategy(monkeypatch):
 
 def test_frame_engine_is_selected():
     """Config 3 is planned as strategy 3 on the device; config 4 as strategy 5 (Pauli basis)
-    for <Z> / probabilities and as strategy 3 when the density matrix itself is asked for."""
+    (the density matrix is rebuilt from the coefficients by a phased Walsh-Hadamard transform)."""
     ex = get_executor()
     from qml_essentials_b200 import backend
     import test_cabi
@@ -96,7 +96,7 @@ def test_frame_engine_is_selected():
     for n, L, ct, typ, noise, want in ((6, 3, "Circuit_15", "expval", None, 3),
                                        (8, 4, "Strongly_Entangling", "expval", NOISE, 5),
                                        (8, 4, "Strongly_Entangling", "probs", NOISE, 5),
-                                       (8, 4, "Strongly_Entangling", "density", NOISE, 3)):
+                                       (8, 4, "Strongly_Entangling", "density", NOISE, 5)):
         plan = test_cabi._plan_of(n, L, ct, "complex128", typ, noise)
         h = backend.ProgramHandle(ex.lib, plan.program, plan.out_type, plan.obs_recs,
                                   plan.obs_pool, "complex128")
@@ -107,6 +107,8 @@ def test_frame_engine_is_selected():
 @pytest.mark.parametrize("n,L,typ,B_I,B_P", [
     (8, 4, "expval", 3, 2), (8, 2, "probs", 2, 2), (7, 2, "expval", 5, 3), (5, 3, "probs", 9, 4),
     (3, 2, "expval", 17, 5), (2, 2, "probs", 4, 4),
+    (8, 2, "density", 2, 1), (7, 1, "density", 3, 1), (6, 2, "density", 2, 3), (5, 2, "density", 5, 2),
+    (4, 2, "density", 7, 3), (3, 3, "density", 9, 5),
 ])
 def test_pauli_basis_equals_complex_engine(monkeypatch, precision, n, L, typ, B_I, B_P):
     """Strategy 5 (real Pauli coefficients, CX folded + sign op) against the complex (ket,
