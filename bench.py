@@ -332,7 +332,8 @@ def config_legs(ex, peak_f64_tf):
                 noise_params={"Depolarizing": 0.01, "AmplitudeDamping": 0.02},
                 execution_type="density"), 2.69e9,
                 "Model(8,4,'Strongly_Entangling') noisy density matrices, batch 4096 "
-                "(4 GiB written once)", "k_frame<double,256,wide> (cluster of 8 CTAs, DSMEM)"),
+                "(4 GiB written once)",
+                "k_frame_ptm<double,512> (real Pauli coefficients, cluster of 4 CTAs, DSMEM)"),
         }
         for name, (mk_model, mk_kw, flop, what, kernel) in cases.items():
             try:
