@@ -492,27 +492,37 @@ def main():
             torch.cuda.synchronize()
             dist.barrier()
             peer_ptrs = (C.c_void_p * world)(*[int(q) for q in hdl.buffer_ptrs])
-            collective = ("one-shot all-reduce over symmetric memory (k_allreduce_oneshot), "
-                          "pipelined by one step and drained after the last step inside the "
-                          "timed region")
+            collective = ("one-shot all-reduce over symmetric memory (k_allreduce_oneshot) on a "
+                          "forked stream: step k publishes the statistics of step k - 1 while "
+                          "k_reg runs; the last two reductions are drained inside the timed "
+                          "region")
         except Exception as exc:  # noqa: BLE001
             print(f"[bench] symmetric memory unavailable ({exc}); using NCCL", file=sys.stderr)
             collective = "NCCL all_reduce"
 
+    side = torch.cuda.Stream(device=dev) if world > 1 else None
+
     def step_device():
+        main = torch.cuda.current_stream(dev)
+        st = main.cuda_stream
+        rc = 0
+        if world > 1 and peer_ptrs is not None:
+            # two-deep pipeline: the statistics of step k - 1 are published (and those of step
+            # k - 2 summed) on a side stream WHILE k_reg of step k runs - fork here, join before
+            # k_coef_moments overwrites `moments`; the sequence is drained inside the timed
+            # region (finish() below)
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                rc |= lib.qmlb_allreduce_peer(peer_ptrs, world, rank, n_stat, moments.data_ptr(),
+                                              reduced.data_ptr(), 1, side.cuda_stream)
         out = call.launch()  # (B, 4) expvals, flat order b = i * B_P + p
-        st = torch.cuda.current_stream(dev).cuda_stream
-        rc = lib.qmlb_grid_dft(out.data_ptr(), dt_code, B_I, B_P, N_QUBITS, None,
-                               coef.data_ptr(), st)
+        rc |= lib.qmlb_grid_dft(out.data_ptr(), dt_code, B_I, B_P, N_QUBITS, None,
+                                coef.data_ptr(), st)
+        if world > 1 and peer_ptrs is not None:
+            main.wait_stream(side)
         rc |= lib.qmlb_coef_moments(coef.data_ptr(), dt_code, rows.data_ptr(), K, B_P,
                                     moments.data_ptr(), st)
-        if world > 1 and peer_ptrs is not None:
-            # pipelined: this call publishes step k and returns the reduction of step k - 1,
-            # so the skew between GPUs (each flushes its L2 between steps) is not serialised
-            # into every step; the sequence is drained inside the timed region (below)
-            rc |= lib.qmlb_allreduce_peer(peer_ptrs, world, rank, n_stat, moments.data_ptr(),
-                                          reduced.data_ptr(), 1, st)
-        elif world > 1:
+        if world > 1 and peer_ptrs is None:
             reduced.copy_(moments)
             dist.all_reduce(reduced)
         if rc != 0:
@@ -528,11 +538,13 @@ def main():
         step_device()
     barrier()
     def drain():
+        # publish the statistics of the last step, then sum them: `reduced` = their all-reduce
         if world > 1 and peer_ptrs is not None:
             st = torch.cuda.current_stream(dev).cuda_stream
-            if lib.qmlb_allreduce_peer(peer_ptrs, world, rank, n_stat, moments.data_ptr(),
-                                       reduced.data_ptr(), 2, st) != 0:
-                raise RuntimeError(lib.qmlb_last_error().decode())
+            for mode in (1, 2):
+                if lib.qmlb_allreduce_peer(peer_ptrs, world, rank, n_stat, moments.data_ptr(),
+                                           reduced.data_ptr(), mode, st) != 0:
+                    raise RuntimeError(lib.qmlb_last_error().decode())
 
     collective_err = None
     if world > 1 and peer_ptrs is not None:  # the one-shot all-reduce against NCCL's
@@ -548,11 +560,11 @@ def main():
     if not args.no_graph:
         try:
             l0 = ex.launch_count()
-            side = torch.cuda.Stream()
-            side.wait_stream(torch.cuda.current_stream())
-            with torch.cuda.stream(side):
+            warm = torch.cuda.Stream()
+            warm.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(warm):
                 step_device()
-            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.current_stream().wait_stream(warm)
             graph = torch.cuda.CUDAGraph()
             l0 = ex.launch_count()
             with torch.cuda.graph(graph):

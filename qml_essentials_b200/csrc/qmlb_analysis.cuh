@@ -214,11 +214,15 @@ __global__ void __launch_bounds__(256) k_allreduce_oneshot(PeerReduce R,
       double* dst = slot(r, epoch, R.rank);
       for (int64_t i = threadIdx.x; i < n; i += blockDim.x) dst[i] = in[i];
     }
-    __threadfence_system();
+    if (R.pad == 0) __threadfence_system();  // every thread fences its own stores
   }
   __syncthreads();
   if (threadIdx.x < R.n_peers) {
     if (R.mode != 2) {
+      // pad = 1: the CTA barrier orders the data stores of all threads before this thread,
+      // whose system-scope fence + release store is cumulative over them (the grid-sync
+      // pattern) - n_peers fences instead of 256
+      if (R.pad != 0) __threadfence_system();
       unsigned long long* flag = static_cast<unsigned long long*>(R.buf[threadIdx.x]) + R.rank;
       asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(flag), "l"(epoch) : "memory");
     }

@@ -1409,6 +1409,11 @@ int qmlb_allreduce_peer(const void* const* peer_buf, int32_t n_peers, int32_t ra
   R.rank = rank;
   R.mode = mode;
   R.n = n;
+  static const int light = [] {
+    const char* v = std::getenv("QMLB_AR_FENCE");
+    return (v && std::string(v) == "all") ? 0 : 1;
+  }();
+  R.pad = light;
   g_launches.fetch_add(1, std::memory_order_relaxed);
   k_allreduce_oneshot<<<1, 256, 0, static_cast<cudaStream_t>(stream)>>>(R, in, out);
   CUDA_TRY(cudaGetLastError());
