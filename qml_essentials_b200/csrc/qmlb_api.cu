@@ -500,6 +500,7 @@ int upload(qmlb_program* p) {
       }
       fast[i] = f;
     }
+    p->reg_ops_host = fast;
   }
   const size_t o_fast = place(off, fast);
   const size_t o_matlist = place(off, p->stream_matlist);

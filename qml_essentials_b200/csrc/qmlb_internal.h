@@ -51,6 +51,7 @@ struct qmlb_program {
   std::vector<qmlb_obs> obs;
   std::vector<double> obs_consts;
   std::vector<qmlb_pre> pre;
+  std::vector<qmlb::RegOp> reg_ops_host;                    // strategy 0: the compact op stream
   std::vector<int32_t> pre_ids[QMLB_MAX_ARGS];        // pre entries per argument slot
   const int32_t* pre_ids_dev[QMLB_MAX_ARGS] = {};     // same, in the device blob
   int max_arg = -1;

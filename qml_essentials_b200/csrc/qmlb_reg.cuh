@@ -231,6 +231,35 @@ __host__ inline bool reg_supports(const qmlb_op& op, const double* consts, int n
   return false;
 }
 
+// CTA tile of the (fast axis x slow axis) batch, e.g. 16 parameter sets x 8 grid points:
+// every hoisted factor the tile's 128 evaluations read (16 + 8 table rows per op instead of
+// 128 + 1) is staged ONCE into shared memory with cp.async, so a gate's matrix costs
+// shared-memory latency instead of an L2 round trip, no prefetch registers are needed, and
+// the L2 -> SM traffic per evaluation drops ~7x (config 2: 30 KB per CTA).
+//   cls[slot]: 0 = slot has no hoisted factors here, 1 = FAST (row = fast index p, div = 1),
+//              2 = SLOW (row = slow index i = b / BP), 3 = CONST (mod = 1: row 0)
+struct RegTile {
+  int32_t tp_bits, ti_bits;
+  int64_t n_ptiles, BP, BI;
+  uint8_t cls[QMLB_MAX_ARGS];
+};
+
+template <typename T>
+__device__ __forceinline__ void reg_cp_async(cx<T>* smem, const cx<T>* gmem) {
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+  if constexpr (sizeof(cx<T>) == 16)
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(gmem));
+  else
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(sa), "l"(gmem));
+}
+
+// shared-memory stride of one staged 2x2 factor in cx<T> units: 4 entries + 16 bytes of
+// padding, which spreads the rows of a quarter warp over all banks (80 / 48 byte stride)
+template <typename T>
+__host__ __device__ constexpr int reg_tile_stride() {
+  return sizeof(T) == 8 ? 5 : 6;
+}
+
 // rows cached in shared memory: slot a of this thread at base[a * 128]
 struct RowsShared {
   const int32_t* base;
@@ -249,9 +278,9 @@ constexpr int reg_min_ctas() {
 // MINB: resident CTAs per SM the variant is compiled for (0 = reg_min_ctas default).  The
 // complex128 n = 4 kernel exists at 2 (210 registers, no spills) and 3 (168 registers, 124
 // bytes of spills, 12 instead of 8 warps per SM).
-template <typename T, int N, int MINB = 0>
+template <typename T, int N, int MINB = 0, bool TILED = false>
 __global__ void __launch_bounds__(128, MINB ? MINB : reg_min_ctas<T, N>())
-    k_reg(DevProg P, RunArgs R, int mode, int n_args, void* __restrict__ out) {
+    k_reg(DevProg P, RunArgs R, int mode, int n_args, void* __restrict__ out, const RegTile Tl) {
   constexpr int D = 1 << N;
   // op stream -> shared memory (all threads take part before anyone leaves)
   extern __shared__ __align__(16) unsigned char reg_smem[];
@@ -264,8 +293,63 @@ __global__ void __launch_bounds__(128, MINB ? MINB : reg_min_ctas<T, N>())
     __syncthreads();
   }
   const RegOp* ops = staged ? s_ops : P.rops;
-  const int64_t bl = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (bl >= R.batch) return;
+  int64_t bl = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  // TILED: [ops | 2 offsets per op | staged factor tables]
+  constexpr int ES = reg_tile_stride<T>();
+  int32_t* s_off = reinterpret_cast<int32_t*>(s_ops + P.n_ops);
+  cx<T>* s_tab = reinterpret_cast<cx<T>*>(
+      reg_smem + ((sizeof(RegOp) * P.n_ops + 8 * (size_t)P.n_ops + 15) & ~size_t(15)));
+  int row_f = 0, row_s = 0;  // this thread's rows in the staged FAST / SLOW factors
+  if constexpr (TILED) {
+    const int TP = 1 << Tl.tp_bits, TI = 1 << Tl.ti_bits;
+    const int64_t cp = (int64_t)blockIdx.x % Tl.n_ptiles, ci = (int64_t)blockIdx.x / Tl.n_ptiles;
+    const int tp = threadIdx.x & (TP - 1), ti = threadIdx.x >> Tl.tp_bits;
+    const int64_t p0 = cp * TP, i0 = ci * TI;
+    const int rows_f = (int)(Tl.BP - p0 < TP ? Tl.BP - p0 : TP);
+    const int rows_s = (int)(Tl.BI - i0 < TI ? Tl.BI - i0 : TI);
+    if (threadIdx.x == 0) {
+      int acc = 0;
+      for (int o = 0; o < P.n_ops; ++o) {
+        const RegOp d = s_ops[o];
+        const bool use = d.n >= 1 && R.pre_on[d.slot0] && (d.n == 1 || R.pre_on[d.slot1]);
+        for (int j = 0; j < 2; ++j) {
+          int off = -1;
+          if (use && j < d.n) {
+            const int c = Tl.cls[j ? d.slot1 : d.slot0];
+            off = acc;
+            acc += (c == 1 ? rows_f : (c == 2 ? rows_s : 1)) * ES;
+          }
+          s_off[2 * o + j] = off;
+        }
+      }
+    }
+    __syncthreads();
+    for (int o = 0; o < P.n_ops; ++o) {
+      const RegOp d = s_ops[o];
+      for (int j = 0; j < 2; ++j) {
+        const int off = s_off[2 * o + j];
+        if (off < 0) continue;
+        const int slot = j ? d.slot1 : d.slot0, local = j ? d.local1 : d.local0;
+        const int c = Tl.cls[slot];
+        const int rows = c == 1 ? rows_f : (c == 2 ? rows_s : 1);
+        const int64_t row0 = c == 1 ? p0 : (c == 2 ? i0 : 0);
+        const cx<T>* src = static_cast<const cx<T>*>(R.pre_tab[slot]) +
+                           ((int64_t)local * R.a[slot].mod + row0) * 4;
+        cx<T>* dst = s_tab + off;
+        for (int e = threadIdx.x; e < rows * 4; e += 128)
+          reg_cp_async<T>(dst + (e >> 2) * ES + (e & 3), src + e);
+      }
+    }
+    asm volatile("cp.async.commit_group;\n" ::);
+    asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+    __syncthreads();
+    if (tp >= rows_f || ti >= rows_s) return;
+    bl = (i0 + ti) * Tl.BP + p0 + tp;
+    row_f = tp;
+    row_s = ti;
+  } else {
+    if (bl >= R.batch) return;
+  }
   const int64_t b = bl + R.batch_offset;
 
   // rows of the argument slots this element reads, computed once (64-bit div/mod)
@@ -291,6 +375,7 @@ __global__ void __launch_bounds__(128, MINB ? MINB : reg_min_ctas<T, N>())
   int nfn = 0;
   auto fetch = [&](int o) {
     nfn = 0;
+    if constexpr (TILED) return;  // factors come from shared memory, no prefetch registers
     if (o >= P.n_ops) return;
     const RegOp d = ops[o];
     if (d.n < 1 || !R.pre_on[d.slot0] || (d.n == 2 && !R.pre_on[d.slot1])) return;
@@ -311,13 +396,32 @@ __global__ void __launch_bounds__(128, MINB ? MINB : reg_min_ctas<T, N>())
   for (int o = 0; o < P.n_ops; ++o) {
     const RegOp op = ops[o];
     cx<T> m[4];
-    const bool have_m = nfn > 0;
-    if (have_m) {
+    bool have_m = nfn > 0;
+    if constexpr (TILED) {
+      const int off0 = s_off[2 * o], off1 = s_off[2 * o + 1];
+      have_m = off0 >= 0;
+      if (have_m) {
+        const int c0 = Tl.cls[op.slot0];
+        const cx<T>* e0 = s_tab + off0 + (c0 == 1 ? row_f : (c0 == 2 ? row_s : 0)) * ES;
 #pragma unroll
-      for (int i = 0; i < 4; ++i) m[i] = nf0[i];
-      if (nfn == 2) mul2_left<T>(nf1, m);
+        for (int i = 0; i < 4; ++i) m[i] = e0[i];
+        if (off1 >= 0) {
+          const int c1 = Tl.cls[op.slot1];
+          const cx<T>* e1 = s_tab + off1 + (c1 == 1 ? row_f : (c1 == 2 ? row_s : 0)) * ES;
+          cx<T> f1[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) f1[i] = e1[i];
+          mul2_left<T>(f1, m);
+        }
+      }
+    } else {
+      if (have_m) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) m[i] = nf0[i];
+        if (nfn == 2) mul2_left<T>(nf1, m);
+      }
+      fetch(o + 1);
     }
-    fetch(o + 1);
     if (op.kind == QMLB_OP_PERM) {
       if (op.k == 1) {  // the only non-identity 1-bit permutation is X
         dispatch1<T, N>(op.b0, [&](auto B) {
