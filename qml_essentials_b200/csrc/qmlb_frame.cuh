@@ -466,14 +466,17 @@ __global__ void __launch_bounds__(THREADS, (THREADS == 512 || WIDE) ? 1 : 2)
   const int team = threadIdx.x >> F.team_bits;
   const int tlane = threadIdx.x & (tsize - 1);
   // [tiles | matrices | 2 step records | relayout tables | reduction scratch]
+  const uint32_t pitch = F.tile_pitch ? (uint32_t)F.tile_pitch : tile_n;
+  const bool direct = F.mat_resident == 2;  // matrices read from global memory
   cx<T>* tiles = reinterpret_cast<cx<T>*>(fsm);
-  cx<T>* mats_all = tiles + (size_t)teams * tile_n;
-  FrameStep* sstep = reinterpret_cast<FrameStep*>(mats_all + (size_t)teams * F.mat_cap);
-  uint32_t* tab_lo = reinterpret_cast<uint32_t*>(sstep + 2);
+  cx<T>* mats_all = tiles + (((size_t)teams * pitch + 63) & ~size_t(63));
+  FrameStep* sstep =
+      reinterpret_cast<FrameStep*>(mats_all + (direct ? 0 : (size_t)teams * F.mat_cap));
+  uint32_t* tab_lo = reinterpret_cast<uint32_t*>(sstep + (F.steps_resident ? F.n_steps : 2));
   uint32_t* tab_hi = tab_lo + 256;
   double* red = reinterpret_cast<double*>(tab_hi + 64);
-  cx<T>* tile = tiles + (size_t)team * tile_n;
-  cx<T>* mats = mats_all + (size_t)team * F.mat_cap;
+  cx<T>* tile = tiles + (size_t)team * pitch;
+  const cx<T>* mats = mats_all + (size_t)team * F.mat_cap;
 
   const bool clustered = F.outer_bits > 0;
   cg::cluster_group cluster = cg::this_cluster();
@@ -492,24 +495,34 @@ __global__ void __launch_bounds__(THREADS, (THREADS == 512 || WIDE) ? 1 : 2)
   const int64_t rounds = (A.batch + per_round - 1) / per_round;
   const uint32_t n_items = 1u << (Tb - FRAME_R);
 
+  if (F.steps_resident) {  // the whole step program, once per CTA
+    const int4* src = reinterpret_cast<const int4*>(F.steps);
+    int4* dst = reinterpret_cast<int4*>(sstep);
+    for (int i = threadIdx.x; i < F.n_steps * 64; i += THREADS) dst[i] = src[i];
+  }
+
   for (int64_t rd = 0; rd < rounds; ++rd) {
     const int64_t bl = rd * per_round + cluster_id * teams + team;
     const bool valid = bl < A.batch;
     const cx<T>* prow = premats + (size_t)(valid ? bl : 0) * F.premat_row;
+    if (direct) mats = prow;
 
     // |0..0>: the frame is linear, so logical index 0 sits at physical index 0
     for (uint32_t i = tlane; i < tile_n; i += tsize)
       tile[i] = mk<T>((i == 0 && rank == 0) ? (T)1 : (T)0, (T)0);
-    if (F.mat_resident)  // every matrix of this element, once
-      for (int i = tlane; i < F.premat_row; i += tsize) mats[i] = prow[i];
-    for (int i = threadIdx.x; i < 256; i += THREADS)
-      reinterpret_cast<uint32_t*>(&sstep[0])[i] =
-          reinterpret_cast<const uint32_t*>(&F.steps[0])[i];
+    if (F.mat_resident == 1) {  // every matrix of this element, once
+      cx<T>* mdst = mats_all + (size_t)team * F.mat_cap;
+      for (int i = tlane; i < F.premat_row; i += tsize) mdst[i] = prow[i];
+    }
+    if (!F.steps_resident)
+      for (int i = threadIdx.x; i < 256; i += THREADS)
+        reinterpret_cast<uint32_t*>(&sstep[0])[i] =
+            reinterpret_cast<const uint32_t*>(&F.steps[0])[i];
     sync_all();
 
     for (int si = 0; si < F.n_steps; ++si) {
-      const FrameStep& st = sstep[si & 1];
-      if (si + 1 < F.n_steps)
+      const FrameStep& st = sstep[F.steps_resident ? si : (si & 1)];
+      if (!F.steps_resident && si + 1 < F.n_steps)
         for (int i = threadIdx.x; i < 256; i += THREADS)
           reinterpret_cast<uint32_t*>(&sstep[(si + 1) & 1])[i] =
               reinterpret_cast<const uint32_t*>(&F.steps[si + 1])[i];
@@ -555,13 +568,15 @@ __global__ void __launch_bounds__(THREADS, (THREADS == 512 || WIDE) ? 1 : 2)
 
       // ---- SUBPASS ------------------------------------------------------------------------
       if (!F.mat_resident) {  // stage the matrices of this step
-        if (valid)
+        if (valid) {
+          cx<T>* mdst = mats_all + (size_t)team * F.mat_cap;
           for (int o = 0; o < st.n_ops; ++o) {
             const FrameOp fo = st.ops[o];
             const int n = fo.code == QMLB_FOP_DIAG ? (1 << fo.k) : (1 << (2 * fo.k));
-            for (int e = tlane; e < n; e += tsize) mats[fo.smem_off + e] = prow[fo.premat_off + e];
+            for (int e = tlane; e < n; e += tsize) mdst[fo.smem_off + e] = prow[fo.premat_off + e];
             if (fo.code == QMLB_FOP_DIAG) ++o;
           }
+        }
         __syncthreads();
       }
 

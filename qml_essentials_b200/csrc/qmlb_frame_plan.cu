@@ -958,7 +958,11 @@ int plan_frame(qmlb_program* p) {
   };
   int cap = std::max(row, 1);
   bool resident = true;
-  if (!fits(teams, cap)) {
+  // several tiles per CTA: matrices straight from global memory, all step records resident,
+  // padded tile pitch (FrameProg::steps_resident); QMLB_FRAME_SMALL=0 -> round-1 geometry
+  const char* es = std::getenv("QMLB_FRAME_SMALL");
+  const bool small = teams > 1 && !(es && std::atoi(es) == 0);
+  if (!small && !fits(teams, cap)) {
     int tm = teams;
     while (tm > 1 && (tm << team_bits) > 128 && !fits(tm, cap)) tm >>= 1;
     if (fits(tm, cap)) {
@@ -1009,7 +1013,7 @@ int plan_frame(qmlb_program* p) {
   fp.team_bits = team_bits;
   fp.teams = teams;
   fp.mat_cap = cap;
-  fp.mat_resident = resident ? 1 : 0;
+  fp.mat_resident = small ? 2 : (resident ? 1 : 0);
   fp.premat_row = row;
   fp.density = p->density;
   fp.n_qubits = p->n_qubits;
@@ -1018,8 +1022,17 @@ int plan_frame(qmlb_program* p) {
   p->frame_heavy = false;
   for (const qmlb_op& o : p->ops)
     if (o.kind == QMLB_OP_MAT && o.k >= 3) p->frame_heavy = true;
-  // [tiles | matrices | 2 step records | relayout tables | reduction scratch]
-  p->frame_smem = (size_t)teams * (tile_bytes + (size_t)cap * cs) + fixed;
+  // [tiles | matrices | step records | relayout tables | reduction scratch]
+  if (small) {
+    fp.tile_pitch = (1 << B.T) + 1;
+    fp.steps_resident = fp.n_steps <= 64 ? 1 : 0;
+    const size_t tiles = (((size_t)teams * fp.tile_pitch + 63) & ~size_t(63)) * cs;
+    p->frame_smem = tiles + (size_t)(fp.steps_resident ? fp.n_steps : 2) * sizeof(FrameStep) +
+                    (fixed - 2 * sizeof(FrameStep));
+  } else {
+    p->frame_smem = (((size_t)teams * (size_t(1) << B.T) + 63) & ~size_t(63)) * cs +
+                    (size_t)teams * cap * cs + fixed;
+  }
   return QMLB_OK;
 }
 

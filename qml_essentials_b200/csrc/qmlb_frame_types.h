@@ -125,6 +125,12 @@ struct FrameProg {
   int32_t out_mode;    // 0: complex state in index order, 1: probabilities, 2: Z-string expvals
   int32_t density, n_qubits, n_obs;
   int32_t ptm;         // 1: the state is the REAL Pauli-coefficient vector of a density matrix
+  // several tiles per CTA (small states): every step record is loaded once per CTA instead of
+  // once per round and step; tiles sit tile_pitch elements apart (2^T + 1: the teams of a warp
+  // then hit different banks); mat_resident = 2 reads matrices straight from the element's
+  // row in global memory (they are used once - staging them would cost the shared memory
+  // that limits the resident warps)
+  int32_t steps_resident, tile_pitch;
 };
 
 }  // namespace qmlb
