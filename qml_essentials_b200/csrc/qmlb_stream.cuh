@@ -218,15 +218,24 @@ __device__ __forceinline__ void reg_perm2(RegState<T, N>& S, unsigned packed) {
 // Batched streaming runs (density matrices, config 4): one thread per (element, matrix)
 // evaluates the matrix sources of ALL passes once into a table, so the gate-pass CTAs only
 // copy their few hundred bytes instead of each re-deriving sincos + 4x4 chain products.
-template <typename T>
-__global__ void k_stream_mats(DevProg P, RunArgs A, const StreamMatOp* __restrict__ list,
-                              int n_list, int mat_row, cx<T>* __restrict__ out) {
+// PLAIN: no entry needs the role swap or the Pauli transform - the light variant (64
+// registers, 16 warps per SM instead of 10 resident: the kernel is a chain of dependent
+// loads through the source / angle / argument records, i.e. latency bound; config 3:
+// 70 -> ~25 us for 960 000 matrices)
+template <typename T, bool PLAIN>
+__global__ void __launch_bounds__(128, PLAIN ? 8 : 2)
+    k_stream_mats(DevProg P, RunArgs A, const StreamMatOp* __restrict__ list, int n_list,
+                  int mat_row, cx<T>* __restrict__ out) {
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= A.batch * n_list) return;
   const int64_t bl = t / n_list;
   const StreamMatOp mo = list[t % n_list];
   cx<T>* dst = out + (size_t)bl * mat_row + mo.off;
   const RowsDirect rows{A, bl + A.batch_offset};
+  if constexpr (PLAIN) {
+    eval_source_mem<T>(P, A, rows, mo.src, dst);
+    return;
+  }
   if (mo.swap2 >= 2) {
     // Pauli transfer matrix of a 1-qubit superoperator: R = T S T^-1 with S in (ket, bra)
     // order [rho00, rho01, rho10, rho11], Pauli order (I, Z, X, Y) and T^-1 = T^dagger / 2,

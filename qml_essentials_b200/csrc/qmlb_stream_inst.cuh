@@ -28,9 +28,17 @@ cudaError_t QMLB_LAUNCH_STREAM_MATS(const qmlb_program* p, const RunArgs& R, voi
   const int64_t total = R.batch * (int64_t)p->stream_matlist.size();
   if (total == 0) return cudaSuccess;
   g_launches.fetch_add(1, std::memory_order_relaxed);
-  k_stream_mats<QMLB_T><<<(unsigned)((total + 63) / 64), 64, 0, st>>>(
-      p->dev, R, p->stream_matlist_dev, (int)p->stream_matlist.size(), p->stream_mat_row,
-      static_cast<cx<QMLB_T>*>(out));
+  bool plain = true;
+  for (const StreamMatOp& mo : p->stream_matlist) plain = plain && mo.swap2 == 0;
+  const unsigned grid = (unsigned)((total + 127) / 128);
+  if (plain)
+    k_stream_mats<QMLB_T, true><<<grid, 128, 0, st>>>(
+        p->dev, R, p->stream_matlist_dev, (int)p->stream_matlist.size(), p->stream_mat_row,
+        static_cast<cx<QMLB_T>*>(out));
+  else
+    k_stream_mats<QMLB_T, false><<<grid, 128, 0, st>>>(
+        p->dev, R, p->stream_matlist_dev, (int)p->stream_matlist.size(), p->stream_mat_row,
+        static_cast<cx<QMLB_T>*>(out));
   return cudaGetLastError();
 }
 #endif

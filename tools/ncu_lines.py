@@ -30,7 +30,8 @@ for r in rows:
         continue
     total += smp
     lines.append((smp, cur, int(r[0]), r[1].strip(), int(d["Instructions Executed"]),
-                  int(d["L1 Wavefronts Shared"]), int(d["L1 Wavefronts Shared Ideal"])))
+                  int(d.get("L1 Wavefronts Shared", 0) or 0),
+                  int(d.get("L1 Wavefronts Shared Ideal", 0) or 0)))
 lines.sort(reverse=True)
 print(f"samples {total}")
 for smp, f, ln, src, ins, wf, wfi in lines[:top]:
