@@ -98,16 +98,10 @@ class Coefficients:
         if not hasattr(ex, "grid_dft"):
             return None
         n_freqs = mfs * model.degree[0]
-        grid = np.arange(0, 2 * mts * np.pi, 2 * np.pi / n_freqs).reshape(-1, 1)
+        grid, freqs, order, self_conj = cls._grid_constants(int(n_freqs), mts, bool(shift),
+                                                            bool(trim))
         n_x = grid.shape[0]
-        freqs = np.fft.fftfreq(int(mts * n_freqs), 1 / n_freqs)
-        order = np.arange(n_x)
-        if trim and n_x % 2 == 0:
-            order = np.delete(order, n_x // 2)
-            freqs = np.delete(freqs, len(freqs) // 2)
-        if shift:
-            order = np.fft.fftshift(order)
-            freqs = np.fft.fftshift(freqs)
+        freqs = freqs.copy()  # callers own (and may edit) the frequency axis
         kw = {k: v for k, v in kwargs.items() if k != "force_mean"}
         ev = model.device_result(inputs=grid, **kw)
         coef = ex.grid_dft(ev.reshape(n_x, -1, ev.shape[-1]), order)
@@ -117,9 +111,34 @@ class Coefficients:
         # the kernel writes coefficient n - k as the conjugate of coefficient k, so the
         # imaginary parts cancel pairwise; only the self-conjugate rows (k = 0, n / 2) can
         # carry the imbalance the reference tests for (coefficients.py:66-70)
-        self_conj = [r for r, k in enumerate(order) if (2 * k) % n_x == 0]
         cls._check_real(coeffs[self_conj])
         return coeffs, [freqs]
+
+    _GRID_CACHE: dict = {}
+
+    @classmethod
+    def _grid_constants(cls, n_freqs: int, mts, shift: bool, trim: bool):
+        """Input grid, frequency axis, output row order and the self-conjugate rows of one
+        (n_freqs, mts, shift, trim) setting - pure functions of their key, computed once."""
+        key = (n_freqs, mts, shift, trim)
+        hit = cls._GRID_CACHE.get(key)
+        if hit is None:
+            grid = np.arange(0, 2 * mts * np.pi, 2 * np.pi / n_freqs).reshape(-1, 1)
+            n_x = grid.shape[0]
+            freqs = np.fft.fftfreq(int(mts * n_freqs), 1 / n_freqs)
+            order = np.arange(n_x)
+            if trim and n_x % 2 == 0:
+                order = np.delete(order, n_x // 2)
+                freqs = np.delete(freqs, len(freqs) // 2)
+            if shift:
+                order = np.fft.fftshift(order)
+                freqs = np.fft.fftshift(freqs)
+            self_conj = [r for r, k in enumerate(order) if (2 * k) % n_x == 0]
+            order.setflags(write=False)
+            if len(cls._GRID_CACHE) > 64:
+                cls._GRID_CACHE.clear()
+            hit = cls._GRID_CACHE[key] = (grid, freqs, order, self_conj)
+        return hit
 
     @classmethod
     def _fourier_transform(cls, model: Model, mfs: int, mts: int, **kwargs: Any):
