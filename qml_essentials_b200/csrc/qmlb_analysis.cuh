@@ -9,7 +9,8 @@
 
 namespace qmlb {
 
-constexpr int DFT_PCOLS = 4;  // parameter samples per CTA
+constexpr int DFT_PCOLS = 8;  // parameter samples per CTA
+constexpr int DFT_TC = 4;     // ... of which one thread sums four (one twiddle load feeds 8 FMAs)
 
 // out[row_of[k]][p] = (1 / n_x) * sum_x s[x][p] * exp(-2 pi i k x / n_x),
 // s[x][p] = mean over the n_obs observables of ev[x][p][:]   (ev: (n_x, n_p, n_obs) real)
@@ -21,7 +22,7 @@ constexpr int DFT_PCOLS = 4;  // parameter samples per CTA
 // frequency k on an output row of the caller's choice (-1 = not wanted): get_spectrum's
 // shift / trim cost nothing.
 template <typename T>
-__global__ void __launch_bounds__(256) k_grid_dft(const T* __restrict__ ev, int n_x, int64_t n_p,
+__global__ void __launch_bounds__(1024) k_grid_dft(const T* __restrict__ ev, int n_x, int64_t n_p,
                                                   int n_obs, const int32_t* __restrict__ row_of,
                                                   cx<T>* __restrict__ out) {
   extern __shared__ __align__(16) unsigned char dsm[];
@@ -52,27 +53,47 @@ __global__ void __launch_bounds__(256) k_grid_dft(const T* __restrict__ ev, int 
     sig[(n_x - x) * DFT_PCOLS + c] = a - b;
   }
   __syncthreads();
-  const int c = threadIdx.x % DFT_PCOLS;
+  constexpr int GROUPS = DFT_PCOLS / DFT_TC;
+  const int c0 = (threadIdx.x % GROUPS) * DFT_TC;
   const double inv = 1.0 / (double)n_x;
-  for (int k = threadIdx.x / DFT_PCOLS; k <= n_x / 2; k += blockDim.x / DFT_PCOLS) {
-    double re = sig[c], im = 0.0;
-    if ((n_x & 1) == 0) re += (k & 1) ? -sig[(n_x / 2) * DFT_PCOLS + c] : sig[(n_x / 2) * DFT_PCOLS + c];
+  for (int k = threadIdx.x / GROUPS; k <= n_x / 2; k += blockDim.x / GROUPS) {
+    double re[DFT_TC], im[DFT_TC];
+#pragma unroll
+    for (int j = 0; j < DFT_TC; ++j) {
+      re[j] = sig[c0 + j];
+      im[j] = 0.0;
+      if ((n_x & 1) == 0) {
+        const double ny = sig[(n_x / 2) * DFT_PCOLS + c0 + j];
+        re[j] += (k & 1) ? -ny : ny;
+      }
+    }
     int idx = 0;  // (k * x) mod n_x
     for (int x = 1; x <= half; ++x) {
       idx += k;
       if (idx >= n_x) idx -= n_x;
       const double2 w = tw[idx];
-      re = fma(sig[x * DFT_PCOLS + c], w.x, re);
-      im = fma(sig[(n_x - x) * DFT_PCOLS + c], w.y, im);
+      const double2* e = reinterpret_cast<const double2*>(sig + x * DFT_PCOLS + c0);
+      const double2* o = reinterpret_cast<const double2*>(sig + (n_x - x) * DFT_PCOLS + c0);
+      const double2 e0 = e[0], e1 = e[1], o0 = o[0], o1 = o[1];
+      re[0] = fma(e0.x, w.x, re[0]);
+      re[1] = fma(e0.y, w.x, re[1]);
+      re[2] = fma(e1.x, w.x, re[2]);
+      re[3] = fma(e1.y, w.x, re[3]);
+      im[0] = fma(o0.x, w.y, im[0]);
+      im[1] = fma(o0.y, w.y, im[1]);
+      im[2] = fma(o1.x, w.y, im[2]);
+      im[3] = fma(o1.y, w.y, im[3]);
     }
-    if (p0 + c < n_p) {
-      const int r0 = row_of ? row_of[k] : k;
-      if (r0 >= 0) out[(size_t)r0 * n_p + p0 + c] = mk<T>((T)(re * inv), (T)(im * inv));
-      const int km = (n_x - k) % n_x;
-      if (km != k) {
-        const int r1 = row_of ? row_of[km] : km;
-        if (r1 >= 0) out[(size_t)r1 * n_p + p0 + c] = mk<T>((T)(re * inv), (T)(-im * inv));
-      }
+    const int r0 = row_of ? row_of[k] : k;
+    const int km = (n_x - k) % n_x;
+    const int r1 = km != k ? (row_of ? row_of[km] : km) : -1;
+#pragma unroll
+    for (int j = 0; j < DFT_TC; ++j) {
+      if (p0 + c0 + j >= n_p) continue;
+      if (r0 >= 0)
+        out[(size_t)r0 * n_p + p0 + c0 + j] = mk<T>((T)(re[j] * inv), (T)(im[j] * inv));
+      if (r1 >= 0)
+        out[(size_t)r1 * n_p + p0 + c0 + j] = mk<T>((T)(re[j] * inv), (T)(-im[j] * inv));
     }
   }
 }
@@ -81,32 +102,34 @@ __global__ void __launch_bounds__(256) k_grid_dft(const T* __restrict__ ev, int 
 //   out[i]             = sum_p c_i(p)                 i < K
 //   out[K + i]         = sum_p |c_i(p)|^2 (real)
 //   out[2K + i*K + j]  = sum_p conj(c_i(p)) * c_j(p)
-// One WARP per output: lanes stride over the samples (coalesced), complex128 accumulators,
-// fixed xor-shuffle tree - bitwise reproducible.
+// One CTA of 128 threads per output: threads stride over the samples (coalesced), complex128
+// accumulators, fixed xor-shuffle tree, warp partials summed in warp order - bitwise
+// reproducible.  (One warp per output left 13 CTAs on the GPU: 14 us of latency.)
 template <typename T>
-__global__ void __launch_bounds__(256) k_coef_moments(const cx<T>* __restrict__ coef,
+__global__ void __launch_bounds__(128) k_coef_moments(const cx<T>* __restrict__ coef,
                                                       const int32_t* __restrict__ rows, int K,
                                                       int64_t n_p, double2* __restrict__ out) {
-  const int64_t t = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
+  __shared__ double2 part[4];
+  const int64_t t = blockIdx.x;
+  const int lane = threadIdx.x & 31, tid = threadIdx.x;
   if (t >= (int64_t)K * K + 2 * K) return;
   double re = 0.0, im = 0.0;
   if (t < 2 * K) {
     const cx<T>* ci = coef + (size_t)rows[t % K] * n_p;
     if (t < K) {
-      for (int64_t p = lane; p < n_p; p += 32) {
+      for (int64_t p = tid; p < n_p; p += 128) {
         re += (double)ci[p].x;
         im += (double)ci[p].y;
       }
     } else {
-      for (int64_t p = lane; p < n_p; p += 32)
+      for (int64_t p = tid; p < n_p; p += 128)
         re += (double)ci[p].x * ci[p].x + (double)ci[p].y * ci[p].y;
     }
   } else {
     const int i = (int)((t - 2 * K) / K), j = (int)((t - 2 * K) % K);
     const cx<T>* ci = coef + (size_t)rows[i] * n_p;
     const cx<T>* cj = coef + (size_t)rows[j] * n_p;
-    for (int64_t p = lane; p < n_p; p += 32) {
+    for (int64_t p = tid; p < n_p; p += 128) {
       const double ar = ci[p].x, ai = ci[p].y, br = cj[p].x, bi = cj[p].y;
       re += ar * br + ai * bi;  // conj(a) * b
       im += ar * bi - ai * br;
@@ -116,7 +139,16 @@ __global__ void __launch_bounds__(256) k_coef_moments(const cx<T>* __restrict__ 
     re += __shfl_xor_sync(0xffffffffu, re, off);
     im += __shfl_xor_sync(0xffffffffu, im, off);
   }
-  if (lane == 0) out[t] = make_double2(re, im);
+  if (lane == 0) part[tid >> 5] = make_double2(re, im);
+  __syncthreads();
+  if (tid == 0) {
+    double2 s = part[0];
+    for (int w = 1; w < 4; ++w) {
+      s.x += part[w].x;
+      s.y += part[w].y;
+    }
+    out[t] = s;
+  }
 }
 
 // Sub-register outputs (jaqsi.py:79-146): partial trace of density matrices and marginal

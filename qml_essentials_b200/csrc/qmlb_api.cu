@@ -1299,18 +1299,21 @@ int qmlb_grid_dft(const void* ev, int dtype, int32_t n_x, int64_t n_p, int32_t n
   if (smem > 200 * 1024) return fail(QMLB_ERR_UNSUPPORTED, "grid too long for the on-chip DFT");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const unsigned grid = (unsigned)((n_p + DFT_PCOLS - 1) / DFT_PCOLS);
+  // one pass over the frequencies: (n_x / 2 + 1) x (column groups) threads, whole warps
+  const unsigned dft_threads = (unsigned)std::min<int64_t>(
+      1024, std::max<int64_t>(64, (((int64_t)(n_x / 2 + 1) * (DFT_PCOLS / DFT_TC) + 31) / 32) * 32));
   g_launches.fetch_add(1, std::memory_order_relaxed);
   if (dtype == QMLB_C128) {
     if (smem > 48 * 1024)
       CUDA_TRY(cudaFuncSetAttribute(k_grid_dft<double>,
                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_grid_dft<double><<<grid, 256, smem, st>>>(static_cast<const double*>(ev), n_x, n_p, n_obs,
+    k_grid_dft<double><<<grid, dft_threads, smem, st>>>(static_cast<const double*>(ev), n_x, n_p, n_obs,
                                                 row_of, static_cast<cx<double>*>(out));
   } else {
     if (smem > 48 * 1024)
       CUDA_TRY(cudaFuncSetAttribute(k_grid_dft<float>,
                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_grid_dft<float><<<grid, 256, smem, st>>>(static_cast<const float*>(ev), n_x, n_p, n_obs,
+    k_grid_dft<float><<<grid, dft_threads, smem, st>>>(static_cast<const float*>(ev), n_x, n_p, n_obs,
                                                row_of, static_cast<cx<float>*>(out));
   }
   CUDA_TRY(cudaGetLastError());
@@ -1325,10 +1328,10 @@ int qmlb_coef_moments(const void* coef, int dtype, const int32_t* rows, int32_t 
   const int64_t total = (int64_t)K * K + 2 * K;
   g_launches.fetch_add(1, std::memory_order_relaxed);
   if (dtype == QMLB_C128)
-    k_coef_moments<double><<<(unsigned)((total * 32 + 255) / 256), 256, 0, st>>>(
+    k_coef_moments<double><<<(unsigned)total, 128, 0, st>>>(
         static_cast<const cx<double>*>(coef), rows, K, n_p, static_cast<double2*>(out));
   else
-    k_coef_moments<float><<<(unsigned)((total * 32 + 255) / 256), 256, 0, st>>>(
+    k_coef_moments<float><<<(unsigned)total, 128, 0, st>>>(
         static_cast<const cx<float>*>(coef), rows, K, n_p, static_cast<double2*>(out));
   CUDA_TRY(cudaGetLastError());
   return QMLB_OK;
