@@ -359,7 +359,12 @@ struct Builder {
 
 // One SUBPASS (plus the folds that follow it).  Returns false when nothing could be done.
 bool Builder::build_step() {
-  uint64_t S = 0, blocked = 0;
+  // blocked: bits of an op that was skipped - everything later on them waits for the next
+  // step.  folded: bits of the permutations collected in this step - later GATES on them see
+  // the new frame (next step), but later permutations still fold now, in program order (a
+  // CX ladder is one chain of folds: blocking them on each other applied one CX per step
+  // and scattered the gates behind the ladder over single-gate sub-passes).
+  uint64_t S = 0, blocked = 0, folded = 0;
   std::vector<int> picked;       // gate ops of the step, program order
   std::vector<int> folds;        // permutations folded after the step
   std::vector<int> pinned;       // k >= 3: register position j -> logical bit
@@ -369,7 +374,7 @@ bool Builder::build_step() {
     if (done[i]) continue;
     const qmlb_op& o = p->ops[i];
     const OpInfo& f = info[i];
-    if (f.bits & blocked) {
+    if ((f.bits & blocked) || (!f.fold && (f.bits & folded))) {
       blocked |= f.bits;
       continue;
     }
@@ -382,7 +387,7 @@ bool Builder::build_step() {
     }
     if (f.fold) {
       folds.push_back((int)i);
-      blocked |= f.bits;  // later ops on these bits see the new frame: next step
+      folded |= f.bits;
       continue;
     }
     // gate: register group, parity rows, slots, matrix area
