@@ -411,17 +411,68 @@ __device__ __forceinline__ void frame_subpass(cx<T>* tile, const cx<T>* mats, co
 // map; PER amplitudes per thread held in registers across the cluster barrier
 // NB > 0: the tile is swizzled (qmlb_frame_ptm.cuh) - the tables then hold swizzled source
 // indices and the destination index is swizzled here
+// htab (the step's lane table, 2^LB entries without bits below LB, LB = log2(elements per
+// 128-byte wavefront)): the thread copies d = d_std ^ htab[d_std & (2^LB - 1)] - the
+// planner's choice of lane directions that keeps gather AND store free of bank conflicts
 template <typename V, int PER, int NB = 0, typename Cluster>
 __device__ __forceinline__ void frame_relayout_v(V* tv, Cluster& cluster, bool clustered,
                                                  unsigned rank, int Tb, int team_bits, int tlane,
                                                  uint32_t cmine, const uint32_t* tab_lo,
-                                                 const uint32_t* tab_hi, int hi_shift = 8) {
+                                                 const uint32_t* tab_hi,
+                                                 const uint32_t* htab = nullptr) {
+  constexpr int hi_shift = 8;
+  constexpr int LB = sizeof(V) == 16 ? 3 : (sizeof(V) == 8 ? 4 : 5);
   const uint32_t tile_mask = (1u << Tb) - 1u;
+  if (htab == nullptr) {
+    // plain form (consecutive destinations per warp): the Pauli-basis kernel, whose swizzled
+    // tile already spreads the gather - there the lane table measured 8 % slower
+    V hold[PER];
+#pragma unroll
+    for (int k = 0; k < PER; ++k) {
+      const uint32_t d = (uint32_t)tlane + ((uint32_t)k << team_bits);
+      const uint32_t src = cmine ^ tab_lo[d & 255u] ^ tab_hi[d >> hi_shift];
+      const uint32_t r = src >> Tb, loc = src & tile_mask;
+      const V* from = tv;
+      if (clustered && r != rank) from = cluster.map_shared_rank(tv, r);
+      hold[k] = from[loc];
+    }
+    if (clustered)
+      cluster.sync();
+    else
+      __syncthreads();
+#pragma unroll
+    for (int k = 0; k < PER; ++k) {
+      uint32_t d = (uint32_t)tlane + ((uint32_t)k << team_bits);
+      if constexpr (NB > 0)
+        d ^= ((d >> NB) ^ (d >> (2 * NB)) ^ (d >> (3 * NB))) & ((1u << NB) - 1u);
+      tv[d] = hold[k];
+    }
+    return;
+  }
+  // Every map here is GF(2)-linear, and tlane + (k << team_bits) = tlane ^ (k << team_bits):
+  // the thread's part (lane table included) is folded into per-thread constants once, the
+  // k part is uniform - one XOR per element and side.  team_bits >= LB: the low LB bits of
+  // every index of this thread are those of its lane (small tiles look the table up per
+  // element instead).
+  const bool hoist = htab != nullptr && team_bits >= LB;
+  const uint32_t base = (uint32_t)tlane ^ (hoist ? htab[tlane & ((1 << LB) - 1)] : 0u);
+  auto swz = [](uint32_t d) {
+    if constexpr (NB > 0)
+      d ^= ((d >> NB) ^ (d >> (2 * NB)) ^ (d >> (3 * NB))) & ((1u << NB) - 1u);
+    return d;
+  };
+  const uint32_t base_sw = swz(base);
+  const uint32_t src0 = cmine ^ tab_lo[base & 255u] ^ tab_hi[base >> hi_shift];
   V hold[PER];
 #pragma unroll
   for (int k = 0; k < PER; ++k) {
-    const uint32_t d = (uint32_t)tlane + ((uint32_t)k << team_bits);
-    const uint32_t src = cmine ^ tab_lo[d & 255u] ^ tab_hi[d >> hi_shift];
+    const uint32_t dk = (uint32_t)k << team_bits;  // uniform
+    uint32_t src = src0 ^ tab_lo[dk & 255u] ^ tab_hi[dk >> hi_shift];
+    if (htab != nullptr && !hoist) {
+      const uint32_t d = ((uint32_t)tlane ^ dk);
+      const uint32_t dd = d ^ htab[d & ((1u << LB) - 1u)];
+      src = cmine ^ tab_lo[dd & 255u] ^ tab_hi[dd >> hi_shift];
+    }
     const uint32_t r = src >> Tb, loc = src & tile_mask;
     const V* from = tv;
     if (clustered && r != rank) from = cluster.map_shared_rank(tv, r);
@@ -433,9 +484,12 @@ __device__ __forceinline__ void frame_relayout_v(V* tv, Cluster& cluster, bool c
     __syncthreads();
 #pragma unroll
   for (int k = 0; k < PER; ++k) {
-    uint32_t d = (uint32_t)tlane + ((uint32_t)k << team_bits);
-    if constexpr (NB > 0)
-      d ^= ((d >> NB) ^ (d >> (2 * NB)) ^ (d >> (3 * NB))) & ((1u << NB) - 1u);
+    const uint32_t dk = (uint32_t)k << team_bits;
+    uint32_t d = base_sw ^ swz(dk);
+    if (htab != nullptr && !hoist) {
+      const uint32_t d0 = ((uint32_t)tlane ^ dk);
+      d = swz(d0 ^ htab[d0 & ((1u << LB) - 1u)]);
+    }
     tv[d] = hold[k];
   }
 }
@@ -444,10 +498,11 @@ template <typename T, int PER, typename Cluster>
 __device__ __forceinline__ void frame_relayout(cx<T>* tile, Cluster& cluster, bool clustered,
                                                unsigned rank, int Tb, int team_bits, int tlane,
                                                uint32_t cmine, const uint32_t* tab_lo,
-                                               const uint32_t* tab_hi) {
+                                               const uint32_t* tab_hi,
+                                               const uint32_t* htab = nullptr) {
   using V = typename std::conditional<sizeof(T) == 8, double2, float2>::type;  // one access
   frame_relayout_v<V, PER>(reinterpret_cast<V*>(tile), cluster, clustered, rank, Tb, team_bits,
-                           tlane, cmine, tab_lo, tab_hi);
+                           tlane, cmine, tab_lo, tab_hi, htab);
 }
 
 // HEAVY = the program holds a dense op on 3 or 4 bits (rare: 2-qubit channels, CCX as a
@@ -546,6 +601,7 @@ __global__ void __launch_bounds__(THREADS, (THREADS == 512 || WIDE) ? 1 : 2)
         for (int g = 0; g < F.outer_bits; ++g)
           if (rank >> g & 1) cmine ^= (uint32_t)st.qcol[Tb + g];
         const bool across = clustered && st.mat_entries == 0;  // else a tile-local shuffle
+        const uint32_t* htab = reinterpret_cast<const uint32_t*>(st.ops);
         if (across)
           cluster.sync();  // tables visible; every CTA of the cluster finished its previous step
         else
@@ -553,14 +609,14 @@ __global__ void __launch_bounds__(THREADS, (THREADS == 512 || WIDE) ? 1 : 2)
         const int per = (int)(tile_n >> F.team_bits);
         if (per == 16) {
           frame_relayout<T, 16>(tile, cluster, across, rank, Tb, F.team_bits, tlane, cmine,
-                                tab_lo, tab_hi);
+                                tab_lo, tab_hi, htab);
         } else if (per == 32) {
           frame_relayout<T, 32>(tile, cluster, across, rank, Tb, F.team_bits, tlane, cmine,
-                                tab_lo, tab_hi);
+                                tab_lo, tab_hi, htab);
         } else {
           if constexpr (WIDE && sizeof(T) == 4)  // complex64, 2^14 amplitudes, 256 threads
             frame_relayout<T, 64>(tile, cluster, across, rank, Tb, F.team_bits, tlane, cmine,
-                                  tab_lo, tab_hi);
+                                  tab_lo, tab_hi, htab);
         }
         __syncthreads();  // the next reader of this tile is this CTA (or a later relayout)
         continue;

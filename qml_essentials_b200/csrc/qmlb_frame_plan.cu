@@ -204,6 +204,7 @@ struct Builder {
   bool resident = false;   // matrices of the whole element stay in shared memory
   bool ptm = false;        // Pauli-basis engine: real state, 4x4 transfer matrices
   int swz_bits = 0;        // log2(elements per shared-memory wavefront) of the swizzled tile
+  int bank_bits = 0;       // log2(elements per 128-byte wavefront): relayout lane choice
   int team_bits = 0;       // log2(threads per tile): item bits above belong to one thread
   std::vector<char> ptm_diag;  // per op: its transfer matrix is provably diagonal
   uint64_t init_xmask = 0;     // physical positions that hold x bits in the initial frame
@@ -239,9 +240,74 @@ struct Builder {
     std::memset(&s, 0, sizeof(s));
     s.kind = QMLB_FSTEP_RELAYOUT;
     for (int j = 0; j < N; ++j) s.qcol[pos[j]] = F.col[j];
+    relayout_lanes(s);
     steps.push_back(s);
     step_ops.emplace_back();
     F.set_permutation(pos);
+  }
+
+  // Which destinations the lanes of one wavefront take.  A thread copies the elements
+  // d = d_std ^ htab[d_std & (2^NB - 1)] (d_std = its consecutive indices; htab entries
+  // have no bits below NB, so this is a bijection of the tile): lane bit i then moves along
+  // u_i = e_i ^ h_i instead of e_i.  The h_i are chosen so that BOTH the destination banks
+  // beta(u_i) and the source banks beta(M u_i) are independent - a conflict-free gather
+  // and a conflict-free store for an arbitrary linear shuffle M (consecutive destinations
+  // made 8-way conflicts of the gather typical: 134 M wavefronts for 17 M ideal in a
+  // k_fstream pass).  The table lives in the step's unused op slots.
+  void relayout_lanes(FrameStep& s) const {
+    uint32_t* htab = reinterpret_cast<uint32_t*>(s.ops);
+    const int NB = bank_bits;
+    static const int lanes_on = [] {
+      const char* v = std::getenv("QMLB_RELAYOUT_LANES");
+      return v ? std::atoi(v) : 1;
+    }();
+    if (!lanes_on || NB <= 0 || T <= NB || T - NB > 12) return;
+    const uint32_t tile_mask = (1u << T) - 1u, dm = (1u << NB) - 1u;
+    auto beta = [&](uint32_t x) {
+      x &= tile_mask;
+      if (!swz_bits) return x & dm;
+      uint32_t w = 0;
+      for (; x; x >>= swz_bits) w ^= x & dm;
+      return w;
+    };
+    auto src_of = [&](uint32_t u) {
+      uint32_t acc = 0;
+      for (int q = 0; q < T; ++q)
+        if (u >> q & 1) acc ^= (uint32_t)s.qcol[q];
+      return acc;
+    };
+    auto insert = [](std::vector<uint32_t>& basis, uint32_t w) {
+      for (uint32_t b : basis)
+        if ((w ^ b) < w) w ^= b;
+      if (!w) return false;
+      basis.push_back(w);
+      std::sort(basis.rbegin(), basis.rend());
+      return true;
+    };
+    std::vector<uint32_t> bd, bs;
+    uint32_t h[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int i = 0; i < NB; ++i) {
+      bool found = false;
+      for (uint32_t c = 0; c < (1u << (T - NB)) && !found; ++c) {
+        const uint32_t u = (1u << i) | (c << NB);
+        std::vector<uint32_t> td = bd, ts = bs;
+        if (insert(td, beta(u)) && insert(ts, beta(src_of(u)))) {
+          bd = td, bs = ts;
+          h[i] = c << NB;
+          found = true;
+        }
+      }
+      if (!found) {  // keep what independence the plain direction still offers
+        insert(bd, beta(1u << i));
+        insert(bs, beta(src_of(1u << i)));
+      }
+    }
+    for (uint32_t l = 0; l < (1u << NB); ++l) {
+      uint32_t m = 0;
+      for (int i = 0; i < NB; ++i)
+        if (l >> i & 1) m ^= h[i];
+      htab[l] = m;
+    }
   }
 
   // Layout change to the permutation frame `pos`.  Across a cluster it is split so that the
@@ -861,6 +927,7 @@ int plan_frame_stream(qmlb_program* p) {
   for (const qmlb_op& o : p->ops)
     if (o.kind == QMLB_OP_MAT && o.k >= 3) return QMLB_ERR_UNSUPPORTED;
   B.N = N;
+  B.bank_bits = p->dtype == QMLB_C128 ? 3 : 4;  // complex elements per 128-byte wavefront
   B.T = T;
   B.G = N - T;
   B.L = L;
@@ -926,6 +993,7 @@ int plan_frame(qmlb_program* p) {
   B.p = p;
   if (!analyse(p, B.info)) return QMLB_ERR_UNSUPPORTED;
   B.N = N;
+  B.bank_bits = p->dtype == QMLB_C128 ? 3 : 4;  // complex elements per 128-byte wavefront
   B.G = std::max(0, N - maxT);
   B.T = N - B.G;
 
@@ -1228,6 +1296,7 @@ int plan_frame_ptm(qmlb_program* p) {
     teams = threads >> team_bits;
   }
   B.swz_bits = p->dtype == QMLB_C128 ? 4 : 5;  // 128-byte wavefront / element size
+  B.bank_bits = 0;  // the swizzled tile keeps the plain relayout form (measured faster)
   B.team_bits = team_bits;
   int row = 0;
   B.premat_off.assign(q.ops.size(), 0);
@@ -1313,6 +1382,9 @@ std::string describe_frame(const qmlb_program* p) {
     if (st.kind == QMLB_FSTEP_RELAYOUT) {
       s += st.mat_entries ? "relayout local" : "relayout";
       for (int b = 0; b < fp.n_bits; ++b) s += " " + std::to_string((unsigned long long)st.qcol[b]);
+      s += " htab";
+      const uint32_t* htab = reinterpret_cast<const uint32_t*>(st.ops);
+      for (int l = 0; l < 32; ++l) s += " " + std::to_string(htab[l]);
       s += "\n";
       continue;
     }

@@ -263,6 +263,7 @@ __global__ void __launch_bounds__(THREADS, MINB)
           if (rank >> g & 1) cmine ^= (uint32_t)st.qcol[Tb + g];
         cmine = (cmine & ~tile_mask) | ptm_swz<NB>(cmine & tile_mask);
         const bool across = clustered && st.mat_entries == 0;
+        const uint32_t* htab = nullptr;  // plain relayout form (see frame_relayout_v)
         if (across)
           cluster.sync();
         else
@@ -270,13 +271,13 @@ __global__ void __launch_bounds__(THREADS, MINB)
         const int per = (int)(tile_n >> F.team_bits);
         if (per == 16)
           frame_relayout_v<T, 16, NB>(tile, cluster, across, rank, Tb, F.team_bits, tlane,
-                                      cmine, tab_lo, tab_hi);
+                                      cmine, tab_lo, tab_hi, htab);
         else if (per == 32)
           frame_relayout_v<T, 32, NB>(tile, cluster, across, rank, Tb, F.team_bits, tlane,
-                                      cmine, tab_lo, tab_hi);
+                                      cmine, tab_lo, tab_hi, htab);
         else if (sizeof(T) == 4 && per == 64)  // floats only: 64 doubles do not fit the registers
           frame_relayout_v<T, sizeof(T) == 4 ? 64 : 16, NB>(tile, cluster, across, rank, Tb, F.team_bits, tlane,
-                                      cmine, tab_lo, tab_hi);
+                                      cmine, tab_lo, tab_hi, htab);
         __syncthreads();
         continue;
       }

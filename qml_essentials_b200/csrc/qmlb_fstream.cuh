@@ -159,22 +159,23 @@ __global__ void __launch_bounds__(THREADS, THREADS == 512 ? 2 : (sizeof(T) == 4 
         __syncthreads();
         cg::cluster_group cluster = cg::this_cluster();
         constexpr int TB = THREADS == 512 ? 9 : 8;
+        const uint32_t* htab = reinterpret_cast<const uint32_t*>(st.ops);
         const int per = (int)(tile_n >> TB);
         if (per == 16)
           frame_relayout<T, 16>(tile, cluster, false, 0u, Tb, TB, (int)threadIdx.x, cmine, tab_lo,
-                                tab_hi);
+                                tab_hi, htab);
         else if (per == 32 && THREADS == 256)
           frame_relayout<T, 32>(tile, cluster, false, 0u, Tb, TB, (int)threadIdx.x, cmine, tab_lo,
-                                tab_hi);
+                                tab_hi, htab);
         else if (per == 8)
           frame_relayout<T, 8>(tile, cluster, false, 0u, Tb, TB, (int)threadIdx.x, cmine, tab_lo,
-                               tab_hi);
+                               tab_hi, htab);
         else if (per == 4)
           frame_relayout<T, 4>(tile, cluster, false, 0u, Tb, TB, (int)threadIdx.x, cmine, tab_lo,
-                               tab_hi);
+                               tab_hi, htab);
         else if (per == 2)
           frame_relayout<T, 2>(tile, cluster, false, 0u, Tb, TB, (int)threadIdx.x, cmine, tab_lo,
-                               tab_hi);
+                               tab_hi, htab);
         __syncthreads();
         continue;
       }

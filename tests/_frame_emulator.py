@@ -28,6 +28,7 @@ def parse(text):
     geo = {"passes": []}
     steps = []
     lanes = []
+    relayouts = []
     for line in lines[1:]:
         tok = line.split()
         if tok[0] == "frame":
@@ -45,7 +46,10 @@ def parse(text):
             continue
         if tok[0] == "relayout":
             local = tok[1] == "local"
-            steps.append(("relayout", [int(x) for x in tok[(2 if local else 1):]], local))
+            ih = tok.index("htab") if "htab" in tok else len(tok)
+            steps.append(("relayout", [int(x) for x in tok[(2 if local else 1):ih]], local))
+            relayouts.append(dict(qcol=steps[-1][1], local=local,
+                                  htab=[int(x) for x in tok[ih + 1:]]))
             continue
         assert tok[0] == "subpass"
         ip, ie, ipar, io = (tok.index(k) for k in ("pivots", "eoff", "par", "ops"))
@@ -70,7 +74,48 @@ def parse(text):
             if steps[-1][5] >= 128:
                 _check_ptm_fast(steps[-1][5], ops, lanes[-1]["sg"])
     geo["lanes"] = lanes
+    geo["relayouts"] = relayouts
     return geo, steps
+
+
+def relayout_wavefronts(geo, elem_bytes, swizzled):
+    """Shared-memory wavefronts (gather + store) of the tile-local relayouts relative to the
+    ideal, with the planner's lane table (thread copies d = d_std ^ htab[d_std & mask])."""
+    nb = {16: 3, 8: 4, 4: 5}[elem_bytes]
+    per = 1 << nb
+    T = geo["tile_bits"]
+    tmask = (1 << T) - 1
+
+    def bank(x):
+        x &= tmask
+        if not swizzled:
+            return x & (per - 1)
+        b = 0
+        while x:
+            b ^= x & (per - 1)
+            x >>= nb
+        return b
+
+    got = ideal = 0
+    for r in geo["relayouts"]:
+        assert all(h & (per - 1) == 0 for h in r["htab"][:per]), "htab keeps the lane bits"
+        for start in range(0, min(1 << T, 1024), per):
+            ds = [d ^ r["htab"][d & (per - 1)] for d in range(start, start + per)]
+            assert sorted(d & (per - 1) for d in ds) == list(range(per))
+            srcs = []
+            for d in ds:
+                s_ = 0
+                for q in range(T):
+                    if d >> q & 1:
+                        s_ ^= r["qcol"][q]
+                srcs.append(s_ & tmask)
+            for addrs in (ds, srcs):
+                banks = {}
+                for a in addrs:
+                    banks.setdefault(bank(a), set()).add(a)
+                got += max(len(v) for v in banks.values())
+                ideal += 1
+    return got / max(ideal, 1)
 
 
 def check_item_maps(geo):

@@ -159,6 +159,18 @@ def test_pauli_basis_schedules(lib, n, L, ct, typ, noise):
     assert err < 1e-12
 
 
+def test_relayout_lane_tables(lib, monkeypatch):
+    """Tile-local relayouts of the complex engines: the planner's lane table makes gather and
+    store conflict-free in the bank model (consecutive destinations: 2-3.6x the ideal)."""
+    ex, err = _both(lib, 14, 3, "Hardware_Efficient", "expval", None, B_I=1, B_P=1)
+    geo, _ = fe.parse(ex.steps[0])
+    assert geo["relayouts"] and fe.relayout_wavefronts(geo, 16, swizzled=False) < 1.1
+    for r in geo["relayouts"]:
+        r["htab"] = [0] * 32
+    assert fe.relayout_wavefronts(geo, 16, swizzled=False) > 1.5
+    assert err < 1e-12
+
+
 def test_config4_pauli_basis_shape(lib):
     """BASELINE config 4 with <Z> output: 512 KiB of real coefficients per evaluation -> a
     cluster of 4 CTAs (the complex form needs 8), 512 threads with two items each."""

@@ -72,6 +72,12 @@ def main():
                       inputs=np.linspace(-np.pi, np.pi, int(arg or 4096)).reshape(-1, 1),
                       noise_params={"Depolarizing": 0.01, "AmplitudeDamping": 0.02})
             types = ["expval", "density"]
+        elif name == "sv":  # sv:N:BATCH  statevector circuit of N qubits (frame engine sizes)
+            n, _, bs = arg.partition(":")
+            config.set_precision("complex128")
+            m = Model(int(n), 3, "Hardware_Efficient")
+            kw = dict(params=rng.uniform(0, 2 * np.pi, (int(bs or 256), *m._params_shape)))
+            types = ["expval"]
         else:
             continue
         for typ in types:
