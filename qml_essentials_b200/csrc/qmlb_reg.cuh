@@ -239,7 +239,10 @@ __host__ inline bool reg_supports(const qmlb_op& op, const double* consts, int n
 //   cls[slot]: 0 = slot has no hoisted factors here, 1 = FAST (row = fast index p, div = 1),
 //              2 = SLOW (row = slow index i = b / BP), 3 = CONST (mod = 1: row 0)
 struct RegTile {
-  int32_t tp_bits, ti_bits;
+  int32_t tp_bits, ti_bits;  // fast / slow rows per CTA tile (log2); 2^(tp_bits + ti_bits) =
+                             // 128 * reps: a thread runs `reps` evaluations (slow rows
+                             // ti, ti + 2^ti_bits / reps, ...) against the same staged tables
+  int32_t reps, pad;
   int64_t n_ptiles, BP, BI;
   uint8_t cls[QMLB_MAX_ARGS];
 };
@@ -300,13 +303,18 @@ __global__ void __launch_bounds__(128, MINB ? MINB : reg_min_ctas<T, N>())
   cx<T>* s_tab = reinterpret_cast<cx<T>*>(
       reg_smem + ((sizeof(RegOp) * P.n_ops + 8 * (size_t)P.n_ops + 15) & ~size_t(15)));
   int row_f = 0, row_s = 0;  // this thread's rows in the staged FAST / SLOW factors
+  int rows_f = 0, rows_s = 0, ti_step = 0, n_rep = 1;
+  int64_t p0 = 0, i0 = 0;
   if constexpr (TILED) {
     const int TP = 1 << Tl.tp_bits, TI = 1 << Tl.ti_bits;
     const int64_t cp = (int64_t)blockIdx.x % Tl.n_ptiles, ci = (int64_t)blockIdx.x / Tl.n_ptiles;
-    const int tp = threadIdx.x & (TP - 1), ti = threadIdx.x >> Tl.tp_bits;
-    const int64_t p0 = cp * TP, i0 = ci * TI;
-    const int rows_f = (int)(Tl.BP - p0 < TP ? Tl.BP - p0 : TP);
-    const int rows_s = (int)(Tl.BI - i0 < TI ? Tl.BI - i0 : TI);
+    p0 = cp * TP;
+    i0 = ci * TI;
+    rows_f = (int)(Tl.BP - p0 < TP ? Tl.BP - p0 : TP);
+    rows_s = (int)(Tl.BI - i0 < TI ? Tl.BI - i0 : TI);
+    n_rep = Tl.reps;
+    ti_step = TI / Tl.reps;
+    row_f = threadIdx.x & (TP - 1);
     if (threadIdx.x == 0) {
       int acc = 0;
       for (int o = 0; o < P.n_ops; ++o) {
@@ -343,12 +351,18 @@ __global__ void __launch_bounds__(128, MINB ? MINB : reg_min_ctas<T, N>())
     asm volatile("cp.async.commit_group;\n" ::);
     asm volatile("cp.async.wait_group 0;\n" ::: "memory");
     __syncthreads();
-    if (tp >= rows_f || ti >= rows_s) return;
-    bl = (i0 + ti) * Tl.BP + p0 + tp;
-    row_f = tp;
-    row_s = ti;
+    if (row_f >= rows_f) return;
   } else {
     if (bl >= R.batch) return;
+  }
+  // TILED: `reps` evaluations per thread against the same staged tables (the staging
+  // prologue - two barriers and an L2 round trip - is paid once for all of them)
+#pragma unroll 1
+  for (int rep = 0; rep < n_rep; ++rep) {
+  if constexpr (TILED) {
+    row_s = (int)(threadIdx.x >> Tl.tp_bits) + rep * ti_step;
+    if (row_s >= rows_s) break;
+    bl = (i0 + row_s) * Tl.BP + p0 + row_f;
   }
   const int64_t b = bl + R.batch_offset;
 
@@ -515,6 +529,7 @@ __global__ void __launch_bounds__(128, MINB ? MINB : reg_min_ctas<T, N>())
       o[j] = acc;
     }
   }
+  }  // rep
 }
 
 }  // namespace qmlb

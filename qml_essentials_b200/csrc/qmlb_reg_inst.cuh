@@ -57,6 +57,16 @@ static bool reg_tile_plan(const qmlb_program* p, const RunArgs& R, RegTile& Tl, 
     tp_bits = pow2ceil_bits(BP);
     ti_bits = 7 - tp_bits;
   }
+  // two evaluations per thread when the slow axis is long enough (QMLB_REG_REPS=1: one)
+  static const int want_reps = [] {
+    const char* v = std::getenv("QMLB_REG_REPS");
+    return v ? std::atoi(v) : 2;
+  }();
+  Tl.reps = 1;
+  if (want_reps == 2 && BI >= (int64_t(2) << ti_bits)) {
+    Tl.reps = 2;
+    ti_bits += 1;
+  }
   Tl.tp_bits = tp_bits;
   Tl.ti_bits = ti_bits;
   Tl.BP = BP;

@@ -233,6 +233,17 @@ __global__ void __launch_bounds__(128, PLAIN ? 8 : 2)
   cx<T>* dst = out + (size_t)bl * mat_row + mo.off;
   const RowsDirect rows{A, bl + A.batch_offset};
   if constexpr (PLAIN) {
+    // 2x2 sources (every statevector gate): registers only - the generic path below keeps
+    // its matrices in local memory
+    const qmlb_source s0 = P.src[mo.src];
+    if (s0.k == 1 && (s0.kind == QMLB_SRC_TRIG || s0.kind == QMLB_SRC_CHAIN ||
+                      s0.kind == QMLB_SRC_PRE)) {
+      cx<T> m[4];
+      eval_2x2<T>(P, A, rows, mo.src, m);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) dst[i] = m[i];
+      return;
+    }
     eval_source_mem<T>(P, A, rows, mo.src, dst);
     return;
   }
