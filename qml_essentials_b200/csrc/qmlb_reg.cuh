@@ -247,6 +247,15 @@ struct RegTile {
   uint8_t cls[QMLB_MAX_ARGS];
 };
 
+// The op stream in the KERNEL PARAMETERS (constant bank) for programs of up to REG_PARAM_OPS
+// ops: op records are then uniform data, the dispatch on kind / bit becomes uniform
+// branches (no BSSY / BSYNC reconvergence code, no shared-memory load in front of every
+// gate).  PO = 1 variants of k_reg take the ops from here instead of the staged copy.
+constexpr int REG_PARAM_OPS = 72;
+struct RegParamOps {
+  RegOp ops[REG_PARAM_OPS];
+};
+
 template <typename T>
 __device__ __forceinline__ void reg_cp_async(cx<T>* smem, const cx<T>* gmem) {
   const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
@@ -281,9 +290,10 @@ constexpr int reg_min_ctas() {
 // MINB: resident CTAs per SM the variant is compiled for (0 = reg_min_ctas default).  The
 // complex128 n = 4 kernel exists at 2 (210 registers, no spills) and 3 (168 registers, 124
 // bytes of spills, 12 instead of 8 warps per SM).
-template <typename T, int N, int MINB = 0, bool TILED = false>
+template <typename T, int N, int MINB = 0, bool TILED = false, bool PO = false>
 __global__ void __launch_bounds__(128, MINB ? MINB : reg_min_ctas<T, N>())
-    k_reg(DevProg P, RunArgs R, int mode, int n_args, void* __restrict__ out, const RegTile Tl) {
+    k_reg(DevProg P, RunArgs R, int mode, int n_args, void* __restrict__ out, const RegTile Tl,
+          const __grid_constant__ RegParamOps Po) {
   constexpr int D = 1 << N;
   // op stream -> shared memory (all threads take part before anyone leaves)
   extern __shared__ __align__(16) unsigned char reg_smem[];
@@ -318,7 +328,7 @@ __global__ void __launch_bounds__(128, MINB ? MINB : reg_min_ctas<T, N>())
     if (threadIdx.x == 0) {
       int acc = 0;
       for (int o = 0; o < P.n_ops; ++o) {
-        const RegOp d = s_ops[o];
+        const RegOp d = PO ? Po.ops[o] : s_ops[o];
         const bool use = d.n >= 1 && R.pre_on[d.slot0] && (d.n == 1 || R.pre_on[d.slot1]);
         for (int j = 0; j < 2; ++j) {
           int off = -1;
@@ -333,7 +343,7 @@ __global__ void __launch_bounds__(128, MINB ? MINB : reg_min_ctas<T, N>())
     }
     __syncthreads();
     for (int o = 0; o < P.n_ops; ++o) {
-      const RegOp d = s_ops[o];
+      const RegOp d = PO ? Po.ops[o] : s_ops[o];
       for (int j = 0; j < 2; ++j) {
         const int off = s_off[2 * o + j];
         if (off < 0) continue;
@@ -408,7 +418,7 @@ __global__ void __launch_bounds__(128, MINB ? MINB : reg_min_ctas<T, N>())
   fetch(0);
 
   for (int o = 0; o < P.n_ops; ++o) {
-    const RegOp op = ops[o];
+    const RegOp op = PO ? Po.ops[o] : ops[o];
     cx<T> m[4];
     bool have_m = nfn > 0;
     if constexpr (TILED) {

@@ -104,28 +104,41 @@ static cudaError_t launch_n(const qmlb_program* p, const RunArgs& R, void* dst, 
     if (smem <= 96 * 1024) {
       const int64_t n_itiles = (Tl.BI + (int64_t(1) << Tl.ti_bits) - 1) >> Tl.ti_bits;
       const unsigned grid = (unsigned)(Tl.n_ptiles * n_itiles);
+      static const int want_po = [] {
+        const char* v = std::getenv("QMLB_REG_PARAM_OPS");
+        return v ? std::atoi(v) : 1;
+      }();
+      RegParamOps po{};
+      const bool use_po = want_po && p->dev.n_ops <= REG_PARAM_OPS;
+      if (use_po)
+        std::memcpy(po.ops, p->reg_ops_host.data(), p->reg_ops_host.size() * sizeof(RegOp));
       auto launch = [&](auto kern) {
         static bool attr = false;
         if (!attr) {
           cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
           attr = true;
         }
-        kern<<<grid, threads, smem, st>>>(p->dev, R, p->reg_mode, p->max_arg + 1, dst, Tl);
+        kern<<<grid, threads, smem, st>>>(p->dev, R, p->reg_mode, p->max_arg + 1, dst, Tl, po);
       };
-      if (three)
-        launch(k_reg<QMLB_T, N, MB3, true>);
+      if (three && use_po)
+        launch(k_reg<QMLB_T, N, MB3, true, true>);
+      else if (three)
+        launch(k_reg<QMLB_T, N, MB3, true, false>);
+      else if (use_po)
+        launch(k_reg<QMLB_T, N, 0, true, true>);
       else
-        launch(k_reg<QMLB_T, N, 0, true>);
+        launch(k_reg<QMLB_T, N, 0, true, false>);
       return cudaGetLastError();
     }
   }
   const unsigned grid = (unsigned)((R.batch + threads - 1) / threads);
+  RegParamOps none{};
   if (three)
     k_reg<QMLB_T, N, MB3><<<grid, threads, ops_bytes, st>>>(p->dev, R, p->reg_mode,
-                                                             p->max_arg + 1, dst, Tl);
+                                                             p->max_arg + 1, dst, Tl, none);
   else
     k_reg<QMLB_T, N><<<grid, threads, ops_bytes, st>>>(p->dev, R, p->reg_mode, p->max_arg + 1,
-                                                        dst, Tl);
+                                                        dst, Tl, none);
   return cudaGetLastError();
 }
 
