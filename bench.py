@@ -695,15 +695,17 @@ def main():
                 "kernel": f"k_reg<{'double' if prec64 else 'float'},4>",
                 "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
                 "frac": achieved_tf / peak_tf,
-                "traffic": 1666304 if prec64 else None,
+                "traffic": 1667584 if prec64 else None,
                 "traffic_source": "ncu --set full capture of this kernel, not measured in "
-                                  "this run (profiles/r1_final_kreg_v5_smem_ops_full_summary"
-                                  ".txt): parameters + hoisted tables in; the 8.6 MB of "
-                                  "results stay in L2",
+                                  "this run (profiles/r2_final_kreg_digest.txt: dram read "
+                                  "1.67 MB, write 0): parameters + hoisted tables in; the "
+                                  "8.6 MB of results stay in L2",
                 "kernel_ms": kern_ms,
                 "note": "achieved = algorithmic (unfused, dense) 26624 flop/eval x 270336 "
                         "evals / CUDA-event launch time; peak = qmlb_fma_peak measured on "
-                        "this GPU (no FMA figure in MEASURED_PEAKS.json)",
+                        "this GPU (no FMA figure in MEASURED_PEAKS.json).  The kernel fuses "
+                        "and hoists, so it EXECUTES ~4x fewer flops than the algorithmic "
+                        "count (frac can exceed 1); its FP64 pipe is 29 % busy (ncu)",
             },
         }
         if gp is not None and "error" not in gp:
