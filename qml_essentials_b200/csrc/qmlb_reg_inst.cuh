@@ -112,22 +112,28 @@ static cudaError_t launch_n(const qmlb_program* p, const RunArgs& R, void* dst, 
       const bool use_po = want_po && p->dev.n_ops <= REG_PARAM_OPS;
       if (use_po)
         std::memcpy(po.ops, p->reg_ops_host.data(), p->reg_ops_host.size() * sizeof(RegOp));
-      auto launch = [&](auto kern) {
-        static bool attr = false;
+      // every instantiation has the same pointer type, so the "attribute set" flags are
+      // kept per variant explicitly (one flag inside a generic lambda would be shared)
+      static bool attr_set[4] = {false, false, false, false};
+      cudaError_t attr_err = cudaSuccess;
+      auto launch = [&](auto kern, bool& attr) {
         if (!attr) {
-          cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
-          attr = true;
+          attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          96 * 1024);
+          attr = attr_err == cudaSuccess;
         }
-        kern<<<grid, threads, smem, st>>>(p->dev, R, p->reg_mode, p->max_arg + 1, dst, Tl, po);
+        if (attr_err == cudaSuccess)
+          kern<<<grid, threads, smem, st>>>(p->dev, R, p->reg_mode, p->max_arg + 1, dst, Tl, po);
       };
       if (three && use_po)
-        launch(k_reg<QMLB_T, N, MB3, true, true>);
+        launch(k_reg<QMLB_T, N, MB3, true, true>, attr_set[0]);
       else if (three)
-        launch(k_reg<QMLB_T, N, MB3, true, false>);
+        launch(k_reg<QMLB_T, N, MB3, true, false>, attr_set[1]);
       else if (use_po)
-        launch(k_reg<QMLB_T, N, 0, true, true>);
+        launch(k_reg<QMLB_T, N, 0, true, true>, attr_set[2]);
       else
-        launch(k_reg<QMLB_T, N, 0, true, false>);
+        launch(k_reg<QMLB_T, N, 0, true, false>, attr_set[3]);
+      if (attr_err != cudaSuccess) return attr_err;
       return cudaGetLastError();
     }
   }

@@ -264,3 +264,45 @@ def test_device_partial_trace_and_marginals_equal_host_helpers(precision):
                 got = sub(inputs=x, execution_type="probs", noise_params=nz)
                 want = js.marginalize_probs(pr.reshape(5, -1), 6, keep)
                 assert np.abs(got.reshape(5, -1) - want).max() < tol, (keep, nz)
+
+
+@pytest.mark.parametrize("precision", ["complex128", "complex64"])
+@pytest.mark.parametrize("n,L,ct,B_I,B_P,typ", [
+    (4, 4, "Hardware_Efficient", 37, 19, "expval"),   # partial tiles on both axes, 2 reps
+    (4, 12, "Hardware_Efficient", 9, 5, "probs"),     # > 72 ops: op stream from shared memory
+    (3, 2, "Circuit_19", 1, 300, "expval"),           # one grid point: fast axis only
+    (2, 1, "Circuit_19", 130, 1, "state"),            # one parameter set (BASELINE config 1)
+    (5, 2, "Strongly_Entangling", 17, 33, "expval"),  # n = 5: 32 amplitudes per thread
+])
+def test_register_kernel_tile_shapes(monkeypatch, precision, n, L, ct, B_I, B_P, typ):
+    """k_reg's CTA-tiled factor staging (16 parameter sets x 8 or 16 grid points per CTA,
+    tables in shared memory, one or two evaluations per thread, op stream in the kernel
+    parameters or in shared memory) on batch shapes that do not fill the tiles - against
+    the oracle, and against the untiled path (QMLB_REG_TILED=0: factors through L2)."""
+    err = pc.case_model(n, L, ct, B_I, B_P, typ, precision=precision)
+    assert err < pc.TOL[precision]
+    rng = np.random.default_rng(5)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        m = Model(n, L, ct, precision=precision)
+        params = rng.uniform(0, 2 * np.pi, (B_P, *m._params_shape))
+        inputs = rng.uniform(-1, 1, (B_I, 1))
+        a = np.asarray(m(params=params, inputs=inputs, execution_type=typ))
+    # a fresh process reads the environment switch at its first launch
+    code = (
+        "import sys, warnings, numpy as np; sys.path.insert(0, %r); warnings.simplefilter('ignore');"
+        "from qml_essentials_b200.model import Model;"
+        "rng = np.random.default_rng(5); m = Model(%d, %d, %r, precision=%r);"
+        "params = rng.uniform(0, 2 * np.pi, (%d, *m._params_shape));"
+        "inputs = rng.uniform(-1, 1, (%d, 1));"
+        "np.save(sys.argv[1], np.asarray(m(params=params, inputs=inputs, execution_type=%r)))"
+    ) % (ROOT, n, L, ct, precision, B_P, B_I, typ)
+    import tempfile
+
+    with tempfile.TemporaryDirectory() as d:
+        out = os.path.join(d, "b.npy")
+        env = dict(os.environ, QMLB_REG_TILED="0")
+        subprocess.run([sys.executable, "-c", code, out], check=True, env=env, timeout=300)
+        b = np.load(out)
+    assert a.shape == b.shape
+    assert np.abs(a - b).max() < (1e-13 if precision == "complex128" else 1e-6)
