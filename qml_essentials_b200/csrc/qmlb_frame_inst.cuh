@@ -15,6 +15,10 @@ static cudaError_t launch_frame_t(const qmlb_program* p, const RunArgs& R, const
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
+  // the relayout keeps 2^T / team elements per thread in registers: only these variants exist
+  const int per = (1 << F.tile_bits) >> F.team_bits;
+  const bool per_ok = per == 16 || per == 32 || (per == 64 && WIDE && sizeof(QMLB_T) == 4);
+  if (!per_ok) return cudaErrorInvalidConfiguration;
   const int csize = 1 << F.outer_bits;
   const int64_t units = (R.batch + F.teams - 1) / F.teams;  // clusters (CTAs) of work
   cudaLaunchConfig_t cfg{};

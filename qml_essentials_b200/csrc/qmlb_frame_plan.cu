@@ -987,7 +987,12 @@ int plan_frame_stream(qmlb_program* p) {
 int plan_frame(qmlb_program* p) {
   const int N = p->n_bits;
   const size_t cs = p->dtype == QMLB_C128 ? 16 : 8;
-  const int maxT = p->dtype == QMLB_C128 ? 13 : 14;
+  // programs with a dense op on 3-4 bits run the HEAVY kernel variant (128 registers): its
+  // relayout holds at most 32 elements per thread, i.e. tiles of 2^13 also in complex64
+  bool heavy = false;
+  for (const qmlb_op& o : p->ops)
+    if (o.kind == QMLB_OP_MAT && o.k >= 3) heavy = true;
+  const int maxT = (p->dtype == QMLB_C128 || heavy) ? 13 : 14;
   if (N < 6 || N > maxT + 3) return QMLB_ERR_UNSUPPORTED;
   Builder B;
   B.p = p;

@@ -15,6 +15,9 @@ static cudaError_t launch_ptm_t(const qmlb_program* p, const RunArgs& R, const F
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
+  const int per = (1 << F.tile_bits) >> F.team_bits;  // relayout registers per thread
+  if (!(per == 16 || per == 32 || (per == 64 && sizeof(QMLB_T) == 4)))
+    return cudaErrorInvalidConfiguration;
   const int csize = 1 << F.outer_bits;
   const int64_t units = (R.batch + F.teams - 1) / F.teams;
   cudaLaunchConfig_t cfg{};

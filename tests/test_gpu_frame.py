@@ -58,6 +58,20 @@ def test_config4_full_size_vs_oracle(typ):
     assert err < 1e-10
 
 
+@pytest.mark.parametrize("precision", ["complex128", "complex64"])
+@pytest.mark.parametrize("n,L,ct,typ", [
+    (7, 2, "Strongly_Entangling", "probs"), (7, 1, "Circuit_10", "density"),
+    (8, 1, "Circuit_19", "probs"), (6, 2, "Circuit_5", "density"),
+])
+def test_two_qubit_channels_on_cluster_sized_states(precision, n, L, ct, typ):
+    """16x16 superoperators (MultiQubitDepolarizing) run the HEAVY kernel variant, whose
+    relayout holds at most 32 amplitudes per thread: complex64 must not take the
+    2^14-amplitude tile (found by tools/fuzz_gpu.py: the relayout was silently skipped)."""
+    noise = {"BitFlip": 0.01, "MultiQubitDepolarizing": 0.02}
+    err = pc.case_model(n, L, ct, 2, 2, typ, noise, precision=precision)
+    assert err < pc.TOL[precision]
+
+
 def test_frame_equals_streamed_strategy(monkeypatch):
     """The same circuits through the HBM-streaming kernels (QMLB_FRAME=0) and the frame
     engine: independent schedules, same numbers."""
