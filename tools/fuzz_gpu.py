@@ -25,21 +25,27 @@ NOISES = [None, None, {"Depolarizing": 0.02}, {"AmplitudeDamping": 0.05, "PhaseD
 def main():
     n_cases = int(sys.argv[1]) if len(sys.argv) > 1 else 120
     rng = np.random.default_rng(int(sys.argv[2]) if len(sys.argv) > 2 else 7)
+    big = len(sys.argv) > 3 and sys.argv[3] == "big"  # statevectors of 12..19 qubits
     names = [c.__name__ for c in Ansaetze.get_available()]
     names = [c for c in names if c not in ("No_Ansatz", "GHZ")]  # no parameters to batch
     worst = []
     fails = 0
     for case in range(n_cases):
         ct = names[rng.integers(len(names))]
-        noise = NOISES[rng.integers(len(NOISES))]
+        noise = None if big else NOISES[rng.integers(len(NOISES))]
         nmax = 8 if noise else 13
-        n = int(rng.integers(2, nmax + 1))
-        L = int(rng.integers(1, 4))
+        n = int(rng.integers(12, 20)) if big else int(rng.integers(2, nmax + 1))
+        L = int(rng.integers(1, 3 if big else 4))
         typ = ["expval", "probs", "density" if (noise or n <= 7) else "state", "state"][rng.integers(4)]
         if noise and typ == "state":
             typ = "density"
         prec = ["complex128", "complex64"][rng.integers(2)]
         B_I, B_P = int(rng.integers(1, 6)), int(rng.integers(1, 5))
+        if big:
+            B_I, B_P = int(rng.integers(1, 3)), 1
+            typ = ["expval", "probs", "state"][rng.integers(3)]
+        elif n <= 5 and not noise:  # register kernel: batch shapes that cut its CTA tiles
+            B_I, B_P = int(rng.integers(1, 41)), int(rng.integers(1, 41))
         tag = f"{ct} n={n} L={L} {typ} {prec} noise={sorted(noise) if noise else None} B=({B_I},{B_P})"
         try:
             with warnings.catch_warnings():
