@@ -291,10 +291,18 @@ __global__ void __launch_bounds__(THREADS, MINB)
         {
           const uint4 ip4 = *reinterpret_cast<const uint4*>(sx->ipos);
           const uint32_t ipw[4] = {ip4.x, ip4.y, ip4.z, ip4.w};
+          constexpr int TBC = THREADS == 1024 ? 10 : THREADS == 512 ? 9 : THREADS == 256 ? 8
+                              : THREADS == 128 ? 7 : THREADS == 64 ? 6 : 5;
+          if (teams == 1) {  // one tile per CTA: the lane bits are those of the thread index
 #pragma unroll
-          for (int b = 0; b < 12; ++b)
-            if (b < F.team_bits)
+            for (int b = 0; b < TBC; ++b)
               base0 |= (((uint32_t)tlane >> b) & 1u) << ((ipw[b >> 2] >> (8 * (b & 3))) & 31u);
+          } else {
+#pragma unroll
+            for (int b = 0; b < 12; ++b)
+              if (b < F.team_bits)
+                base0 |= (((uint32_t)tlane >> b) & 1u) << ((ipw[b >> 2] >> (8 * (b & 3))) & 31u);
+          }
         }
         {
           int c = 0;
