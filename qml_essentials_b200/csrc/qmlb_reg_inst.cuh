@@ -87,15 +87,16 @@ static cudaError_t launch_n(const qmlb_program* p, const RunArgs& R, void* dst, 
   const int threads = 128;
   g_launches.fetch_add(1, std::memory_order_relaxed);
   const size_t ops_bytes = (size_t)std::min<int>(p->dev.n_ops, REG_SMEM_OPS) * sizeof(RegOp);
-  // complex128, n = 4: three resident CTAs per SM (168 registers, 12 warps) measured 5.6 %
-  // faster than two (210 registers, 8 warps): 0.214 vs 0.227 ms on config 2;
-  // QMLB_REG_CTAS=2 selects the latter
+  // complex128, n = 4: more resident warps beat fewer spills - two CTAs per SM (210
+  // registers) 0.227 ms, three (168) 0.214 ms on config 2 in the untiled form; in the tiled
+  // form with parameter ops, four (128 registers, 176 bytes of spills) 0.1855 vs three 0.1895.
+  // QMLB_REG_CTAS=2 / 3 select the others.
   static const int want3 = [] {
     const char* v = std::getenv("QMLB_REG_CTAS");
-    return v ? std::atoi(v) : 3;
+    return v ? std::atoi(v) : 4;
   }();
   constexpr int MB3 = (sizeof(QMLB_T) == 8 && N == 4) ? 3 : 0;
-  const bool three = sizeof(QMLB_T) == 8 && N == 4 && want3 == 3;
+  const bool three = sizeof(QMLB_T) == 8 && N == 4 && want3 >= 3;
   RegTile Tl{};
   size_t tab_bytes = 0;
   if (reg_tile_plan(p, R, Tl, tab_bytes)) {
@@ -125,7 +126,10 @@ static cudaError_t launch_n(const qmlb_program* p, const RunArgs& R, void* dst, 
         if (attr_err == cudaSuccess)
           kern<<<grid, threads, smem, st>>>(p->dev, R, p->reg_mode, p->max_arg + 1, dst, Tl, po);
       };
-      if (three && use_po)
+      if (sizeof(QMLB_T) == 8 && N == 4 && want3 == 4 && use_po) {
+        static bool a4 = false;
+        launch(k_reg<QMLB_T, N, (sizeof(QMLB_T) == 8 && N == 4) ? 4 : 0, true, true>, a4);
+      } else if (three && use_po)
         launch(k_reg<QMLB_T, N, MB3, true, true>, attr_set[0]);
       else if (three)
         launch(k_reg<QMLB_T, N, MB3, true, false>, attr_set[1]);
