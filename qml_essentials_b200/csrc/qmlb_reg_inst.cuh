@@ -126,9 +126,14 @@ static cudaError_t launch_n(const qmlb_program* p, const RunArgs& R, void* dst, 
         if (attr_err == cudaSuccess)
           kern<<<grid, threads, smem, st>>>(p->dev, R, p->reg_mode, p->max_arg + 1, dst, Tl, po);
       };
-      if (sizeof(QMLB_T) == 8 && N == 4 && want3 == 4 && use_po) {
+      static const int f4 = [] {
+        const char* v = std::getenv("QMLB_REG_CTAS_F32");
+        return v ? std::atoi(v) : 4;
+      }();
+      // complex64 n = 4: four CTAs (128 registers) 0.135 ms, three 0.159, five 0.136, six 0.168
+      if (N == 4 && use_po && ((sizeof(QMLB_T) == 8 && want3 == 4) || (sizeof(QMLB_T) == 4 && f4 == 4))) {
         static bool a4 = false;
-        launch(k_reg<QMLB_T, N, (sizeof(QMLB_T) == 8 && N == 4) ? 4 : 0, true, true>, a4);
+        launch(k_reg<QMLB_T, N, N == 4 ? 4 : 0, true, true>, a4);
       } else if (three && use_po)
         launch(k_reg<QMLB_T, N, MB3, true, true>, attr_set[0]);
       else if (three)
