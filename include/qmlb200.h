@@ -184,13 +184,20 @@ int qmlb_program_destroy(qmlb_program* prog);
  * writes a text description into buf - "strategy S", then for streamed programs one
  * line per fused gate pass: "pass flags F group b0 b1 .. ops i:kind:bits ..." where i is the
  * index of the op in desc->ops and bits are register positions (state bits for diagonal
- * ops).  Used by the CPU test-suite to check the pass scheduler. */
+ * ops); for the frame engines (strategies 3 - 5) a "frame ..." geometry line and one line
+ * per step ("subpass ..." / "relayout ...", format in qmlb_frame_plan.cu:describe_frame).
+ * Used by the CPU test-suite to check the schedulers (tests/_frame_emulator.py replays the
+ * frame-engine steps in NumPy). */
 int qmlb_plan_describe(const qmlb_program_desc* desc, char* buf, size_t buflen);
 
 /* strategy: 0 = register-resident (one thread per circuit), 1 = shared-memory
  * resident (one warp / CTA per circuit), 2 = streamed fused gate passes over HBM
- * (register groups of 4 state bits, one launch per pass).
- * n_passes: state passes per run (strategy 2), n_device_ops: ops after fusion. */
+ * (register groups of 4 state bits, one launch per pass), 3 = on-chip frame engine (state
+ * in shared memory / cluster DSMEM for the whole tape), 4 = streaming frame engine (tile
+ * passes over an HBM-resident state, TMA bulk copies), 5 = Pauli-basis frame engine (noisy
+ * density programs as real Pauli-coefficient vectors).
+ * n_passes: state passes per run (strategies 2, 4) or steps of the on-chip step program
+ * (strategies 3, 5); n_device_ops: ops after fusion. */
 int qmlb_program_info(const qmlb_program* prog, int32_t* strategy, int32_t* n_passes,
                       int32_t* n_device_ops);
 
