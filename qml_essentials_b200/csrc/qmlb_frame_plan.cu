@@ -202,6 +202,10 @@ struct Builder {
   int N, T, G;
   int mat_cap;
   bool resident = false;   // matrices of the whole element stay in shared memory
+  // streaming mode: only the matrices of the current HBM pass are staged (once per element
+  // and pass), numbered compactly in the order the pass uses them
+  bool pass_compact = false;
+  int pass_used = 0, pass_used_max = 0;
   bool ptm = false;        // Pauli-basis engine: real state, 4x4 transfer matrices
   int swz_bits = 0;        // log2(elements per shared-memory wavefront) of the swizzled tile
   int bank_bits = 0;       // log2(elements per 128-byte wavefront): relayout lane choice
@@ -393,6 +397,7 @@ struct Builder {
                               : T + (int)(std::find(opos.begin(), opos.end(), h) - opos.begin());
     }
     F.set_permutation(pos);
+    pass_used = 0;
     FramePassHost ps;
     ps.first_step = (int)steps.size();
     ps.n_steps = 0;
@@ -593,7 +598,7 @@ bool Builder::build_step() {
       std::memset(&fo, 0, sizeof(fo));
       fo.k = (uint8_t)o.k;
       fo.premat_off = premat_off[i];
-      fo.smem_off = resident ? premat_off[i] : used;
+      fo.smem_off = pass_compact ? pass_used + used : (resident ? premat_off[i] : used);
       if (o.kind != QMLB_OP_DIAG && o.kind != QMLB_OP_SIGN) {
         const Shape sh = shape_of(p, o.src);
         fo.shape = sh.xshape && o.kind == QMLB_OP_MAT && o.k == 2
@@ -779,6 +784,10 @@ bool Builder::build_step() {
         for (int j = 0; j < 4; ++j) s.foff[j] = 0;
       }
     }
+    if (pass_compact) {
+      pass_used += used;
+      pass_used_max = std::max(pass_used_max, pass_used);
+    }
     steps.push_back(s);
     step_ops.push_back(ops_of_step);
   }
@@ -952,10 +961,9 @@ int plan_frame_stream(qmlb_program* p) {
   if (tile_bytes + (size_t)row * cs > 96 * 1024) return QMLB_ERR_UNSUPPORTED;
   B.mat_cap = std::max(row, 1);
   B.resident = true;
+  B.pass_compact = true;
   const int rc = B.run_stream();
   if (rc != QMLB_OK) return rc;
-  int max_steps = 1;
-  for (const FramePassHost& ps : B.passes) max_steps = std::max(max_steps, ps.n_steps);
   p->frame_steps = std::move(B.steps);
   p->frame_step_ops = std::move(B.step_ops);
   p->fstream_passes = std::move(B.passes);
@@ -968,7 +976,7 @@ int plan_frame_stream(qmlb_program* p) {
   fp.outer_bits = N - T;
   fp.team_bits = 8;
   fp.teams = 1;
-  fp.mat_cap = B.mat_cap;
+  fp.mat_cap = (std::max(B.pass_used_max, 1) + 15) & ~15;  // keeps the step records 128-byte aligned
   fp.mat_resident = 1;
   fp.premat_row = row;
   fp.density = p->density;
@@ -976,8 +984,9 @@ int plan_frame_stream(qmlb_program* p) {
   fp.n_obs = (int)p->obs.size();
   p->fstream_low_bits = L;
   p->frame_threads = 256;
-  // [tile | matrices | step records of the longest pass | relayout tables | mbarrier]
-  p->frame_smem = tile_bytes + (size_t)B.mat_cap * cs + (size_t)max_steps * sizeof(FrameStep) +
+  // [tile | matrices of the largest pass | two step records | relayout tables | mbarrier]:
+  // 2^13 complex64 amplitudes + ~4 KiB leave room for three CTAs per SM
+  p->frame_smem = tile_bytes + (size_t)fp.mat_cap * cs + 2 * sizeof(FrameStep) +
                   (256 + 64) * sizeof(uint32_t) + 64;
   return QMLB_OK;
 }

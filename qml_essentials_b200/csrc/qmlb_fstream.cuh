@@ -22,7 +22,7 @@ struct FStreamPass {
   int32_t n_bits, tile_bits, low_bits, outer_bits;
   int32_t init;             // 1: |0..0> (no read), 2: zero vector, 0: read the state
   int32_t premat_row;
-  int32_t pad;
+  int32_t mat_cap;          // matrix entries of the largest pass (shared-memory area)
   uint8_t tp[16];           // tile index bit -> HBM bit position (tp[i] = i for i < low_bits)
   uint8_t opos[32];         // tile number bit -> HBM bit position
 };
@@ -81,11 +81,11 @@ __global__ void __launch_bounds__(THREADS, THREADS == 512 ? 2 : (sizeof(T) == 4 
   extern __shared__ __align__(128) unsigned char fsm[];
   const int Tb = P.tile_bits, Lb = P.low_bits;
   const uint32_t tile_n = 1u << Tb;
-  // [tile | matrices | step records | relayout tables | mbarrier]
+  // [tile | matrices of this pass | two step records | relayout tables | mbarrier]
   cx<T>* tile = reinterpret_cast<cx<T>*>(fsm);
   cx<T>* mats = tile + tile_n;
-  FrameStep* sstep = reinterpret_cast<FrameStep*>(mats + (P.premat_row > 0 ? P.premat_row : 1));
-  uint32_t* tab_lo = reinterpret_cast<uint32_t*>(sstep + (P.n_steps > 0 ? P.n_steps : 1));
+  FrameStep* sstep = reinterpret_cast<FrameStep*>(mats + P.mat_cap);
+  uint32_t* tab_lo = reinterpret_cast<uint32_t*>(sstep + 2);
   uint32_t* tab_hi = tab_lo + 256;
   uint64_t* bar = reinterpret_cast<uint64_t*>(tab_hi + 64);
 
@@ -95,8 +95,13 @@ __global__ void __launch_bounds__(THREADS, THREADS == 512 ? 2 : (sizeof(T) == 4 
   const int64_t tiles_per_elem = (int64_t)1 << P.outer_bits;
   const int64_t total = A.batch * tiles_per_elem;
 
-  for (int i = threadIdx.x; i < P.n_steps * 256; i += blockDim.x)
-    reinterpret_cast<uint32_t*>(sstep)[i] = reinterpret_cast<const uint32_t*>(P.steps)[i];
+  // step records are double-buffered: record si + 1 is fetched while step si runs (the
+  // barrier that ends a step publishes it), so the shared memory holds two of them
+  auto fetch_step = [&](int si) {
+    for (int i = threadIdx.x; i < 256; i += blockDim.x)
+      reinterpret_cast<uint32_t*>(&sstep[si & 1])[i] =
+          reinterpret_cast<const uint32_t*>(&P.steps[si])[i];
+  };
   if (threadIdx.x == 0) {
     mbar_init(bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -118,11 +123,26 @@ __global__ void __launch_bounds__(THREADS, THREADS == 512 ? 2 : (sizeof(T) == 4 
       return o;
     };
 
-    if (bl != cur_elem) {  // matrices of this element (a CTA rarely changes element)
+    if (bl != cur_elem) {  // matrices this pass uses (a CTA rarely changes element)
       const cx<T>* prow = premats + (size_t)bl * P.premat_row;
-      for (int i = threadIdx.x; i < P.premat_row; i += blockDim.x) mats[i] = prow[i];
+      for (int si = 0; si < P.n_steps; ++si) {
+        const FrameStep& gst = P.steps[si];
+        if (gst.kind != QMLB_FSTEP_SUBPASS) continue;
+        for (int o = 0; o < gst.n_ops; ++o) {
+          const FrameOp fo = gst.ops[o];
+          if (fo.code == QMLB_FOP_SIGN) {
+            o += 3;
+            continue;
+          }
+          const int n = fo.code == QMLB_FOP_DIAG ? (1 << fo.k) : (1 << (2 * fo.k));
+          for (int e = threadIdx.x; e < n; e += blockDim.x)
+            mats[fo.smem_off + e] = prow[fo.premat_off + e];
+          if (fo.code == QMLB_FOP_DIAG) ++o;
+        }
+      }
       cur_elem = bl;
     }
+    if (P.n_steps > 0) fetch_step(0);
     if (P.init) {
       for (uint32_t i = threadIdx.x; i < tile_n; i += blockDim.x)
         tile[i] = mk<T>((i == 0 && tnum == 0 && P.init == 1) ? (T)1 : (T)0, (T)0);
@@ -137,7 +157,8 @@ __global__ void __launch_bounds__(THREADS, THREADS == 512 ? 2 : (sizeof(T) == 4 
     }
 
     for (int si = 0; si < P.n_steps; ++si) {
-      const FrameStep& st = sstep[si];
+      const FrameStep& st = sstep[si & 1];
+      if (si + 1 < P.n_steps) fetch_step(si + 1);
       if (st.kind == QMLB_FSTEP_RELAYOUT) {  // tile-local shuffle (tables depend on the tile)
         for (int i = threadIdx.x; i < 256 + 64; i += blockDim.x) {
           uint32_t acc = 0;

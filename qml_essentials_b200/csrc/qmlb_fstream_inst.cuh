@@ -36,6 +36,7 @@ static cudaError_t launch_fstream_t(const qmlb_program* p, const RunArgs& R, voi
     P.outer_bits = F.outer_bits;
     P.init = (first && ps.init) ? init_mode : 0;
     P.premat_row = F.premat_row;
+    P.mat_cap = F.mat_cap;
     for (int i = 0; i < F.tile_bits; ++i) P.tp[i] = (uint8_t)ps.tp[i];
     for (int g = 0; g < F.outer_bits; ++g) P.opos[g] = (uint8_t)ps.opos[g];
     g_launches.fetch_add(1, std::memory_order_relaxed);
