@@ -201,6 +201,37 @@ __device__ __forceinline__ void frame_store(RegState<T, FRAME_R>& S, cx<T>* tile
   for (int v = 0; v < FRAME_D; ++v) tile[base ^ st.eoff[v]] = mk<T>(S.re(v), S.im(v));
 }
 
+// eoff is GF(2)-linear in the slot number, so six words in registers - the four masks and the
+// two pair sums - give every slot address with ONE three-input XOR: no eoff word is read
+// from shared memory inside the item loop (the compiler had to re-read them after every
+// tile store, which may alias the step record).
+struct FrameLin {
+  uint32_t lo[4], hi[4];  // lo[v & 3] ^ hi[v >> 2] = eoff[v]
+};
+__device__ __forceinline__ FrameLin frame_lin(const FrameStep& st) {
+  FrameLin L;
+  L.lo[0] = 0u, L.lo[1] = st.eoff[1], L.lo[2] = st.eoff[2], L.lo[3] = st.eoff[3];
+  L.hi[0] = 0u, L.hi[1] = st.eoff[4], L.hi[2] = st.eoff[8], L.hi[3] = st.eoff[12];
+  return L;
+}
+template <typename T>
+__device__ __forceinline__ void frame_load_lin(RegState<T, FRAME_R>& S, const cx<T>* tile,
+                                               uint32_t base, const FrameLin& L) {
+#pragma unroll
+  for (int v = 0; v < FRAME_D; ++v) {
+    const cx<T> a = tile[base ^ L.lo[v & 3] ^ L.hi[v >> 2]];
+    S.re(v) = a.x;
+    S.im(v) = a.y;
+  }
+}
+template <typename T>
+__device__ __forceinline__ void frame_store_lin(RegState<T, FRAME_R>& S, cx<T>* tile,
+                                                uint32_t base, const FrameLin& L) {
+#pragma unroll
+  for (int v = 0; v < FRAME_D; ++v)
+    tile[base ^ L.lo[v & 3] ^ L.hi[v >> 2]] = mk<T>(S.re(v), S.im(v));
+}
+
 // fast path: at most one 4x4 on register pair (1,0) (shape SA) and one on (3,2) (shape SB);
 // -1 = absent.  Straight-line code: no op decoding, no dispatch inside the item loop.
 template <typename T, int SA, int SB>
@@ -257,15 +288,16 @@ __device__ __noinline__ void frame_items_m1(cx<T>* tile, const cx<T>* mats, cons
   uint32_t piv[FRAME_R];
 #pragma unroll
   for (int j = 0; j < FRAME_R; ++j) piv[j] = st.pivots[j];
+  const FrameLin L = frame_lin(st);
   for (uint32_t it = tlane; it < n_items; it += tsize) {
     const uint32_t base = frame_item_base(st, it, piv, rank);
     RegState<T, FRAME_R> S;
-    frame_load<T>(S, tile, base, st);
+    frame_load_lin<T>(S, tile, base, L);
     if constexpr (MASK & 1) frame_mat1<T, 0, SH>(S, mats + st.foff[0]);
     if constexpr (MASK & 2) frame_mat1<T, 1, SH>(S, mats + st.foff[1]);
     if constexpr (MASK & 4) frame_mat1<T, 2, SH>(S, mats + st.foff[2]);
     if constexpr (MASK & 8) frame_mat1<T, 3, SH>(S, mats + st.foff[3]);
-    frame_store<T>(S, tile, base, st);
+    frame_store_lin<T>(S, tile, base, L);
   }
 }
 
