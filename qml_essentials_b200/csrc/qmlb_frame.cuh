@@ -660,7 +660,9 @@ __global__ void __launch_bounds__(THREADS, (THREADS == 512 || WIDE) ? 1 : 2)
           cx<T>* mdst = mats_all + (size_t)team * F.mat_cap;
           for (int o = 0; o < st.n_ops; ++o) {
             const FrameOp fo = st.ops[o];
-            const int n = fo.code == QMLB_FOP_DIAG ? (1 << fo.k) : (1 << (2 * fo.k));
+            const int n = fo.code == QMLB_FOP_DIAG    ? (1 << fo.k)
+                          : fo.code == QMLB_FOP_CTRL1 ? 4  // the 2x2 alone, not 4^k
+                                                      : (1 << (2 * fo.k));
             for (int e = tlane; e < n; e += tsize) mdst[fo.smem_off + e] = prow[fo.premat_off + e];
             if (fo.code == QMLB_FOP_DIAG) ++o;
           }

@@ -134,7 +134,10 @@ __global__ void __launch_bounds__(THREADS, THREADS == 512 ? 2 : (sizeof(T) == 4 
             o += 3;
             continue;
           }
-          const int n = fo.code == QMLB_FOP_DIAG ? (1 << fo.k) : (1 << (2 * fo.k));
+          // entries of the op's source: a controlled 2x2 (k = 2) stores only the 2x2
+          const int n = fo.code == QMLB_FOP_DIAG    ? (1 << fo.k)
+                        : fo.code == QMLB_FOP_CTRL1 ? 4
+                                                    : (1 << (2 * fo.k));
           for (int e = threadIdx.x; e < n; e += blockDim.x)
             mats[fo.smem_off + e] = prow[fo.premat_off + e];
           if (fo.code == QMLB_FOP_DIAG) ++o;

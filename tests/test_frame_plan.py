@@ -133,6 +133,47 @@ def test_config5_pass_count(lib):
     assert all(s[2] for s in steps if s[0] == "relayout")
 
 
+@pytest.mark.parametrize("n,L,ct,precision", [
+    (32, 8, "Hardware_Efficient", "complex64"), (28, 4, "Hardware_Efficient", "complex128"),
+    (20, 2, "Circuit_19", "complex64"), (22, 2, "Strongly_Entangling", "complex64"),
+])
+def test_streamed_tiles_stage_one_pass_of_matrices(lib, n, L, ct, precision):
+    """Strategy 4 stages only the matrices of the current HBM pass next to the tile: inside a
+    pass the shared-memory ranges of the ops are disjoint and fit ``mat_cap``, every op keeps
+    its own offset in the element's row of evaluated matrices, and tile + matrices + two
+    step records leave room for three CTAs per SM at the default tile size."""
+    import test_cabi
+
+    plan = test_cabi._plan_of(n, L, ct, precision)
+    text = backend.plan_describe(lib, plan.program, plan.out_type, plan.obs_recs, plan.obs_pool,
+                                 precision)
+    assert text.startswith("strategy 4")
+    geo, steps = fe.parse(text)
+    cs = 16 if precision == "complex128" else 8
+    assert geo["mat_cap"] % 16 == 0 and geo["mat_cap"] <= geo["premat_row"] + 15
+    assert geo["smem"] == (cs << geo["tile_bits"]) + geo["mat_cap"] * cs + 2 * 1024 + 320 * 4 + 64
+    assert 3 * (geo["smem"] + 1024) <= 227 * 1024
+    seen_rows = set()
+    for ps in geo["passes"]:
+        used = []
+        for st in steps[ps["first"]:ps["first"] + ps["steps"]]:
+            if st[0] != "subpass":
+                continue
+            for o in st[4]:
+                if o["code"] == 5:  # sign op: no matrix
+                    continue
+                # diagonal: 2^k entries, controlled 2x2: the 2x2 alone, dense: 4^k
+                size = (1 << o["k"]) if o["code"] == 4 else (4 if o["code"] == 3 else 1 << (2 * o["k"]))
+                used.append((o["smem_off"], o["smem_off"] + size))
+                assert o["premat_off"] not in seen_rows
+                seen_rows.add(o["premat_off"])
+        used.sort()
+        if not used:  # a pass that only brings the bits home
+            continue
+        assert used[0][0] == 0 and used[-1][1] <= geo["mat_cap"]
+        assert all(a[1] == b[0] for a, b in zip(used, used[1:]))  # compact, no overlap
+
+
 @pytest.mark.parametrize("n,L,ct,typ,noise", [
     (3, 2, "Strongly_Entangling", "expval", NOISE),
     (4, 2, "Hardware_Efficient", "probs", NOISE),
