@@ -1,0 +1,95 @@
+"""Golden vectors from the reference's OWN `Model.__call__`, run in this container.
+
+    python tools/gen_golden_reference_model.py   # writes tests/golden/reference_model.npz
+
+Companion of `tools/gen_golden_reference.py` (read its header first).  Here the unmodified
+`/root/reference/qml_essentials/model.py` (+ `ansaetze.py`, `gates.py`, `unitary.py`,
+`topologies.py`, `script.py`, `simulation.py`, `operations.py`, `tape.py`) is imported on
+the NumPy stand-in for JAX, with the packages it never reaches on this path replaced by
+inert placeholders (`tools/jax_numpy_shim/stub_missing.py`).  Each sample is ONE call of the
+reference's `Model.__call__` with a single parameter set and a single input - that is the
+reference's un-batched route (`script.py:205-219`: record the tape, `simulate_and_measure`),
+which needs neither `jax.vmap` nor `jax.jit`.  Recorded per case: constructor arguments,
+parameters, inputs, noise parameters and the result of every (input, parameter) pair.
+`tests/test_reference_golden.py` replays them through `oracle/circuits.py` + `oracle/sim.py`.
+Not recorded: anything that draws random numbers inside the reference (GateError, shots,
+initial parameters) - the stand-in's draws are not jax.random's.
+"""
+import json
+import os
+import sys
+import warnings
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, "jax_numpy_shim"))
+sys.path.insert(1, "/root/reference")
+import stub_missing  # noqa: E402
+
+stub_missing.install()
+
+import numpy as np  # noqa: E402
+
+import qml_essentials.model as rmodel  # noqa: E402
+from qml_essentials.ansaetze import Ansaetze  # noqa: E402
+
+assert rmodel.__file__.startswith("/root/reference/"), rmodel.__file__
+
+NOISE_A = {"Depolarizing": 0.01, "AmplitudeDamping": 0.02}
+NOISE_B = {"BitFlip": 0.03, "PhaseFlip": 0.02, "PhaseDamping": 0.04, "Depolarizing": 0.01,
+           "MultiQubitDepolarizing": 0.02}
+
+
+def cases():
+    out = [
+        # the five BASELINE configs at sizes the reference finishes in seconds
+        dict(n=2, L=1, ct="Circuit_19", typ="expval", B_I=9, B_P=1, noise=None),
+        dict(n=4, L=4, ct="Hardware_Efficient", typ="expval", B_I=7, B_P=3, noise=None),
+        dict(n=6, L=3, ct="Circuit_15", typ="state", B_I=1, B_P=3, noise=None),
+        dict(n=6, L=3, ct="Circuit_15", typ="probs", B_I=2, B_P=2, noise=None),
+        dict(n=4, L=2, ct="Strongly_Entangling", typ="density", B_I=3, B_P=1, noise=NOISE_A),
+        dict(n=3, L=4, ct="Strongly_Entangling", typ="expval", B_I=2, B_P=2, noise=NOISE_A),
+        dict(n=8, L=2, ct="Hardware_Efficient", typ="expval", B_I=1, B_P=2, noise=None),
+        dict(n=3, L=2, ct="Circuit_6", typ="density", B_I=2, B_P=1, noise=NOISE_B),
+        dict(n=2, L=2, ct="Circuit_19", typ="probs", B_I=2, B_P=2, noise=NOISE_B),
+    ]
+    for a in Ansaetze.get_available():
+        name = a.__name__
+        out.append(dict(n=4, L=2, ct=name, typ="state", B_I=2,
+                        B_P=1 if name in ("GHZ", "No_Ansatz") else 2, noise=None))
+        out.append(dict(n=3, L=1, ct=name, typ="expval", B_I=2, B_P=1, noise=None))
+    return out
+
+
+def main():
+    rng = np.random.default_rng(20260002)
+    store, index = {}, []
+    for ci, c in enumerate(cases()):
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            m = rmodel.Model(n_qubits=c["n"], n_layers=c["L"], circuit_type=c["ct"])
+        shape = tuple(np.shape(m.params))[1:]
+        params = rng.uniform(0, 2 * np.pi, (c["B_P"],) + shape)
+        inputs = rng.uniform(-np.pi, np.pi, (c["B_I"], 1))
+        res = []
+        for i in range(c["B_I"]):
+            for p in range(c["B_P"]):
+                with warnings.catch_warnings():
+                    warnings.simplefilter("ignore")
+                    r = m(params=params[p:p + 1], inputs=inputs[i:i + 1],
+                          execution_type=c["typ"],
+                          noise_params=dict(c["noise"]) if c["noise"] else None)
+                res.append(np.asarray(r).reshape(-1))
+        tag = f"model{ci}"
+        store[tag + "_params"] = params
+        store[tag + "_inputs"] = inputs
+        store[tag + "_out"] = np.stack(res)  # row b = i * B_P + p, flattened result
+        index.append(dict(c, id=ci, params_shape=list(shape)))
+        print(tag, c["ct"], c["typ"], store[tag + "_out"].shape)
+    store["index_json"] = np.frombuffer(json.dumps(index).encode(), dtype=np.uint8)
+    out = os.path.join(HERE, "..", "tests", "golden", "reference_model.npz")
+    np.savez_compressed(out, **store)
+    print(f"wrote {os.path.normpath(out)}: {len(index)} cases, {os.path.getsize(out)} bytes")
+
+
+if __name__ == "__main__":
+    main()
