@@ -172,6 +172,10 @@ def test_model_fixture_covers_baseline_configs_and_every_ansatz(golden_model):
                                  "Strongly_Entangling", "GHZ", "No_Ansatz"} <= names
     assert {c["typ"] for c in index} == {"expval", "probs", "state", "density"}
     assert any(c["noise"] for c in index)
+    opts = [c["kw"] for c in index if c.get("kw")]
+    assert {"binary", "ternary", "golomb"} <= {k["encoding"]["strategy"] for k in opts
+                                                if isinstance(k.get("encoding"), dict)}
+    assert any("output_qubit" in k for k in opts) and any("data_reupload" in k for k in opts)
 
 
 def test_model_calls_equal_the_reference(golden_model):
@@ -181,6 +185,8 @@ def test_model_calls_equal_the_reference(golden_model):
     z, index = golden_model
     worst = 0.0
     for c in index:
+        if c.get("kw"):
+            continue  # constructor options: replayed through the drop-in API below
         tag = f"model{c['id']}"
         params, inputs, want = z[tag + "_params"], z[tag + "_inputs"], z[tag + "_out"]
         got = _oracle_model_rows(c, params, inputs)
@@ -196,34 +202,43 @@ def _api_model_rows(c, params, inputs, precision="complex128"):
     sets, flat order b = i * B_P + p as `model.py:1414-1483` assimilates them)."""
     import warnings
 
+    from qml_essentials_b200.ansaetze import Encoding
     from qml_essentials_b200.model import Model
 
+    kw = dict(c.get("kw") or {})
+    if isinstance(kw.get("encoding"), dict):
+        kw["encoding"] = Encoding(kw["encoding"]["strategy"], kw["encoding"]["gates"])
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
-        m = Model(n_qubits=c["n"], n_layers=c["L"], circuit_type=c["ct"], precision=precision)
+        m = Model(n_qubits=c["n"], n_layers=c["L"], circuit_type=c["ct"], precision=precision,
+                  **kw)
         assert tuple(m._params_shape) == tuple(c["params_shape"]), (c["ct"], m._params_shape)
         out = np.asarray(m(params=params, inputs=inputs, execution_type=c["typ"],
                            noise_params=dict(c["noise"]) if c["noise"] else None))
     return out.reshape(c["B_I"] * c["B_P"], -1)
 
 
-def _check_api_against_fixture(golden_model, tol, precision="complex128"):
+def _check_api_against_fixture(golden_model, tol, precision="complex128", options=None):
+    """options: None = every case, False = the plain cases, True = the constructor options."""
     z, index = golden_model
     worst = 0.0
     for c in index:
+        if options is not None and bool(c.get("kw")) != options:
+            continue
         tag = f"model{c['id']}"
         got = _api_model_rows(c, z[tag + "_params"], z[tag + "_inputs"], precision)
         want = z[tag + "_out"]
         assert got.shape == want.shape, (c, got.shape, want.shape)
         err = float(np.abs(got - want).max())
-        assert err < tol, (c["ct"], c["typ"], c["n"], err)
+        assert err < tol, (c["ct"], c["typ"], c["n"], c.get("kw"), err)
         worst = max(worst, err)
     return worst
 
 
 def test_drop_in_model_equals_the_reference_through_the_interpreter(golden_model):
-    """Host logic of the drop-in (recording, tape -> program compiler, batch factors, output
-    shapes) on the CPU program interpreter, against the reference's own results."""
+    """Host logic of the drop-in (recording, tape -> program compiler, batch factors, encodings,
+    output-qubit post-processing, output shapes) on the CPU program interpreter, against the
+    reference's own results: all 70 cases."""
     assert _check_api_against_fixture(golden_model, 1e-10) < 1e-10
 
 
@@ -231,5 +246,15 @@ def test_drop_in_model_equals_the_reference_through_the_interpreter(golden_model
 @pytest.mark.parametrize("precision,tol", [("complex128", 1e-10), ("complex64", 1e-5)])
 def test_cuda_model_equals_the_reference(golden_model, precision, tol):
     """The CUDA path (ctypes -> libqmlb200.so) against results of the reference's own
-    `Model.__call__` on identical parameters, inputs and noise: the north star's tolerance."""
-    assert _check_api_against_fixture(golden_model, tol, precision) < tol
+    `Model.__call__` on identical parameters, inputs and noise, at the north star's tolerance:
+    the BASELINE configurations (reduced), every ansatz, noisy density / probs / expval."""
+    assert _check_api_against_fixture(golden_model, tol, precision, options=False) < tol
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("precision,tol", [("complex128", 1e-10), ("complex64", 1e-5)])
+def test_cuda_model_options_equal_the_reference(golden_model, precision, tol):
+    """Same, for the constructor options: two input features, RY / binary / ternary / golomb
+    encodings, no re-uploading, output-qubit subsets (expval, marginal probs, partial trace),
+    state preparation."""
+    assert _check_api_against_fixture(golden_model, tol, precision, options=True) < tol

@@ -60,16 +60,55 @@ def cases():
     return out
 
 
+def option_cases():
+    """Constructor options of model.py:26-45 (encodings, re-uploading, output qubits, state
+    preparation).  `kw` is JSON: an encoding is a gate name, a list of gate names (one input
+    feature each) or {"strategy", "gates"} for `Encoding(strategy, gates)`."""
+    base = dict(n=3, L=2, ct="Circuit_19", B_I=2, B_P=2, noise=None)
+    kws = [
+        (dict(encoding=["RX", "RY"]), "expval"),
+        (dict(encoding="RY"), "expval"),
+        (dict(encoding={"strategy": "binary", "gates": ["RX"]}), "expval"),
+        (dict(encoding={"strategy": "ternary", "gates": ["RX"]}), "expval"),
+        (dict(encoding={"strategy": "golomb", "gates": ["RX"]}), "expval"),
+        (dict(encoding={"strategy": "binary", "gates": ["RY"]}), "probs"),
+        (dict(data_reupload=False), "expval"),
+        (dict(output_qubit=0), "expval"),
+        (dict(output_qubit=[0, 2]), "expval"),
+        (dict(output_qubit=[0, 2]), "probs"),
+        (dict(output_qubit=[0, 1]), "density"),
+        (dict(state_preparation="H"), "probs"),
+        (dict(state_preparation="H", encoding=["RX", "RZ"], output_qubit=[1, 2]), "probs"),
+    ]
+    out = [dict(base, kw=kw, typ=typ) for kw, typ in kws]
+    out.append(dict(base, kw=dict(output_qubit=[0, 1]), typ="density", noise=NOISE_A))
+    out.append(dict(base, n=4, ct="Hardware_Efficient", kw=dict(encoding=["RX", "RY"]),
+                    typ="expval", noise=NOISE_A))
+    return out
+
+
+def _ref_kwargs(kw):
+    from qml_essentials.ansaetze import Encoding
+
+    kw = dict(kw)
+    if isinstance(kw.get("encoding"), dict):
+        kw["encoding"] = Encoding(kw["encoding"]["strategy"], kw["encoding"]["gates"])
+    return kw
+
+
 def main():
     rng = np.random.default_rng(20260002)
     store, index = {}, []
-    for ci, c in enumerate(cases()):
+    for ci, c in enumerate(cases() + option_cases()):
+        kw = c.get("kw", {})
         with warnings.catch_warnings():
             warnings.simplefilter("ignore")
-            m = rmodel.Model(n_qubits=c["n"], n_layers=c["L"], circuit_type=c["ct"])
+            m = rmodel.Model(n_qubits=c["n"], n_layers=c["L"], circuit_type=c["ct"],
+                             **_ref_kwargs(kw))
         shape = tuple(np.shape(m.params))[1:]
         params = rng.uniform(0, 2 * np.pi, (c["B_P"],) + shape)
-        inputs = rng.uniform(-np.pi, np.pi, (c["B_I"], 1))
+        n_feat = len(kw["encoding"]) if isinstance(kw.get("encoding"), list) else 1
+        inputs = rng.uniform(-np.pi, np.pi, (c["B_I"], n_feat))
         res = []
         for i in range(c["B_I"]):
             for p in range(c["B_P"]):
@@ -84,7 +123,7 @@ def main():
         store[tag + "_inputs"] = inputs
         store[tag + "_out"] = np.stack(res)  # row b = i * B_P + p, flattened result
         index.append(dict(c, id=ci, params_shape=list(shape)))
-        print(tag, c["ct"], c["typ"], store[tag + "_out"].shape)
+        print(tag, c["ct"], c["typ"], kw, store[tag + "_out"].shape)
     store["index_json"] = np.frombuffer(json.dumps(index).encode(), dtype=np.uint8)
     out = os.path.join(HERE, "..", "tests", "golden", "reference_model.npz")
     np.savez_compressed(out, **store)
