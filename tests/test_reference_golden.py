@@ -258,3 +258,62 @@ def test_cuda_model_options_equal_the_reference(golden_model, precision, tol):
     encodings, no re-uploading, output-qubit subsets (expval, marginal probs, partial trace),
     state preparation."""
     assert _check_api_against_fixture(golden_model, tol, precision, options=True) < tol
+
+
+# ---- analysis helpers of the reference (tools/gen_golden_reference_analysis.py) ------------
+ANALYSIS_PATH = os.path.join(os.path.dirname(__file__), "golden", "reference_analysis.npz")
+
+
+def _close(a, b, tol=1e-12):
+    a, b = np.asarray(a), np.asarray(b)
+    assert a.shape == b.shape, (a.shape, b.shape)
+    assert np.array_equal(np.isnan(a), np.isnan(b))
+    return bool(np.all(np.abs(np.nan_to_num(a) - np.nan_to_num(b)) < tol))
+
+
+def test_fcc_statistics_equal_the_reference():
+    """coefficients.py:1165-1650 as executed (`FCC._correlate` with its four methods, with and
+    without missing values, masks, flat frequency labels, weightings, `calculate_fcc`)
+    against the drop-in's host versions."""
+    import warnings
+
+    from qml_essentials_b200.coefficients import FCC
+
+    z = np.load(ANALYSIS_PATH)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        for method in ("pearson", "complex_pearson", "spearman", "covariance"):
+            assert _close(FCC._correlate(z["corr_mat"], method=method), z[f"corr_{method}"]), method
+            assert _close(FCC._correlate(z["corr_mat_holes"], method=method),
+                          z[f"corr_holes_{method}"]), method
+        assert np.array_equal(np.asarray(FCC._calculate_mask(z["freqs1"])), z["mask1"])
+        assert np.array_equal(np.asarray(FCC._calculate_mask(z["freqs2"])), z["mask2"])
+        assert _close(FCC._flat_frequencies(z["freqs1"]), z["flat1"])
+        assert _close(FCC._flat_frequencies(z["freqs2"]), z["flat2"])
+        assert _close(FCC._weighting_linear(z["fp"]), z["weight_linear"])
+        assert _close(FCC._weighting_mean(z["fp"], z["corr_mat"].transpose()), z["weight_mean"])
+        assert abs(float(FCC.calculate_fcc(z["fp"])) - float(z["fcc"])) < 1e-14
+
+
+def test_spectrum_helpers_equal_the_reference():
+    """coefficients.py:152-238 (`get_psd`, `evaluate_Fourier_series`)."""
+    from qml_essentials_b200.coefficients import Coefficients
+
+    z = np.load(ANALYSIS_PATH)
+    assert _close(Coefficients.get_psd(z["psd_in"]), z["psd"])
+    ys = [Coefficients.evaluate_Fourier_series(z["series_c"], z["series_f"], float(x))
+          for x in z["series_x"]]
+    assert _close(np.real(np.asarray(ys)).reshape(-1), np.real(z["series_y"]).reshape(-1), 1e-11)
+
+
+def test_expressibility_helpers_equal_the_reference():
+    """expressibility.py (`_haar_probability`, `haar_integral`, `kullback_leibler_divergence`)."""
+    from qml_essentials_b200.expressibility import Expressibility
+
+    z = np.load(ANALYSIS_PATH)
+    for nq in (1, 2, 4):
+        got = [Expressibility._haar_probability(float(f), nq) for f in z["haar_fid"]]
+        assert _close(got, z[f"haar_prob_{nq}"])
+        x, y = Expressibility.haar_integral(nq, 20, cache=False)
+        assert _close(x, z[f"haar_int_x_{nq}"]) and _close(y, z[f"haar_int_y_{nq}"], 1e-10)
+    assert _close(Expressibility.kullback_leibler_divergence(z["kl_p"], z["kl_q"]), z["kl"])
