@@ -317,3 +317,21 @@ def test_expressibility_helpers_equal_the_reference():
         x, y = Expressibility.haar_integral(nq, 20, cache=False)
         assert _close(x, z[f"haar_int_x_{nq}"]) and _close(y, z[f"haar_int_y_{nq}"], 1e-10)
     assert _close(Expressibility.kullback_leibler_divergence(z["kl_p"], z["kl_q"]), z["kl"])
+
+
+def test_jaqsi_helpers_and_meyer_wallach_equal_the_reference():
+    """jaqsi.py:79-160 (`partial_trace`, `marginalize_probs`, batched and single) and
+    entanglement.py:69-105 (`_compute_meyer_wallach_meas`) as executed."""
+    from qml_essentials_b200 import jaqsi as js
+    from qml_essentials_b200.entanglement import Entanglement
+
+    z = np.load(ANALYSIS_PATH)
+    n = 3
+    assert _close(Entanglement._compute_meyer_wallach_meas(z["mw_rhos"], n), z["mw_pure"])
+    assert _close(Entanglement._compute_meyer_wallach_meas(z["mw_mixed"], n), z["mw_mix"])
+    for keep in ([0], [2], [0, 2], [1, 2], [0, 1, 2]):
+        tag = "".join(map(str, keep))
+        assert _close(js.partial_trace(z["mw_rhos"], n, keep), z[f"ptrace_{tag}"])
+        assert _close(js.partial_trace(z["mw_rhos"][1], n, keep), z[f"ptrace1_{tag}"])
+        assert _close(js.marginalize_probs(z["marg_probs"], n, tuple(keep)), z[f"marg_{tag}"])
+        assert _close(js.marginalize_probs(z["marg_probs"][2], n, tuple(keep)), z[f"marg1_{tag}"])

@@ -88,6 +88,27 @@ def main():
     store["kl_p"], store["kl_q"] = p, q
     store["kl"] = np.asarray(rx.Expressibility.kullback_leibler_divergence(p, q))
 
+    # jaqsi helpers and the Meyer-Wallach measure on random states (batched and single)
+    import qml_essentials.entanglement as ren
+    import qml_essentials.jaqsi as rjs
+
+    n = 3
+    psi = rng.normal(size=(4, 2 ** n)) + 1j * rng.normal(size=(4, 2 ** n))
+    psi /= np.linalg.norm(psi, axis=1, keepdims=True)
+    rhos = np.einsum("bi,bj->bij", psi, psi.conj())
+    mixed = 0.7 * rhos + 0.3 * np.eye(2 ** n) / 2 ** n
+    store["mw_rhos"], store["mw_mixed"] = rhos, mixed
+    store["mw_pure"] = np.asarray(ren.Entanglement._compute_meyer_wallach_meas(rhos, n))
+    store["mw_mix"] = np.asarray(ren.Entanglement._compute_meyer_wallach_meas(mixed, n))
+    for keep in ([0], [2], [0, 2], [1, 2], [0, 1, 2]):
+        tag = "".join(map(str, keep))
+        store[f"ptrace_{tag}"] = np.asarray(rjs.partial_trace(rhos, n, keep))
+        store[f"ptrace1_{tag}"] = np.asarray(rjs.partial_trace(rhos[1], n, keep))
+        probs = np.abs(psi) ** 2
+        store[f"marg_{tag}"] = np.asarray(rjs.marginalize_probs(probs, n, tuple(keep)))
+        store[f"marg1_{tag}"] = np.asarray(rjs.marginalize_probs(probs[2], n, tuple(keep)))
+    store["marg_probs"] = np.abs(psi) ** 2
+
     out = os.path.join(HERE, "..", "tests", "golden", "reference_analysis.npz")
     np.savez_compressed(out, **store)
     print(f"wrote {os.path.normpath(out)}: {len(store)} arrays, {os.path.getsize(out)} bytes")
