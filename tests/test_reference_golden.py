@@ -185,7 +185,7 @@ def test_model_calls_equal_the_reference(golden_model):
     z, index = golden_model
     worst = 0.0
     for c in index:
-        if c.get("kw"):
+        if c.get("kw") or c.get("api_only"):
             continue  # constructor options: replayed through the drop-in API below
         tag = f"model{c['id']}"
         params, inputs, want = z[tag + "_params"], z[tag + "_inputs"], z[tag + "_out"]
@@ -223,7 +223,7 @@ def _check_api_against_fixture(golden_model, tol, precision="complex128", option
     z, index = golden_model
     worst = 0.0
     for c in index:
-        if options is not None and bool(c.get("kw")) != options:
+        if options is not None and bool(c.get("kw") or c.get("api_only")) != options:
             continue
         tag = f"model{c['id']}"
         got = _api_model_rows(c, z[tag + "_params"], z[tag + "_inputs"], precision)
@@ -238,7 +238,7 @@ def _check_api_against_fixture(golden_model, tol, precision="complex128", option
 def test_drop_in_model_equals_the_reference_through_the_interpreter(golden_model):
     """Host logic of the drop-in (recording, tape -> program compiler, batch factors, encodings,
     output-qubit post-processing, output shapes) on the CPU program interpreter, against the
-    reference's own results: all 70 cases."""
+    reference's own results: all 73 cases."""
     assert _check_api_against_fixture(golden_model, 1e-10) < 1e-10
 
 
@@ -256,7 +256,7 @@ def test_cuda_model_equals_the_reference(golden_model, precision, tol):
 def test_cuda_model_options_equal_the_reference(golden_model, precision, tol):
     """Same, for the constructor options: two input features, RY / binary / ternary / golomb
     encodings, no re-uploading, output-qubit subsets (expval, marginal probs, partial trace),
-    state preparation."""
+    state preparation, and all nine noise keys at once (thermal relaxation in both regimes)."""
     assert _check_api_against_fixture(golden_model, tol, precision, options=True) < tol
 
 

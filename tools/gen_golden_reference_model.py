@@ -81,6 +81,23 @@ def option_cases():
         (dict(state_preparation="H", encoding=["RX", "RZ"], output_qubit=[1, 2]), "probs"),
     ]
     out = [dict(base, kw=kw, typ=typ) for kw, typ in kws]
+    # every noise_params key of model.py:253-265 incl. state-preparation / measurement flips
+    # and depth-dependent thermal relaxation (replayed through the API only: the channel
+    # strength depends on the circuit depth the Model computes)
+    full = {"BitFlip": 0.01, "PhaseFlip": 0.02, "Depolarizing": 0.03,
+            "MultiQubitDepolarizing": 0.04, "AmplitudeDamping": 0.05, "PhaseDamping": 0.06,
+            "StatePreparation": 0.07, "Measurement": 0.08,
+            "ThermalRelaxation": {"t1": 2000.0, "t2": 1000.0, "t_factor": 1.0}}
+    # ONE input per case: the reference computes the depth with zero inputs and drops the
+    # zero encodings only when batch_shape[0] == 1 (model.py:782, 1085-1098), so the gate
+    # time of the thermal channel depends on the input batch size of the call - one call per
+    # sample reproduces a batched call only for a single input
+    one = dict(base, B_I=1, B_P=3)
+    out.append(dict(one, kw={}, api_only=True, typ="probs", noise=full))
+    out.append(dict(one, n=2, ct="Strongly_Entangling", kw={}, api_only=True, typ="density",
+                    noise=full))
+    out.append(dict(one, kw={}, api_only=True, typ="expval",
+                    noise={"ThermalRelaxation": {"t1": 1000.0, "t2": 1800.0, "t_factor": 2.0}}))
     out.append(dict(base, kw=dict(output_qubit=[0, 1]), typ="density", noise=NOISE_A))
     out.append(dict(base, n=4, ct="Hardware_Efficient", kw=dict(encoding=["RX", "RY"]),
                     typ="expval", noise=NOISE_A))
