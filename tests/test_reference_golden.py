@@ -335,3 +335,18 @@ def test_jaqsi_helpers_and_meyer_wallach_equal_the_reference():
         assert _close(js.partial_trace(z["mw_rhos"][1], n, keep), z[f"ptrace1_{tag}"])
         assert _close(js.marginalize_probs(z["marg_probs"], n, tuple(keep)), z[f"marg_{tag}"])
         assert _close(js.marginalize_probs(z["marg_probs"][2], n, tuple(keep)), z[f"marg1_{tag}"])
+
+
+def test_operator_algebra_equals_the_reference():
+    """operations.py:112-400 (dagger / power / scalar and operator products / sums): the same
+    expressions (`tests/golden_algebra_cases.py`) on the drop-in's `operations` module give
+    the matrices and wires the reference's module gave."""
+    import golden_algebra_cases as gac
+
+    from qml_essentials_b200 import operations as op
+
+    z = np.load(ANALYSIS_PATH)
+    for name, fn in gac.CASES.items():
+        o = fn(op)
+        assert list(o.wires) == [int(w) for w in z[f"alg_{name}_wires"]], name
+        assert _close(np.asarray(o.matrix), z[f"alg_{name}_matrix"]), name

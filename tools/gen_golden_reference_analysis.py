@@ -109,6 +109,16 @@ def main():
         store[f"marg1_{tag}"] = np.asarray(rjs.marginalize_probs(probs[2], n, tuple(keep)))
     store["marg_probs"] = np.abs(psi) ** 2
 
+    # operator algebra (operations.py:112-400): the same expressions on both modules
+    sys.path.insert(2, os.path.join(HERE, "..", "tests"))
+    import golden_algebra_cases as gac
+    import qml_essentials.operations as rop
+
+    for name, fn in gac.CASES.items():
+        o = fn(rop)
+        store[f"alg_{name}_matrix"] = np.asarray(o.matrix)
+        store[f"alg_{name}_wires"] = np.asarray(list(o.wires), dtype=np.int64)
+
     out = os.path.join(HERE, "..", "tests", "golden", "reference_analysis.npz")
     np.savez_compressed(out, **store)
     print(f"wrote {os.path.normpath(out)}: {len(store)} arrays, {os.path.getsize(out)} bytes")
