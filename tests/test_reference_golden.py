@@ -215,7 +215,7 @@ def _api_model_rows(c, params, inputs, precision="complex128"):
         assert tuple(m._params_shape) == tuple(c["params_shape"]), (c["ct"], m._params_shape)
         out = np.asarray(m(params=params, inputs=inputs, execution_type=c["typ"],
                            noise_params=dict(c["noise"]) if c["noise"] else None))
-    return out.reshape(c["B_I"] * c["B_P"], -1)
+    return out
 
 
 def _check_api_against_fixture(golden_model, tol, precision="complex128", options=None):
@@ -227,7 +227,9 @@ def _check_api_against_fixture(golden_model, tol, precision="complex128", option
             continue
         tag = f"model{c['id']}"
         got = _api_model_rows(c, z[tag + "_params"], z[tag + "_inputs"], precision)
-        want = z[tag + "_out"]
+        # ONE batched call of the drop-in against ONE batched call of the reference: same
+        # result array, same shape (squeezed axes included)
+        want = z[tag + "_batched"]
         assert got.shape == want.shape, (c, got.shape, want.shape)
         err = float(np.abs(got - want).max())
         assert err < tol, (c["ct"], c["typ"], c["n"], c.get("kw"), err)

@@ -6,11 +6,13 @@ Companion of `tools/gen_golden_reference.py` (read its header first).  Here the 
 `/root/reference/qml_essentials/model.py` (+ `ansaetze.py`, `gates.py`, `unitary.py`,
 `topologies.py`, `script.py`, `simulation.py`, `operations.py`, `tape.py`) is imported on
 the NumPy stand-in for JAX, with the packages it never reaches on this path replaced by
-inert placeholders (`tools/jax_numpy_shim/stub_missing.py`).  Each sample is ONE call of the
-reference's `Model.__call__` with a single parameter set and a single input - that is the
-reference's un-batched route (`script.py:205-219`: record the tape, `simulate_and_measure`),
-which needs neither `jax.vmap` nor `jax.jit`.  Recorded per case: constructor arguments,
-parameters, inputs, noise parameters and the result of every (input, parameter) pair.
+inert placeholders (`tools/jax_numpy_shim/stub_missing.py`).  Every case is evaluated twice:
+one call of the reference's `Model.__call__` per (input, parameter set) - its un-batched
+route (`script.py:205-219`: record the tape, `simulate_and_measure`) - and ONE call with the
+whole batch - its vmapped route (`script.py:399-553`; `jax.vmap` is a loop here); the two must
+agree.  Recorded per case: constructor arguments, parameters, inputs, noise parameters, the
+per-sample results (`_out`, flat order b = i * B_P + p) and the batched result (`_batched`,
+the reference's own output shape).
 `tests/test_reference_golden.py` replays them through `oracle/circuits.py` + `oracle/sim.py`.
 Not recorded: anything that draws random numbers inside the reference (GateError, shots,
 initial parameters) - the stand-in's draws are not jax.random's.
@@ -88,11 +90,13 @@ def option_cases():
             "MultiQubitDepolarizing": 0.04, "AmplitudeDamping": 0.05, "PhaseDamping": 0.06,
             "StatePreparation": 0.07, "Measurement": 0.08,
             "ThermalRelaxation": {"t1": 2000.0, "t2": 1000.0, "t_factor": 1.0}}
-    # ONE input per case: the reference computes the depth with zero inputs and drops the
-    # zero encodings only when batch_shape[0] == 1 (model.py:782, 1085-1098), so the gate
-    # time of the thermal channel depends on the input batch size of the call - one call per
-    # sample reproduces a batched call only for a single input
-    one = dict(base, B_I=1, B_P=3)
+    # ONE sample per call for the depth-dependent thermal channel: the reference computes the
+    # depth with zero inputs and drops the zero encodings only when batch_shape[0] == 1
+    # (model.py:782, 1085-1098), and `_inputs_validation(None)` inside it flips
+    # `self._zero_inputs` while the circuit is being recorded - under real `jax.vmap` the
+    # circuit is traced once, under the stand-in's loop it would be re-recorded per sample
+    # with the flipped flag, so a batched thermal call is NOT reproduced faithfully here
+    one = dict(base, B_I=1, B_P=1)
     out.append(dict(one, kw={}, api_only=True, typ="probs", noise=full))
     out.append(dict(one, n=2, ct="Strongly_Entangling", kw={}, api_only=True, typ="density",
                     noise=full))
@@ -135,12 +139,26 @@ def main():
                           execution_type=c["typ"],
                           noise_params=dict(c["noise"]) if c["noise"] else None)
                 res.append(np.asarray(r).reshape(-1))
+        # the same batch in ONE call of the reference (its vmapped route, script.py:399-553,
+        # on a fresh model: the first call fixes the cached circuit depth)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            mb = rmodel.Model(n_qubits=c["n"], n_layers=c["L"], circuit_type=c["ct"],
+                              **_ref_kwargs(kw))
+            batched = np.asarray(mb(params=params, inputs=inputs, execution_type=c["typ"],
+                                    noise_params=dict(c["noise"]) if c["noise"] else None))
         tag = f"model{ci}"
+        store[tag + "_batched"] = batched
+        assert np.abs(batched.reshape(len(res), -1) - np.stack(res)).max() < 1e-12, (
+            "the reference's batched and per-sample routes disagree under the stand-in", c)
+        c = dict(c, batched_equals_samples=bool(
+            np.abs(batched.reshape(len(res), -1) - np.stack(res)).max() < 1e-12))
         store[tag + "_params"] = params
         store[tag + "_inputs"] = inputs
         store[tag + "_out"] = np.stack(res)  # row b = i * B_P + p, flattened result
         index.append(dict(c, id=ci, params_shape=list(shape)))
-        print(tag, c["ct"], c["typ"], kw, store[tag + "_out"].shape)
+        print(tag, c["ct"], c["typ"], kw, store[tag + "_out"].shape, batched.shape,
+              c["batched_equals_samples"])
     store["index_json"] = np.frombuffer(json.dumps(index).encode(), dtype=np.uint8)
     out = os.path.join(HERE, "..", "tests", "golden", "reference_model.npz")
     np.savez_compressed(out, **store)

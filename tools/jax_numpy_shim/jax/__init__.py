@@ -3,8 +3,9 @@
 
 FIXTURE TOOLING ONLY.  JAX is not installed in the build container, so the reference cannot
 be imported as is; with this package in front of ``sys.path`` its UNMODIFIED source files
-run on NumPy (float64 / complex128, eager, no tracing) and ``tools/gen_golden_reference.py``
-records their outputs as ``tests/golden/reference_sim.npz``.  Nothing in the product, the
+run on NumPy (float64 / complex128, eager, no tracing; ``vmap`` is a Python loop, ``jit`` the
+identity with the ``lower().compile()`` surface) and ``tools/gen_golden_reference*.py`` record
+their outputs as ``tests/golden/reference_*.npz``.  Nothing in the product, the
 tests or the bench imports this directory; it is not a JAX re-implementation (no tracing, no
 autodiff, XLA's summation order is not reproduced - irrelevant at the 1e-10 tolerance).
 """
@@ -28,10 +29,73 @@ config = _Config()
 Array = _np.ndarray
 
 
+class _TreeUtil:
+    @staticmethod
+    def tree_leaves(tree):
+        out = []
+
+        def walk(t):
+            if isinstance(t, (list, tuple)):
+                for x in t:
+                    walk(x)
+            elif isinstance(t, dict):
+                for x in t.values():
+                    walk(x)
+            elif t is not None:
+                out.append(t)
+
+        walk(tree)
+        return out
+
+
+class _Core:
+    class Tracer:  # nothing is ever traced here
+        pass
+
+
+class _Lax:
+    @staticmethod
+    def index_in_dim(a, index, axis=0, keepdims=True):
+        out = _np.take(_np.asarray(a), index, axis=axis)
+        return _np.expand_dims(out, axis) if keepdims else out
+
+    @staticmethod
+    def dynamic_slice_in_dim(a, start, size, axis=0):
+        idx = [slice(None)] * _np.ndim(a)
+        idx[axis] = slice(int(start), int(start) + int(size))
+        return _np.asarray(a)[tuple(idx)]
+
+
+tree_util = _TreeUtil()
+core = _Core()
+lax = _Lax()
+
+
+def clear_caches():
+    pass
+
+
+class _Jitted:
+    """Eager function with the ahead-of-time surface the reference calls
+    (`jit(f).lower(*args).compile()` -> callable)."""
+
+    def __init__(self, fn):
+        self._fn = fn
+
+    def __call__(self, *a, **k):
+        return self._fn(*a, **k)
+
+    def lower(self, *a, **k):
+        return self
+
+    def compile(self):
+        return self._fn
+
+
 def jit(fn=None, **_kw):
     if fn is None:
-        return lambda f: f
-    return fn
+        return lambda f: _Jitted(f)
+    return _Jitted(fn)
 
 
 def vmap(fn, in_axes=0, out_axes=0):

@@ -10,7 +10,7 @@ import importlib.machinery
 import sys
 import types
 
-ROOTS = {"equinox", "diffrax", "matplotlib", "optax", "dill"}
+ROOTS = {"diffrax", "matplotlib", "optax", "dill"}
 
 
 class _Inert:
