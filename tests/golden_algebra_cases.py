@@ -22,3 +22,16 @@ CASES = {
     "h_power3": lambda op: op.H(wires=0, record=False).power(3),
     "s_dagger": lambda op: op.S(wires=0).dagger(),
 }
+
+# callers replayed on both sides: name -> (n_qubits, n_layers, circuit_type, parameter sets)
+CALLER_MODELS = {
+    "he3": (3, 2, "Hardware_Efficient", 4),
+    "c19": (2, 1, "Circuit_19", 1),
+    "se4": (4, 1, "Strongly_Entangling", 3),
+}
+SPECTRUM_SETTINGS = {
+    "default": dict(),
+    "mfs2_shift_trim": dict(mfs=2, shift=True, trim=True),
+    "mts2": dict(mfs=1, mts=2),
+    "shift": dict(shift=True),
+}

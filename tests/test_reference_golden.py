@@ -352,3 +352,30 @@ def test_operator_algebra_equals_the_reference():
         o = fn(op)
         assert list(o.wires) == [int(w) for w in z[f"alg_{name}_wires"]], name
         assert _close(np.asarray(o.matrix), z[f"alg_{name}_matrix"]), name
+
+
+def test_spectrum_and_meyer_wallach_callers_equal_the_reference():
+    """`Coefficients.get_spectrum` (coefficients.py:25-150: grid, batched model call, FFT,
+    trim / shift) and `Entanglement.meyer_wallach(n_samples=None)` (entanglement.py:17-105)
+    of the reference, run end to end on given parameters, against the drop-in's callers (host
+    route on the CPU interpreter; the GPU suite holds the device route to the host route)."""
+    import warnings
+
+    import golden_algebra_cases as gac
+
+    from qml_essentials_b200.coefficients import Coefficients
+    from qml_essentials_b200.entanglement import Entanglement
+    from qml_essentials_b200.model import Model
+
+    z = np.load(ANALYSIS_PATH)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        for name, (n, L, ct, B_P) in gac.CALLER_MODELS.items():
+            m = Model(n_qubits=n, n_layers=L, circuit_type=ct)
+            m.params = z[f"call_{name}_params"]
+            for tag, kw in gac.SPECTRUM_SETTINGS.items():
+                c, f = Coefficients.get_spectrum(m, **kw)
+                assert _close(np.asarray(c), z[f"call_{name}_{tag}_coeffs"], 1e-10), (name, tag)
+                assert _close(np.asarray(f), z[f"call_{name}_{tag}_freqs"]), (name, tag)
+            mw = Entanglement.meyer_wallach(m, n_samples=None)
+            assert abs(float(mw) - float(z[f"call_{name}_mw"])) < 1e-10, name

@@ -119,6 +119,24 @@ def main():
         store[f"alg_{name}_matrix"] = np.asarray(o.matrix)
         store[f"alg_{name}_wires"] = np.asarray(list(o.wires), dtype=np.int64)
 
+    # the callers themselves, deterministic routes (model.params given, no sampling):
+    # Coefficients.get_spectrum (coefficients.py:25-150) and Entanglement.meyer_wallach with
+    # n_samples=None (entanglement.py:17-105), through the reference's batched Model call
+    import qml_essentials.model as rmodel
+
+    sys.path.insert(2, os.path.join(HERE, "..", "tests"))
+    import golden_algebra_cases as gac  # noqa: F811
+
+    for name, (n, L, ct, B_P) in gac.CALLER_MODELS.items():
+        m = rmodel.Model(n_qubits=n, n_layers=L, circuit_type=ct)
+        m.params = rng.uniform(0, 2 * np.pi, (B_P,) + tuple(np.shape(m.params))[1:])
+        store[f"call_{name}_params"] = np.asarray(m.params)
+        for tag, kw in gac.SPECTRUM_SETTINGS.items():
+            c, f = rc.Coefficients.get_spectrum(m, **kw)
+            store[f"call_{name}_{tag}_coeffs"] = np.asarray(c)
+            store[f"call_{name}_{tag}_freqs"] = np.asarray(f)
+        store[f"call_{name}_mw"] = np.asarray(ren.Entanglement.meyer_wallach(m, n_samples=None))
+
     out = os.path.join(HERE, "..", "tests", "golden", "reference_analysis.npz")
     np.savez_compressed(out, **store)
     print(f"wrote {os.path.normpath(out)}: {len(store)} arrays, {os.path.getsize(out)} bytes")
