@@ -25,9 +25,9 @@ CASES = {
 
 # callers replayed on both sides: name -> (n_qubits, n_layers, circuit_type, parameter sets)
 CALLER_MODELS = {
-    "he3": (3, 2, "Hardware_Efficient", 4),
+    "he3": (3, 2, "Hardware_Efficient", 12),
     "c19": (2, 1, "Circuit_19", 1),
-    "se4": (4, 1, "Strongly_Entangling", 3),
+    "se4": (4, 1, "Strongly_Entangling", 9),
 }
 SPECTRUM_SETTINGS = {
     "default": dict(),
@@ -35,3 +35,4 @@ SPECTRUM_SETTINGS = {
     "mts2": dict(mfs=1, mts=2),
     "shift": dict(shift=True),
 }
+FCC_METHODS = ("pearson", "complex_pearson", "covariance", "spearman")

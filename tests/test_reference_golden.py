@@ -379,3 +379,12 @@ def test_spectrum_and_meyer_wallach_callers_equal_the_reference():
                 assert _close(np.asarray(f), z[f"call_{name}_{tag}_freqs"]), (name, tag)
             mw = Entanglement.meyer_wallach(m, n_samples=None)
             assert abs(float(mw) - float(z[f"call_{name}_mw"])) < 1e-10, name
+            if B_P >= 3:  # FCC on the given samples (n_samples=0), every correlation method
+                from qml_essentials_b200.coefficients import FCC
+
+                for method in gac.FCC_METHODS:
+                    got = float(FCC.get_fcc(m, n_samples=0, method=method))
+                    assert abs(got - float(z[f"call_{name}_fcc_{method}"])) < 1e-9, (name, method)
+                fp, fr = FCC.get_fourier_fingerprint(m, n_samples=0)
+                assert _close(np.asarray(fp), z[f"call_{name}_fp"], 1e-9), name
+                assert _close(np.asarray(fr), z[f"call_{name}_fp_freqs"]), name

@@ -136,6 +136,14 @@ def main():
             store[f"call_{name}_{tag}_coeffs"] = np.asarray(c)
             store[f"call_{name}_{tag}_freqs"] = np.asarray(f)
         store[f"call_{name}_mw"] = np.asarray(ren.Entanglement.meyer_wallach(m, n_samples=None))
+        # FCC on the given parameter samples (n_samples=0: no re-initialisation,
+        # coefficients.py:1100-1160)
+        if B_P >= 3:
+            for method in gac.FCC_METHODS:
+                store[f"call_{name}_fcc_{method}"] = np.asarray(
+                    rc.FCC.get_fcc(m, n_samples=0, method=method))
+            fp, fr = rc.FCC.get_fourier_fingerprint(m, n_samples=0)
+            store[f"call_{name}_fp"], store[f"call_{name}_fp_freqs"] = np.asarray(fp), np.asarray(fr)
 
     out = os.path.join(HERE, "..", "tests", "golden", "reference_analysis.npz")
     np.savez_compressed(out, **store)
