@@ -354,7 +354,7 @@ def test_operator_algebra_equals_the_reference():
         assert _close(np.asarray(o.matrix), z[f"alg_{name}_matrix"]), name
 
 
-def test_spectrum_and_meyer_wallach_callers_equal_the_reference():
+def _check_callers(tol, fcc=True):
     """`Coefficients.get_spectrum` (coefficients.py:25-150: grid, batched model call, FFT,
     trim / shift) and `Entanglement.meyer_wallach(n_samples=None)` (entanglement.py:17-105)
     of the reference, run end to end on given parameters, against the drop-in's callers (host
@@ -375,16 +375,32 @@ def test_spectrum_and_meyer_wallach_callers_equal_the_reference():
             m.params = z[f"call_{name}_params"]
             for tag, kw in gac.SPECTRUM_SETTINGS.items():
                 c, f = Coefficients.get_spectrum(m, **kw)
-                assert _close(np.asarray(c), z[f"call_{name}_{tag}_coeffs"], 1e-10), (name, tag)
+                assert _close(np.asarray(c), z[f"call_{name}_{tag}_coeffs"], tol), (name, tag)
                 assert _close(np.asarray(f), z[f"call_{name}_{tag}_freqs"]), (name, tag)
             mw = Entanglement.meyer_wallach(m, n_samples=None)
-            assert abs(float(mw) - float(z[f"call_{name}_mw"])) < 1e-10, name
-            if B_P >= 3:  # FCC on the given samples (n_samples=0), every correlation method
+            assert abs(float(mw) - float(z[f"call_{name}_mw"])) < tol, name
+            if fcc and B_P >= 3:  # FCC on the given samples (n_samples=0), every correlation method
                 from qml_essentials_b200.coefficients import FCC
 
                 for method in gac.FCC_METHODS:
                     got = float(FCC.get_fcc(m, n_samples=0, method=method))
-                    assert abs(got - float(z[f"call_{name}_fcc_{method}"])) < 1e-9, (name, method)
+                    assert abs(got - float(z[f"call_{name}_fcc_{method}"])) < 10 * tol, (name, method)
                 fp, fr = FCC.get_fourier_fingerprint(m, n_samples=0)
-                assert _close(np.asarray(fp), z[f"call_{name}_fp"], 1e-9), name
+                assert _close(np.asarray(fp), z[f"call_{name}_fp"], 10 * tol), name
                 assert _close(np.asarray(fr), z[f"call_{name}_fp_freqs"]), name
+
+
+def test_spectrum_fcc_and_meyer_wallach_callers_equal_the_reference():
+    """Host routes of the callers on the CPU program interpreter."""
+    _check_callers(1e-10)
+
+
+@pytest.mark.gpu
+def test_cuda_callers_equal_the_reference():
+    """`get_spectrum` (circuit kernels + device grid DFT with the trim / shift folded in) and
+    `meyer_wallach` (device purities) on the CUDA library against the reference's end-to-end
+    outputs.  The FCC's device-moments route is held to the host route by
+    `tests/test_gpu_analysis.py`; with the handful of samples of this fixture the two routes
+    may disagree on which near-dead coefficients count as zero-variance, so it is not
+    replayed here."""
+    _check_callers(1e-9, fcc=False)
